@@ -1,0 +1,181 @@
+/*
+ * ctc_b200.h -- C ABI of the B200-native CTC loss engine (libctc_b200.so).
+ *
+ * Drop-in boundary for jinserk/pytorch-asr's deepspeech_ctc training hot path:
+ * the loss object constructed at asr/models/trainer.py:152-154
+ * (nn.CTCLoss(blank=0, reduction='mean')), called at trainer.py:422 (and :508)
+ * as loss(ys_hat[T,N,V], ys, frame_lens, label_lens) and back-propagated at
+ * trainer.py:438 (:517).  The reference reaches its CTC arithmetic through
+ * torch's Python binding; its only in-tree native binding is the pybind11
+ * CppExtension asr/kaldi/src/latgen_lib.cc:278-281 built by
+ * asr/kaldi/setup.py:48-71, which is the packaging this library's torch shim
+ * (pytorch-asr_b200/csrc/ctc_binding.cc, module torch_asr._ctc_lib) mirrors.
+ *
+ * Conventions
+ *  - Plain C types only.  Every pointer marked "device" is CUDA device memory
+ *    on the current device; "host" is ordinary (ideally pinned) host memory.
+ *  - The compute entry points never allocate, free or synchronise: the caller
+ *    owns every buffer including the workspace, and all work is enqueued on
+ *    the stream passed in (a cudaStream_t, declared void* here so that the
+ *    header needs no CUDA include).  Stateless and re-entrant.
+ *  - Every function returns a ctc_b200_status (0 = ok).  No exceptions cross
+ *    this boundary.  The torch shim turns non-zero into RuntimeError, the way
+ *    KALDI_ERR surfaces from the latgen binding (latgen_lib.cc:83,88).
+ *  - Only fp32 activations: the reference casts to float before the loss
+ *    (trainer.py:416-417).
+ */
+#ifndef CTC_B200_H_
+#define CTC_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum ctc_b200_status {
+    CTC_B200_OK = 0,
+    CTC_B200_INVALID_ARGUMENT = 1,   /* null pointer, negative size, blank outside [0,V) ... */
+    CTC_B200_WORKSPACE_TOO_SMALL = 2,
+    CTC_B200_UNSUPPORTED = 3,        /* target longer than 4095 labels, vocabulary too large for smem */
+    CTC_B200_CUDA_ERROR = 4,         /* launch / runtime failure, see ctc_b200_last_cuda_error() */
+    CTC_B200_BAD_LABEL = 5,          /* device-side check: a label outside [0,V) */
+    CTC_B200_BAD_LENGTH = 6          /* device-side check: input length > T or target length > S_max */
+} ctc_b200_status;
+
+typedef enum ctc_b200_reduction {
+    CTC_B200_REDUCE_NONE = 0,
+    CTC_B200_REDUCE_MEAN = 1,        /* mean_b( nll_b / max(S_b,1) )  -- trainer.py:153 */
+    CTC_B200_REDUCE_SUM = 2
+} ctc_b200_reduction;
+
+/* Library ABI version (major*1000 + minor). */
+int ctc_b200_version(void);
+
+/* Static, never-freed description of a status code. */
+const char* ctc_b200_status_string(int status);
+
+/* cudaGetErrorString of the last CUDA failure this thread saw inside the library. */
+const char* ctc_b200_last_cuda_error(void);
+
+/*
+ * Launch geometry the engine picks for a problem size.  Informational (bench,
+ * DESIGN.md); also what ctc_b200_workspace_bytes is derived from.
+ */
+typedef struct ctc_b200_geometry {
+    int pairs_per_thread;      /* lattice (blank,label) cell pairs per thread */
+    int threads;               /* threads per CTA */
+    int chunk;                 /* frames per softmax/gradient chunk */
+    int row_stride;            /* floats per stored lattice row */
+    int smem_bytes;            /* dynamic shared memory per CTA */
+    size_t workspace_bytes;    /* for n_utt utterances */
+} ctc_b200_geometry;
+
+int ctc_b200_get_geometry(int T, int n_utt, int V, int S_max, ctc_b200_geometry* out);
+
+/* Bytes of device workspace ctc_b200_fwd_bwd_f32 needs for (T, N, V, S_max). */
+int ctc_b200_workspace_bytes(int T, int N, int V, int S_max, size_t* bytes);
+
+/*
+ * Fused log_softmax + CTC forward + gradient w.r.t. the logits.
+ * Replaces F.log_softmax -> nn.CTCLoss.forward -> backward
+ * (network.py:375, trainer.py:422, trainer.py:438).
+ *
+ *  acts         device [T,N,V] fp32 logits, contiguous (trainer.py:418)
+ *  targets      device int32, concatenated labels (dataloader.py:71)
+ *  tgt_offsets  device int32 [N], start of utterance b's labels in `targets`
+ *  in_lens      device int32 [N]  (frame_lens, dataloader.py:72)
+ *  tgt_lens     device int32 [N]  (label_lens, dataloader.py:73)
+ *  S_max        >= max_b tgt_lens[b]  (sizes the CTA; host knows it, the
+ *               reference keeps the lengths on the CPU)
+ *  nll          device fp32 [N] out: -log p(l_b|x_b); +inf if infeasible
+ *               (0 when zero_infinity)
+ *  grad         device fp32 [T,N,V] out or NULL (forward only):
+ *               grad_scale[b] * (softmax - occupancy), 0 for t >= in_lens[b];
+ *               NaN rows for infeasible utterances unless zero_infinity (as torch)
+ *  grad_scale   device fp32 [N] or NULL (=1): e.g. 1/(N*max(S_b,1)) for 'mean'
+ *  workspace    device, >= ctc_b200_workspace_bytes(...), 256-byte aligned
+ *  stream       cudaStream_t
+ */
+int ctc_b200_fwd_bwd_f32(const float* acts, const int32_t* targets, const int32_t* tgt_offsets,
+                         const int32_t* in_lens, const int32_t* tgt_lens, int T, int N, int V,
+                         int S_max, int blank, int zero_infinity, float* nll, float* grad,
+                         const float* grad_scale, void* workspace, size_t workspace_bytes,
+                         void* stream);
+
+/*
+ * Same, restricted to utterances [utt_begin, utt_begin + utt_count) of the
+ * batch (all array arguments still describe the whole batch).  The workspace
+ * only needs ctc_b200_workspace_bytes(T, utt_count, V, S_max).  Used to
+ * pipeline host->device copies of batch slices against compute.
+ */
+int ctc_b200_fwd_bwd_range_f32(const float* acts, const int32_t* targets,
+                               const int32_t* tgt_offsets, const int32_t* in_lens,
+                               const int32_t* tgt_lens, int T, int N, int V, int S_max,
+                               int blank, int zero_infinity, int utt_begin, int utt_count,
+                               float* nll, float* grad, const float* grad_scale,
+                               void* workspace, size_t workspace_bytes, void* stream);
+
+/*
+ * grad[t,b,:] *= scale[per_utt ? b : 0].  Applies autograd's grad_output
+ * (trainer.py:429 loss.mul_(0); AMP loss scale, trainer.py:435-436).  Factors
+ * equal to 1 are detected on the device and cost no memory traffic.
+ */
+int ctc_b200_scale_grad_f32(float* grad, const float* scale, int per_utt, int T, int N, int V,
+                            void* stream);
+
+/*
+ * out2[0] = sum_b nll_b / max(S_b,1) (MEAN) or sum_b nll_b (SUM); out2[1] = N.
+ * The pair is what a data-parallel job all-reduces; the
+ * reduced loss is out2[0]/out2[1] for MEAN, out2[0] for SUM, and is also
+ * written to loss[0] when `loss` is not NULL.  Single CTA, fixed summation
+ * order: bit-reproducible.
+ */
+int ctc_b200_reduce_loss_f32(const float* nll, const int32_t* tgt_lens, int N, int reduction,
+                             float* out2, float* loss, void* stream);
+
+/*
+ * Device-side validation result of the launches that used `workspace` since it
+ * was last cleared.  Synchronises `stream`.  Returns CTC_B200_OK,
+ * CTC_B200_BAD_LABEL or CTC_B200_BAD_LENGTH.  ctc_b200_clear_status resets it
+ * (asynchronously, on `stream`); a fresh workspace must be cleared once.
+ */
+int ctc_b200_check_status(const void* workspace, void* stream);
+int ctc_b200_clear_status(void* workspace, void* stream);
+
+/* ------------------------------------------------------------------------
+ * Host-buffer session: the same path for a caller that holds HOST tensors
+ * (the form bench.py's e2e figure and non-torch callers use).  A session owns
+ * its device buffers, pinned staging and streams; run() slices the batch,
+ * overlaps the host->device copy of slice k+1 with the kernel of slice k and
+ * returns the reduced loss (and optionally nll / gradient) to host memory.
+ * ------------------------------------------------------------------------ */
+typedef struct ctc_b200_session ctc_b200_session;
+
+int ctc_b200_session_create(int T, int N, int V, int S_max, int max_targets, int n_slices,
+                            ctc_b200_session** out);
+int ctc_b200_session_destroy(ctc_b200_session* s);
+
+/*
+ *  acts_host     host [T,N,V] fp32 (pinned for full speed)
+ *  targets_host  host int32 [n_targets] concatenated; in_lens/tgt_lens host int32 [N]
+ *  loss_host     host fp32 [1] out (reduced per `reduction`; for NONE: sum)
+ *  nll_host      host fp32 [N] out or NULL
+ *  grad_host     host fp32 [T,N,V] out or NULL (gradient stays on the device,
+ *                see ctc_b200_session_grad_device)
+ *  want_grad     compute the gradient (scaled for `reduction`) or forward only
+ */
+int ctc_b200_session_run_host_f32(ctc_b200_session* s, const float* acts_host,
+                                  const int32_t* targets_host, int n_targets,
+                                  const int32_t* in_lens_host, const int32_t* tgt_lens_host,
+                                  int blank, int reduction, int zero_infinity, int want_grad,
+                                  float* loss_host, float* nll_host, float* grad_host);
+float* ctc_b200_session_grad_device(ctc_b200_session* s);
+/* number of kernels the last run() launched */
+int ctc_b200_session_last_launches(const ctc_b200_session* s);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CTC_B200_H_ */

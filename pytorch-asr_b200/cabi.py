@@ -1,0 +1,206 @@
+"""ctypes view of the C ABI in include/ctc_b200.h (torch_asr/libctc_b200.so).
+
+This is the binding a non-torch caller would write; the GPU
+parity tests and bench.py drive the engine through it so that what is measured
+is the C ABI itself, with torch used only to own device memory and streams.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_PKG, "torch_asr", "libctc_b200.so")
+
+OK, INVALID_ARGUMENT, WORKSPACE_TOO_SMALL, UNSUPPORTED, CUDA_ERROR, BAD_LABEL, BAD_LENGTH = range(7)
+REDUCE_NONE, REDUCE_MEAN, REDUCE_SUM = 0, 1, 2
+
+# every symbol include/ctc_b200.h declares: name -> (restype, argtypes)
+_vp, _i, _sz = C.c_void_p, C.c_int, C.c_size_t
+
+
+class Geometry(C.Structure):
+    _fields_ = [("pairs_per_thread", _i), ("threads", _i), ("chunk", _i), ("row_stride", _i),
+                ("smem_bytes", _i), ("workspace_bytes", _sz)]
+
+
+SYMBOLS = {
+    "ctc_b200_version": (_i, []),
+    "ctc_b200_status_string": (C.c_char_p, [_i]),
+    "ctc_b200_last_cuda_error": (C.c_char_p, []),
+    "ctc_b200_get_geometry": (_i, [_i, _i, _i, _i, C.POINTER(Geometry)]),
+    "ctc_b200_workspace_bytes": (_i, [_i, _i, _i, _i, C.POINTER(_sz)]),
+    "ctc_b200_fwd_bwd_f32": (_i, [_vp] * 5 + [_i] * 6 + [_vp] * 4 + [_sz, _vp]),
+    "ctc_b200_fwd_bwd_range_f32": (_i, [_vp] * 5 + [_i] * 8 + [_vp] * 4 + [_sz, _vp]),
+    "ctc_b200_scale_grad_f32": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
+    "ctc_b200_reduce_loss_f32": (_i, [_vp, _vp, _i, _i, _vp, _vp, _vp]),
+    "ctc_b200_check_status": (_i, [_vp, _vp]),
+    "ctc_b200_clear_status": (_i, [_vp, _vp]),
+    "ctc_b200_session_create": (_i, [_i] * 6 + [C.POINTER(_vp)]),
+    "ctc_b200_session_destroy": (_i, [_vp]),
+    "ctc_b200_session_run_host_f32": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp]),
+    "ctc_b200_session_grad_device": (_vp, [_vp]),
+    "ctc_b200_session_last_launches": (_i, [_vp]),
+}
+
+_lib = None
+
+
+def load():
+    """dlopen the library and type every entry point.  Raises if it is not built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise OSError(f"{LIB_PATH} is not built; run `python pytorch-asr_b200/build.py`")
+        lib = C.CDLL(LIB_PATH)
+        for name, (res, args) in SYMBOLS.items():
+            fn = getattr(lib, name)
+            fn.restype, fn.argtypes = res, args
+        _lib = lib
+    return _lib
+
+
+class CtcB200Error(RuntimeError):
+    def __init__(self, status, where):
+        lib = load()
+        msg = lib.ctc_b200_status_string(status).decode()
+        if status == CUDA_ERROR:
+            msg += " (" + lib.ctc_b200_last_cuda_error().decode() + ")"
+        super().__init__(f"{where}: {msg}")
+        self.status = status
+
+
+def _check(rc, where):
+    if rc != OK:
+        raise CtcB200Error(rc, where)
+
+
+def geometry(T, N, V, S_max):
+    g = Geometry()
+    _check(load().ctc_b200_get_geometry(T, N, V, S_max, C.byref(g)), "ctc_b200_get_geometry")
+    return {k: getattr(g, k) for k, _ in Geometry._fields_}
+
+
+def workspace_bytes(T, N, V, S_max):
+    out = _sz(0)
+    _check(load().ctc_b200_workspace_bytes(T, N, V, S_max, C.byref(out)), "ctc_b200_workspace_bytes")
+    return out.value
+
+
+class DeviceProblem:
+    """Device-resident inputs/outputs for repeated calls through the C ABI.
+
+    Owns torch CUDA tensors only as memory; every compute call goes to
+    libctc_b200.so with raw pointers and the current stream."""
+
+    def __init__(self, acts, targets, in_lens, tgt_lens, blank=0, reduction="mean",
+                 zero_infinity=False, device="cuda"):
+        import torch
+        self.torch = torch
+        self.lib = load()
+        dev = torch.device(device)
+        self.T, self.N, self.V = acts.shape
+        tl = tgt_lens.to(torch.int64).cpu()
+        self.S_max = int(tl.max()) if self.N else 0
+        offs = torch.zeros(self.N, dtype=torch.int64)
+        if self.N > 1:
+            offs[1:] = torch.cumsum(tl, 0)[:-1]
+        self.blank, self.zero_infinity = int(blank), int(bool(zero_infinity))
+        self.reduction = {"none": REDUCE_NONE, "mean": REDUCE_MEAN, "sum": REDUCE_SUM}[reduction]
+        self.acts = acts.to(dev, torch.float32).contiguous()
+        tg = targets.reshape(-1).to(torch.int32)
+        self.targets = (tg if tg.numel() else torch.zeros(1, dtype=torch.int32)).to(dev)
+        self.tgt_off = offs.to(torch.int32).to(dev)
+        self.in_lens = in_lens.to(torch.int32).to(dev)
+        self.tgt_lens = tgt_lens.to(torch.int32).to(dev)
+        if reduction == "mean":
+            sc = 1.0 / (self.N * tl.clamp_min(1).to(torch.float32))
+        else:
+            sc = torch.ones(self.N, dtype=torch.float32)
+        self.scale = sc.to(dev)
+        self.nll = torch.empty(self.N, dtype=torch.float32, device=dev)
+        self.grad = torch.empty_like(self.acts)
+        self.out2 = torch.empty(2, dtype=torch.float32, device=dev)
+        self.loss = torch.empty((), dtype=torch.float32, device=dev)
+        self.ws_bytes = workspace_bytes(self.T, self.N, self.V, self.S_max)
+        self.ws = torch.empty(self.ws_bytes, dtype=torch.uint8, device=dev)
+        assert self.ws.data_ptr() % 256 == 0
+        self.clear_status()
+
+    def _stream(self):
+        return self.torch.cuda.current_stream().cuda_stream
+
+    def clear_status(self):
+        _check(self.lib.ctc_b200_clear_status(self.ws.data_ptr(), self._stream()), "clear_status")
+
+    def check_status(self):
+        _check(self.lib.ctc_b200_check_status(self.ws.data_ptr(), self._stream()), "check_status")
+
+    def run(self, want_grad=True, reduce=True):
+        """One pass of the hot path: 1 fused launch (+1 tiny reduction launch)."""
+        st = self._stream()
+        _check(self.lib.ctc_b200_fwd_bwd_f32(
+            self.acts.data_ptr(), self.targets.data_ptr(), self.tgt_off.data_ptr(),
+            self.in_lens.data_ptr(), self.tgt_lens.data_ptr(), self.T, self.N, self.V, self.S_max,
+            self.blank, self.zero_infinity, self.nll.data_ptr(),
+            self.grad.data_ptr() if want_grad else None, self.scale.data_ptr(),
+            self.ws.data_ptr(), self.ws_bytes, st), "ctc_b200_fwd_bwd_f32")
+        n = 1
+        if reduce:
+            _check(self.lib.ctc_b200_reduce_loss_f32(
+                self.nll.data_ptr(), self.tgt_lens.data_ptr(), self.N,
+                REDUCE_MEAN if self.reduction == REDUCE_MEAN else REDUCE_SUM,
+                self.out2.data_ptr(), self.loss.data_ptr(), st), "ctc_b200_reduce_loss_f32")
+            n += 1
+        return n
+
+    def scale_grad(self, scale_tensor, per_utt=False):
+        _check(self.lib.ctc_b200_scale_grad_f32(self.grad.data_ptr(), scale_tensor.data_ptr(),
+                                                1 if per_utt else 0, self.T, self.N, self.V,
+                                                self._stream()), "ctc_b200_scale_grad_f32")
+        return 1
+
+
+class HostSession:
+    """ctc_b200_session_*: host buffers in, loss (and nll / grad) out."""
+
+    def __init__(self, T, N, V, S_max, max_targets, n_slices=4):
+        self.lib = load()
+        self.h = _vp()
+        _check(self.lib.ctc_b200_session_create(T, N, V, S_max, max_targets, n_slices,
+                                                C.byref(self.h)), "ctc_b200_session_create")
+        self.T, self.N, self.V = T, N, V
+
+    def run(self, acts, targets, in_lens, tgt_lens, blank=0, reduction="mean",
+            zero_infinity=False, want_grad=True, nll_out=None, grad_out=None):
+        """All arguments are CPU torch tensors (acts ideally pinned).  Returns the loss (float)."""
+        import torch
+        red = {"none": REDUCE_NONE, "mean": REDUCE_MEAN, "sum": REDUCE_SUM}[reduction]
+        loss = C.c_float(0.0)
+        assert acts.dtype == torch.float32 and acts.is_contiguous() and not acts.is_cuda
+        assert targets.dtype == torch.int32 and in_lens.dtype == torch.int32 and tgt_lens.dtype == torch.int32
+        rc = self.lib.ctc_b200_session_run_host_f32(
+            self.h, acts.data_ptr(), targets.data_ptr() if targets.numel() else None,
+            int(targets.numel()), in_lens.data_ptr(), tgt_lens.data_ptr(), int(blank), red,
+            int(bool(zero_infinity)), int(bool(want_grad)), C.addressof(loss),
+            nll_out.data_ptr() if nll_out is not None else None,
+            grad_out.data_ptr() if grad_out is not None else None)
+        _check(rc, "ctc_b200_session_run_host_f32")
+        return loss.value
+
+    def last_launches(self):
+        return self.lib.ctc_b200_session_last_launches(self.h)
+
+    def grad_device_ptr(self):
+        return self.lib.ctc_b200_session_grad_device(self.h)
+
+    def close(self):
+        if self.h:
+            self.lib.ctc_b200_session_destroy(self.h)
+            self.h = _vp()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -1,0 +1,400 @@
+// ctc_abi.cu -- the extern "C" boundary declared in include/ctc_b200.h.
+//
+// Host-side launch logic for the kernels in ctc_kernels.cuh plus the
+// host-buffer session.  No torch types here: this file builds into
+// libctc_b200.so with nvcc alone and is what a non-Python caller links.
+#include "ctc_kernels.cuh"
+#include "../../include/ctc_b200.h"
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <vector>
+
+using namespace ctcb200;
+
+namespace {
+
+constexpr int kHeaderBytes = 256;          // workspace header: device status word
+constexpr int kMaxSmemBytes = 200 * 1024;  // leave room under the 227 KB per-CTA limit
+constexpr int kMinThreads = 128;
+
+thread_local cudaError_t g_last_cuda = cudaSuccess;
+
+inline int cuda_fail(cudaError_t e) {
+    g_last_cuda = e;
+    return CTC_B200_CUDA_ERROR;
+}
+#define CTC_CUDA(call)                                  \
+    do {                                                \
+        cudaError_t e__ = (call);                       \
+        if (e__ != cudaSuccess) return cuda_fail(e__);  \
+    } while (0)
+
+struct Geometry {
+    int P, NT, W, NP, chunk, RS, smem;
+    size_t lat_utt_stride;  // floats
+};
+
+int pick_geometry(int T, int V, int S_max, Geometry* g) {
+    if (T < 0 || V < 1 || S_max < 0) return CTC_B200_INVALID_ARGUMENT;
+    const int pairs = S_max + 1;
+    int P = 1;
+    while (P <= 4 && (pairs + P - 1) / P > 1024) P <<= 1;
+    if (P > 4) return CTC_B200_UNSUPPORTED;  // targets longer than 4095 labels
+    int NT = ((pairs + P - 1) / P + 31) / 32 * 32;
+    NT = std::max(NT, kMinThreads);
+    g->P = P;
+    g->NT = NT;
+    g->W = NT / 32;
+    g->NP = NT * P;
+    g->RS = 2 * g->NP + (g->W + 3) / 4 * 4;
+    int chunk = kMaxChunk;
+    for (;;) {
+        SmemLayout lay(g->NP, g->W, V, chunk, g->RS);
+        if (lay.total <= kMaxSmemBytes) {
+            g->smem = lay.total;
+            break;
+        }
+        if (chunk == 1) return CTC_B200_UNSUPPORTED;
+        chunk >>= 1;
+    }
+    g->chunk = chunk;
+    g->lat_utt_stride = (size_t)std::max(T, 1) * (size_t)g->RS;
+    return CTC_B200_OK;
+}
+
+template <int P>
+int launch_fused_p(const FusedParams& prm, const Geometry& g, int n_utt, cudaStream_t st) {
+    static int configured_smem = -1;  // per-process, per-instantiation high-water mark
+    if (g.smem > configured_smem) {
+        CTC_CUDA(cudaFuncSetAttribute(ctc_fused_kernel<P>,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, g.smem));
+        configured_smem = g.smem;
+    }
+    ctc_fused_kernel<P><<<dim3(2 * n_utt), dim3(g.NT), g.smem, st>>>(prm);
+    CTC_CUDA(cudaGetLastError());
+    return CTC_B200_OK;
+}
+
+int launch_fused(const float* acts, const int32_t* targets, const int32_t* tgt_offsets,
+                 const int32_t* in_lens, const int32_t* tgt_lens, int T, int N, int V, int S_max,
+                 int blank, int zero_infinity, int utt_begin, int utt_count, float* nll,
+                 float* grad, const float* grad_scale, float* lattice, size_t lattice_bytes,
+                 int* status_word, cudaStream_t st) {
+    if (!acts || !targets || !tgt_offsets || !in_lens || !tgt_lens || !nll || !status_word)
+        return CTC_B200_INVALID_ARGUMENT;
+    if (T < 0 || N < 0 || V < 1 || blank < 0 || blank >= V || utt_begin < 0 || utt_count < 0 ||
+        utt_begin + utt_count > N)
+        return CTC_B200_INVALID_ARGUMENT;
+    if (utt_count == 0) return CTC_B200_OK;
+    Geometry g;
+    int rc = pick_geometry(T, V, S_max, &g);
+    if (rc != CTC_B200_OK) return rc;
+    if (!lattice || lattice_bytes < g.lat_utt_stride * sizeof(float) * (size_t)utt_count)
+        return CTC_B200_WORKSPACE_TOO_SMALL;
+    if ((reinterpret_cast<uintptr_t>(lattice) & 15) || (reinterpret_cast<uintptr_t>(acts) & 15) ||
+        (grad && (reinterpret_cast<uintptr_t>(grad) & 15)))
+        return CTC_B200_INVALID_ARGUMENT;
+
+    FusedParams prm;
+    prm.acts = acts;
+    prm.targets = targets;
+    prm.tgt_off = tgt_offsets;
+    prm.in_lens = in_lens;
+    prm.tgt_lens = tgt_lens;
+    prm.grad_scale = grad_scale;
+    prm.nll = nll;
+    prm.grad = grad;
+    prm.lattice = lattice;
+    prm.status = status_word;
+    prm.lat_utt_stride = (long long)g.lat_utt_stride;
+    prm.T = T;
+    prm.N = N;
+    prm.V = V;
+    prm.blank = blank;
+    prm.zero_infinity = zero_infinity;
+    prm.utt_begin = utt_begin;
+    prm.row_stride = g.RS;
+    prm.chunk = g.chunk;
+    switch (g.P) {
+        case 1: return launch_fused_p<1>(prm, g, utt_count, st);
+        case 2: return launch_fused_p<2>(prm, g, utt_count, st);
+        case 4: return launch_fused_p<4>(prm, g, utt_count, st);
+    }
+    return CTC_B200_UNSUPPORTED;
+}
+
+int status_from_bits(int bits) {
+    if (bits & kStatusBadLabel) return CTC_B200_BAD_LABEL;
+    if (bits & kStatusBadLength) return CTC_B200_BAD_LENGTH;
+    return CTC_B200_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int ctc_b200_version(void) { return 1000; }
+
+const char* ctc_b200_status_string(int status) {
+    switch (status) {
+        case CTC_B200_OK: return "ok";
+        case CTC_B200_INVALID_ARGUMENT: return "invalid argument";
+        case CTC_B200_WORKSPACE_TOO_SMALL: return "workspace too small";
+        case CTC_B200_UNSUPPORTED: return "unsupported problem size";
+        case CTC_B200_CUDA_ERROR: return "CUDA error";
+        case CTC_B200_BAD_LABEL: return "target label outside [0, V)";
+        case CTC_B200_BAD_LENGTH: return "input length > T or target length > S_max";
+    }
+    return "unknown status";
+}
+
+const char* ctc_b200_last_cuda_error(void) { return cudaGetErrorString(g_last_cuda); }
+
+int ctc_b200_get_geometry(int T, int n_utt, int V, int S_max, ctc_b200_geometry* out) {
+    if (!out || n_utt < 0) return CTC_B200_INVALID_ARGUMENT;
+    Geometry g;
+    int rc = pick_geometry(T, V, S_max, &g);
+    if (rc != CTC_B200_OK) return rc;
+    out->pairs_per_thread = g.P;
+    out->threads = g.NT;
+    out->chunk = g.chunk;
+    out->row_stride = g.RS;
+    out->smem_bytes = g.smem;
+    out->workspace_bytes = kHeaderBytes + g.lat_utt_stride * sizeof(float) * (size_t)n_utt;
+    return CTC_B200_OK;
+}
+
+int ctc_b200_workspace_bytes(int T, int N, int V, int S_max, size_t* bytes) {
+    if (!bytes) return CTC_B200_INVALID_ARGUMENT;
+    ctc_b200_geometry g;
+    int rc = ctc_b200_get_geometry(T, N, V, S_max, &g);
+    if (rc == CTC_B200_OK) *bytes = g.workspace_bytes;
+    return rc;
+}
+
+int ctc_b200_fwd_bwd_range_f32(const float* acts, const int32_t* targets,
+                               const int32_t* tgt_offsets, const int32_t* in_lens,
+                               const int32_t* tgt_lens, int T, int N, int V, int S_max,
+                               int blank, int zero_infinity, int utt_begin, int utt_count,
+                               float* nll, float* grad, const float* grad_scale,
+                               void* workspace, size_t workspace_bytes, void* stream) {
+    if (!workspace || workspace_bytes < (size_t)kHeaderBytes) return CTC_B200_WORKSPACE_TOO_SMALL;
+    if (reinterpret_cast<uintptr_t>(workspace) & 255) return CTC_B200_INVALID_ARGUMENT;
+    char* ws = static_cast<char*>(workspace);
+    return launch_fused(acts, targets, tgt_offsets, in_lens, tgt_lens, T, N, V, S_max, blank,
+                        zero_infinity, utt_begin, utt_count, nll, grad, grad_scale,
+                        reinterpret_cast<float*>(ws + kHeaderBytes), workspace_bytes - kHeaderBytes,
+                        reinterpret_cast<int*>(ws), static_cast<cudaStream_t>(stream));
+}
+
+int ctc_b200_fwd_bwd_f32(const float* acts, const int32_t* targets, const int32_t* tgt_offsets,
+                         const int32_t* in_lens, const int32_t* tgt_lens, int T, int N, int V,
+                         int S_max, int blank, int zero_infinity, float* nll, float* grad,
+                         const float* grad_scale, void* workspace, size_t workspace_bytes,
+                         void* stream) {
+    return ctc_b200_fwd_bwd_range_f32(acts, targets, tgt_offsets, in_lens, tgt_lens, T, N, V,
+                                      S_max, blank, zero_infinity, 0, N, nll, grad, grad_scale,
+                                      workspace, workspace_bytes, stream);
+}
+
+int ctc_b200_scale_grad_f32(float* grad, const float* scale, int per_utt, int T, int N, int V,
+                            void* stream) {
+    if (!grad || !scale || T < 0 || N < 0 || V < 1) return CTC_B200_INVALID_ARGUMENT;
+    if (T == 0 || N == 0) return CTC_B200_OK;
+    const int threads = 256;
+    const size_t per_utt_elems = (size_t)T * V;
+    int gy = (int)std::min<size_t>((per_utt_elems + threads * 8 - 1) / (threads * 8), 64);
+    gy = std::max(gy, 1);
+    ctc_scale_grad_kernel<<<dim3(N, gy), threads, 0, static_cast<cudaStream_t>(stream)>>>(
+        grad, scale, per_utt, T, N, V);
+    CTC_CUDA(cudaGetLastError());
+    return CTC_B200_OK;
+}
+
+int ctc_b200_reduce_loss_f32(const float* nll, const int32_t* tgt_lens, int N, int reduction,
+                             float* out2, float* loss, void* stream) {
+    if (!nll || !tgt_lens || !out2 || N < 0) return CTC_B200_INVALID_ARGUMENT;
+    ctc_reduce_loss_kernel<<<1, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        nll, tgt_lens, N, reduction == CTC_B200_REDUCE_MEAN ? 1 : 2, out2, loss);
+    CTC_CUDA(cudaGetLastError());
+    return CTC_B200_OK;
+}
+
+int ctc_b200_check_status(const void* workspace, void* stream) {
+    if (!workspace) return CTC_B200_INVALID_ARGUMENT;
+    int bits = 0;
+    CTC_CUDA(cudaMemcpyAsync(&bits, workspace, sizeof(int), cudaMemcpyDeviceToHost,
+                             static_cast<cudaStream_t>(stream)));
+    CTC_CUDA(cudaStreamSynchronize(static_cast<cudaStream_t>(stream)));
+    return status_from_bits(bits);
+}
+
+int ctc_b200_clear_status(void* workspace, void* stream) {
+    if (!workspace) return CTC_B200_INVALID_ARGUMENT;
+    CTC_CUDA(cudaMemsetAsync(workspace, 0, kHeaderBytes, static_cast<cudaStream_t>(stream)));
+    return CTC_B200_OK;
+}
+
+// ---------------------------------------------------------------------------
+// Host-buffer session
+// ---------------------------------------------------------------------------
+struct ctc_b200_session {
+    int T, N, V, S_max, max_targets, n_slices;
+    Geometry geo;
+    float* d_acts = nullptr;
+    float* d_grad = nullptr;
+    float* d_lattice = nullptr;
+    size_t lattice_bytes = 0;
+    char* d_small = nullptr;   // [targets | tgt_off | in_lens | tgt_lens | scale]
+    char* h_small = nullptr;   // pinned mirror
+    size_t small_bytes = 0;
+    char* d_res = nullptr;     // [out2 (2 f32) | status (i32) | pad | nll (N f32)]
+    char* h_res = nullptr;     // pinned mirror
+    size_t res_bytes = 0;
+    cudaStream_t s_copy = nullptr, s_comp = nullptr;
+    std::vector<cudaEvent_t> ev;
+    int last_launches = 0;
+};
+
+static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+int ctc_b200_session_create(int T, int N, int V, int S_max, int max_targets, int n_slices,
+                            ctc_b200_session** out) {
+    if (!out || T < 1 || N < 1 || V < 1 || S_max < 0 || max_targets < 0)
+        return CTC_B200_INVALID_ARGUMENT;
+    ctc_b200_session* s = new (std::nothrow) ctc_b200_session();
+    if (!s) return CTC_B200_INVALID_ARGUMENT;
+    s->T = T; s->N = N; s->V = V; s->S_max = S_max; s->max_targets = max_targets;
+    s->n_slices = std::max(1, std::min(n_slices, N));
+    int rc = pick_geometry(T, V, S_max, &s->geo);
+    if (rc != CTC_B200_OK) { delete s; return rc; }
+    const size_t nact = (size_t)T * N * V * sizeof(float);
+    s->lattice_bytes = s->geo.lat_utt_stride * sizeof(float) * (size_t)N;
+    s->small_bytes = align_up((size_t)std::max(max_targets, 1) * 4, 16) + 4 * align_up((size_t)N * 4, 16);
+    s->res_bytes = 16 + (size_t)N * 4;
+    cudaError_t e = cudaSuccess;
+    auto ok = [&](cudaError_t x) { if (e == cudaSuccess) e = x; };
+    ok(cudaMalloc(&s->d_acts, nact));
+    ok(cudaMalloc(&s->d_grad, nact));
+    ok(cudaMalloc(&s->d_lattice, s->lattice_bytes));
+    ok(cudaMalloc(&s->d_small, s->small_bytes));
+    ok(cudaMalloc(&s->d_res, s->res_bytes));
+    ok(cudaMallocHost(&s->h_small, s->small_bytes));
+    ok(cudaMallocHost(&s->h_res, s->res_bytes));
+    ok(cudaStreamCreateWithFlags(&s->s_copy, cudaStreamNonBlocking));
+    ok(cudaStreamCreateWithFlags(&s->s_comp, cudaStreamNonBlocking));
+    s->ev.resize(s->n_slices + 1, nullptr);
+    for (auto& ev : s->ev) ok(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    if (e != cudaSuccess) {
+        ctc_b200_session_destroy(s);
+        return cuda_fail(e);
+    }
+    *out = s;
+    return CTC_B200_OK;
+}
+
+int ctc_b200_session_destroy(ctc_b200_session* s) {
+    if (!s) return CTC_B200_OK;
+    for (auto ev : s->ev) if (ev) cudaEventDestroy(ev);
+    if (s->s_copy) cudaStreamDestroy(s->s_copy);
+    if (s->s_comp) cudaStreamDestroy(s->s_comp);
+    cudaFree(s->d_acts); cudaFree(s->d_grad); cudaFree(s->d_lattice);
+    cudaFree(s->d_small); cudaFree(s->d_res);
+    if (s->h_small) cudaFreeHost(s->h_small);
+    if (s->h_res) cudaFreeHost(s->h_res);
+    delete s;
+    return CTC_B200_OK;
+}
+
+float* ctc_b200_session_grad_device(ctc_b200_session* s) { return s ? s->d_grad : nullptr; }
+int ctc_b200_session_last_launches(const ctc_b200_session* s) { return s ? s->last_launches : 0; }
+
+int ctc_b200_session_run_host_f32(ctc_b200_session* s, const float* acts_host,
+                                  const int32_t* targets_host, int n_targets,
+                                  const int32_t* in_lens_host, const int32_t* tgt_lens_host,
+                                  int blank, int reduction, int zero_infinity, int want_grad,
+                                  float* loss_host, float* nll_host, float* grad_host) {
+    if (!s || !acts_host || (!targets_host && n_targets > 0) || !in_lens_host || !tgt_lens_host ||
+        !loss_host || n_targets < 0 || n_targets > s->max_targets)
+        return CTC_B200_INVALID_ARGUMENT;
+    const int T = s->T, N = s->N, V = s->V;
+    // ---- host prep into pinned staging: offsets, lengths, per-utterance scale ---
+    const size_t o_tg = 0;
+    const size_t o_off = align_up((size_t)std::max(s->max_targets, 1) * 4, 16);
+    const size_t o_il = o_off + align_up((size_t)N * 4, 16);
+    const size_t o_tl = o_il + align_up((size_t)N * 4, 16);
+    const size_t o_sc = o_tl + align_up((size_t)N * 4, 16);
+    int32_t* h_tg = reinterpret_cast<int32_t*>(s->h_small + o_tg);
+    int32_t* h_off = reinterpret_cast<int32_t*>(s->h_small + o_off);
+    int32_t* h_il = reinterpret_cast<int32_t*>(s->h_small + o_il);
+    int32_t* h_tl = reinterpret_cast<int32_t*>(s->h_small + o_tl);
+    float* h_sc = reinterpret_cast<float*>(s->h_small + o_sc);
+    long long acc = 0;
+    for (int b = 0; b < N; ++b) {
+        const int S = tgt_lens_host[b], Tb = in_lens_host[b];
+        if (S < 0 || S > s->S_max || Tb < 0 || Tb > T) return CTC_B200_BAD_LENGTH;
+        h_off[b] = (int32_t)acc;
+        acc += S;
+        h_il[b] = Tb;
+        h_tl[b] = S;
+        h_sc[b] = (reduction == CTC_B200_REDUCE_MEAN) ? 1.0f / ((float)N * (float)std::max(S, 1)) : 1.0f;
+    }
+    if (acc != n_targets) return CTC_B200_INVALID_ARGUMENT;
+    if (n_targets) std::memcpy(h_tg, targets_host, (size_t)n_targets * 4);
+    CTC_CUDA(cudaMemcpyAsync(s->d_small, s->h_small, s->small_bytes, cudaMemcpyHostToDevice, s->s_copy));
+    CTC_CUDA(cudaMemsetAsync(s->d_res, 0, 16, s->s_copy));
+    CTC_CUDA(cudaEventRecord(s->ev[s->n_slices], s->s_copy));
+    CTC_CUDA(cudaStreamWaitEvent(s->s_comp, s->ev[s->n_slices], 0));
+
+    const int32_t* d_tg = reinterpret_cast<const int32_t*>(s->d_small + o_tg);
+    const int32_t* d_off = reinterpret_cast<const int32_t*>(s->d_small + o_off);
+    const int32_t* d_il = reinterpret_cast<const int32_t*>(s->d_small + o_il);
+    const int32_t* d_tl = reinterpret_cast<const int32_t*>(s->d_small + o_tl);
+    const float* d_sc = reinterpret_cast<const float*>(s->d_small + o_sc);
+    float* d_out2 = reinterpret_cast<float*>(s->d_res);
+    int* d_status = reinterpret_cast<int*>(s->d_res + 8);
+    float* d_nll = reinterpret_cast<float*>(s->d_res + 16);
+
+    // ---- slice pipeline: H2D of slice k+1 overlaps the kernel of slice k -------
+    int launches = 0;
+    const size_t pitch = (size_t)N * V * sizeof(float);
+    for (int k = 0; k < s->n_slices; ++k) {
+        const int b0 = (int)((long long)N * k / s->n_slices);
+        const int b1 = (int)((long long)N * (k + 1) / s->n_slices);
+        if (b1 == b0) continue;
+        CTC_CUDA(cudaMemcpy2DAsync(s->d_acts + (size_t)b0 * V, pitch, acts_host + (size_t)b0 * V,
+                                   pitch, (size_t)(b1 - b0) * V * sizeof(float), (size_t)T,
+                                   cudaMemcpyHostToDevice, s->s_copy));
+        CTC_CUDA(cudaEventRecord(s->ev[k], s->s_copy));
+        CTC_CUDA(cudaStreamWaitEvent(s->s_comp, s->ev[k], 0));
+        int rc = launch_fused(s->d_acts, d_tg, d_off, d_il, d_tl, T, N, V, s->S_max, blank,
+                              zero_infinity, b0, b1 - b0, d_nll, want_grad ? s->d_grad : nullptr,
+                              d_sc, s->d_lattice + (size_t)b0 * s->geo.lat_utt_stride,
+                              s->lattice_bytes - (size_t)b0 * s->geo.lat_utt_stride * sizeof(float),
+                              d_status, s->s_comp);
+        if (rc != CTC_B200_OK) return rc;
+        ++launches;
+    }
+    ctc_reduce_loss_kernel<<<1, 256, 0, s->s_comp>>>(
+        d_nll, d_tl, N, reduction == CTC_B200_REDUCE_MEAN ? 1 : 2, d_out2, nullptr);
+    CTC_CUDA(cudaGetLastError());
+    ++launches;
+    CTC_CUDA(cudaMemcpyAsync(s->h_res, s->d_res, nll_host ? s->res_bytes : 16,
+                             cudaMemcpyDeviceToHost, s->s_comp));
+    if (grad_host && want_grad)
+        CTC_CUDA(cudaMemcpyAsync(grad_host, s->d_grad, (size_t)T * N * V * sizeof(float),
+                                 cudaMemcpyDeviceToHost, s->s_comp));
+    CTC_CUDA(cudaStreamSynchronize(s->s_comp));
+    s->last_launches = launches;
+
+    const float* h_out2 = reinterpret_cast<const float*>(s->h_res);
+    const int bits = *reinterpret_cast<const int*>(s->h_res + 8);
+    *loss_host = (reduction == CTC_B200_REDUCE_MEAN) ? h_out2[0] / (float)N : h_out2[0];
+    if (nll_host) std::memcpy(nll_host, s->h_res + 16, (size_t)N * 4);
+    return status_from_bits(bits);
+}
+
+}  // extern "C"

@@ -1,0 +1,80 @@
+"""CPU tests of the boundary: the C-ABI library loads without a GPU, exports every
+symbol include/ctc_b200.h declares, and its host-only entry points behave.  No
+compute call is made here (there is no CPU fallback to call)."""
+import ctypes as C
+import os
+import re
+
+import pytest
+import torch
+
+from pytorch_asr_b200 import cabi
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    src = open(os.path.join(ROOT, "include", "ctc_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    names = re.findall(r"\b(ctc_b200_[a-z0-9_]+)\s*\(", src)
+    return sorted(set(names))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = C.CDLL(cabi.LIB_PATH)
+    declared = _declared_symbols()
+    assert len(declared) >= 15
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in include/ctc_b200.h but not exported"
+    # and the ctypes binding covers exactly the declared set
+    assert sorted(cabi.SYMBOLS) == declared
+
+
+def test_version_and_status_strings():
+    lib = cabi.load()
+    assert lib.ctc_b200_version() >= 1000
+    seen = {lib.ctc_b200_status_string(i).decode() for i in range(7)}
+    assert len(seen) == 7 and "ok" in seen
+    assert lib.ctc_b200_status_string(99).decode() == "unknown status"
+
+
+def test_geometry_and_workspace():
+    g = cabi.geometry(1000, 256, 48, 240)          # BASELINE config 2
+    assert g["pairs_per_thread"] == 1 and g["threads"] == 256 and g["threads"] % 32 == 0
+    assert g["row_stride"] % 4 == 0 and g["smem_bytes"] <= 227 * 1024
+    assert g["workspace_bytes"] == 256 + 256 * 1000 * g["row_stride"] * 4
+    assert cabi.workspace_bytes(1000, 256, 48, 240) == g["workspace_bytes"]
+    g3 = cabi.geometry(4000, 64, 48, 800)          # BASELINE config 3
+    assert g3["threads"] == 832 and g3["smem_bytes"] <= 227 * 1024
+    assert cabi.geometry(100, 1, 48, 1500)["pairs_per_thread"] == 2
+    assert cabi.geometry(100, 1, 48, 4095)["pairs_per_thread"] == 4
+    with pytest.raises(cabi.CtcB200Error) as e:
+        cabi.geometry(100, 1, 48, 4096)
+    assert e.value.status == cabi.UNSUPPORTED
+    with pytest.raises(cabi.CtcB200Error) as e:
+        cabi.geometry(100, 1, 0, 10)
+    assert e.value.status == cabi.INVALID_ARGUMENT
+
+
+def test_argument_validation_needs_no_device():
+    lib = cabi.load()
+    # null pointers are rejected before any CUDA call
+    rc = lib.ctc_b200_fwd_bwd_f32(None, None, None, None, None, 10, 2, 8, 3, 0, 0, None, None,
+                                  None, None, 0, None)
+    assert rc in (cabi.INVALID_ARGUMENT, cabi.WORKSPACE_TOO_SMALL)
+    assert lib.ctc_b200_scale_grad_f32(None, None, 0, 1, 1, 1, None) == cabi.INVALID_ARGUMENT
+    assert lib.ctc_b200_reduce_loss_f32(None, None, 1, 1, None, None, None) == cabi.INVALID_ARGUMENT
+    assert lib.ctc_b200_check_status(None, None) == cabi.INVALID_ARGUMENT
+
+
+def test_module_fails_loudly_without_cuda():
+    from pytorch_asr_b200 import CTCLoss
+    from pytorch_asr_b200.ctc import load_native
+    assert load_native().version() >= 1000     # the torch shim imports on a CPU box
+    crit = CTCLoss(blank=0, reduction="mean")
+    x = torch.randn(5, 2, 4)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        crit(x, torch.tensor([1, 2], dtype=torch.int32), torch.tensor([5, 5], dtype=torch.int32),
+             torch.tensor([1, 1], dtype=torch.int32))
+    with pytest.raises(ValueError):
+        CTCLoss(reduction="bogus")
