@@ -64,6 +64,9 @@ const char* ctc_b200_last_cuda_error(void);
  * DESIGN.md); also what ctc_b200_workspace_bytes is derived from.
  */
 typedef struct ctc_b200_geometry {
+    int kernel;                /* 1: warp-specialised kernel, 0: generic kernel */
+    int rec_warps;             /* warps per CTA running the lattice recursion */
+    int grad_warps;            /* helper warps per CTA: TMA producer, softmax, gradient rows (0: generic kernel) */
     int pairs_per_thread;      /* lattice (blank,label) cell pairs per thread */
     int threads;               /* threads per CTA */
     int chunk;                 /* frames per softmax/gradient chunk */

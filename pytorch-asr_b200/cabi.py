@@ -10,7 +10,7 @@ import ctypes as C
 import os
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG, "torch_asr", "libctc_b200.so")
+LIB_PATH = os.environ.get("CTC_B200_LIB") or os.path.join(_PKG, "torch_asr", "libctc_b200.so")
 
 OK, INVALID_ARGUMENT, WORKSPACE_TOO_SMALL, UNSUPPORTED, CUDA_ERROR, BAD_LABEL, BAD_LENGTH = range(7)
 REDUCE_NONE, REDUCE_MEAN, REDUCE_SUM = 0, 1, 2
@@ -20,7 +20,7 @@ _vp, _i, _sz = C.c_void_p, C.c_int, C.c_size_t
 
 
 class Geometry(C.Structure):
-    _fields_ = [("pairs_per_thread", _i), ("threads", _i), ("chunk", _i), ("row_stride", _i),
+    _fields_ = [("kernel", _i), ("rec_warps", _i), ("grad_warps", _i), ("pairs_per_thread", _i), ("threads", _i), ("chunk", _i), ("row_stride", _i),
                 ("smem_bytes", _i), ("workspace_bytes", _sz)]
 
 

@@ -4,10 +4,12 @@
 // host-buffer session.  No torch types here: this file builds into
 // libctc_b200.so with nvcc alone and is what a non-Python caller links.
 #include "ctc_kernels.cuh"
+#include "ctc_pipe.cuh"
 #include "../../include/ctc_b200.h"
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <vector>
@@ -18,7 +20,8 @@ namespace {
 
 constexpr int kHeaderBytes = 256;          // workspace header: device status word
 constexpr int kMaxSmemBytes = 200 * 1024;  // leave room under the 227 KB per-CTA limit
-constexpr int kMinThreads = 128;
+constexpr int kMinThreads = 32;
+constexpr int kNumSmsHint = 148;           // B200; only shapes the shared-memory budget heuristic
 
 thread_local cudaError_t g_last_cuda = cudaSuccess;
 
@@ -33,21 +36,31 @@ inline int cuda_fail(cudaError_t e) {
     } while (0)
 
 struct Geometry {
+    int pipe;       // 1: warp-specialised kernel (ctc_pipe.cuh), 0: generic kernel (ctc_kernels.cuh)
     int P, NT, W, NP, chunk, RS, smem;
+    int R, G, D;    // pipe only: recursion / gradient warps, fetch distance in chunks
     size_t lat_utt_stride;  // floats
 };
 
-int pick_geometry(int T, int V, int S_max, Geometry* g) {
-    if (T < 0 || V < 1 || S_max < 0) return CTC_B200_INVALID_ARGUMENT;
-    const int pairs = S_max + 1;
-    int P = 1;
-    while (P <= 4 && (pairs + P - 1) / P > 1024) P <<= 1;
-    if (P > 4) return CTC_B200_UNSUPPORTED;  // targets longer than 4095 labels
+int env_int(const char* name, int dflt) {
+    const char* e = std::getenv(name);
+    return e ? std::atoi(e) : dflt;
+}
+
+// Generic kernel: every warp does recursion + its share of softmax / gradient rows.
+int pick_generic(int T, int V, int pairs, Geometry* g) {
+    int P = pairs > 1024 ? (pairs > 2048 ? 4 : 2) : 1;
+    const int q = env_int("CTC_B200_PAIRS", 0);  // tuning override (1, 2 or 4)
+    if ((q == 1 || q == 2 || q == 4) && (pairs + q - 1) / q <= 1024) P = q;
     int NT = ((pairs + P - 1) / P + 31) / 32 * 32;
-    NT = std::max(NT, kMinThreads);
+    NT = std::max(NT, P == 1 ? 128 : kMinThreads);
+    g->pipe = 0;
     g->P = P;
     g->NT = NT;
     g->W = NT / 32;
+    g->R = g->W;
+    g->G = 0;
+    g->D = 1;
     g->NP = NT * P;
     g->RS = 2 * g->NP + (g->W + 3) / 4 * 4;
     int chunk = kMaxChunk;
@@ -65,17 +78,112 @@ int pick_geometry(int T, int V, int S_max, Geometry* g) {
     return CTC_B200_OK;
 }
 
-template <int P>
-int launch_fused_p(const FusedParams& prm, const Geometry& g, int n_utt, cudaStream_t st) {
+// Warp-specialised kernel: R recursion warps (P pairs per thread) + 1 load warp + G gradient warps.
+bool pick_pipe(int T, int V, int pairs, int n_utt, Geometry* g) {
+    if (V % 4) return false;   // TMA row copies need 16-byte aligned logit rows
+    int P = pairs > 64 ? 4 : (pairs > 32 ? 2 : 1);
+    const int q = env_int("CTC_B200_PAIRS", 0);
+    if (q == 1 || q == 2 || q == 4) P = q;
+    const int R = (pairs + 32 * P - 1) / (32 * P);
+    int H = env_int("CTC_B200_HELPERS", 0);
+    if (H < 1 || H > 8) H = pairs > 700 ? 4 : 2;
+    const int NT = 32 * (R + H);
+    if (NT > 1024) return false;
+    // (chunk, fetch distance) candidates.  All CTAs should be co-resident (one wave: the
+    // kernel is as long as its longest utterance), so the shared-memory budget per CTA is
+    // an SM's 227 KB divided by the CTAs per SM the launch needs (at most 4).
+    const int tc_env = env_int("CTC_B200_CHUNK", 0), d_env = env_int("CTC_B200_DIST", 0);
+    const int cand[4][2] = {{4, 1}, {2, 2}, {2, 1}, {1, 1}};
+    const int RS = 2 * 32 * P * R + (R + 3) / 4 * 4;
+    for (int pass = 0; pass < 2; ++pass) {
+        for (int ci = 0; ci < 4; ++ci) {
+            int TC = cand[ci][0], D = cand[ci][1];
+            if (tc_env == 1 || tc_env == 2 || tc_env == 4 || tc_env == 8) TC = tc_env;
+            if (d_env >= 1 && d_env <= 4) D = d_env;
+            PipeSmem lay(32 * P * R, R, V, TC, RS, D);
+            const int need = std::max(1, std::min(4, (2 * std::max(n_utt, 1) + kNumSmsHint - 1) / kNumSmsHint));
+            const int limit = pass == 0 ? std::min(kMaxSmemBytes, 227 * 1024 / need - 2048) : kMaxSmemBytes;
+            if (lay.total > limit) continue;
+            g->pipe = 1;
+            g->P = P;
+            g->NT = NT;
+            g->W = NT / 32;
+            g->R = R;
+            g->G = H;
+            g->D = D;
+            g->NP = 32 * P * R;
+            g->RS = RS;
+            g->chunk = TC;
+            g->smem = lay.total;
+            g->lat_utt_stride = (size_t)std::max(T, 1) * (size_t)RS;
+            return true;
+        }
+    }
+    return false;
+}
+
+int num_sms() {
+    static int n = -1;
+    if (n < 0) {
+        int dev = 0, v = 0;
+        if (cudaGetDevice(&dev) == cudaSuccess &&
+            cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && v > 0)
+            n = v;
+        else
+            n = 148;
+    }
+    return n;
+}
+
+int pick_geometry(int T, int V, int S_max, int n_utt, Geometry* g) {
+    if (T < 0 || V < 1 || S_max < 0) return CTC_B200_INVALID_ARGUMENT;
+    const int pairs = S_max + 1;
+    if (pairs > 4096) return CTC_B200_UNSUPPORTED;  // targets longer than 4095 labels
+    const char* force = std::getenv("CTC_B200_KERNEL");
+    const bool want_generic = force && force[0] == 'g';
+    if (!want_generic && pick_pipe(T, V, pairs, n_utt, g)) return CTC_B200_OK;
+    return pick_generic(T, V, pairs, g);
+}
+
+template <int P, int MAXT>
+int launch_fused_pt(const FusedParams& prm, const Geometry& g, int n_utt, cudaStream_t st) {
     static int configured_smem = -1;  // per-process, per-instantiation high-water mark
     if (g.smem > configured_smem) {
-        CTC_CUDA(cudaFuncSetAttribute(ctc_fused_kernel<P>,
+        CTC_CUDA(cudaFuncSetAttribute(ctc_fused_kernel<P, MAXT>,
                                       cudaFuncAttributeMaxDynamicSharedMemorySize, g.smem));
         configured_smem = g.smem;
     }
-    ctc_fused_kernel<P><<<dim3(2 * n_utt), dim3(g.NT), g.smem, st>>>(prm);
+    ctc_fused_kernel<P, MAXT><<<dim3(2 * n_utt), dim3(g.NT), g.smem, st>>>(prm);
     CTC_CUDA(cudaGetLastError());
     return CTC_B200_OK;
+}
+
+template <int P>
+int launch_fused_p(const FusedParams& prm, const Geometry& g, int n_utt, cudaStream_t st) {
+    // small CTAs get the full register file, large ones the 64-register cap
+    return g.NT <= 256 ? launch_fused_pt<P, 256>(prm, g, n_utt, st)
+                       : launch_fused_pt<P, 1024>(prm, g, n_utt, st);
+}
+
+template <int P, int MAXT, int MINB>
+int launch_pipe_pt(const PipeParams& pp, const Geometry& g, int n_utt, cudaStream_t st) {
+    static int configured_smem = -1;
+    if (g.smem > configured_smem) {
+        CTC_CUDA(cudaFuncSetAttribute(ctc_pipe_kernel<P, MAXT, MINB>,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, g.smem));
+        configured_smem = g.smem;
+    }
+    ctc_pipe_kernel<P, MAXT, MINB><<<dim3(2 * n_utt), dim3(g.NT), g.smem, st>>>(pp);
+    CTC_CUDA(cudaGetLastError());
+    return CTC_B200_OK;
+}
+
+template <int P>
+int launch_pipe_p(const PipeParams& pp, const Geometry& g, int n_utt, cudaStream_t st) {
+    if (g.NT <= 128) return launch_pipe_pt<P, 128, 4>(pp, g, n_utt, st);
+    if (g.NT <= 256) return launch_pipe_pt<P, 256, 2>(pp, g, n_utt, st);
+    if (g.NT <= 512) return launch_pipe_pt<P, 512, 1>(pp, g, n_utt, st);
+    return launch_pipe_pt<P, 1024, 1>(pp, g, n_utt, st);
 }
 
 int launch_fused(const float* acts, const int32_t* targets, const int32_t* tgt_offsets,
@@ -90,7 +198,7 @@ int launch_fused(const float* acts, const int32_t* targets, const int32_t* tgt_o
         return CTC_B200_INVALID_ARGUMENT;
     if (utt_count == 0) return CTC_B200_OK;
     Geometry g;
-    int rc = pick_geometry(T, V, S_max, &g);
+    int rc = pick_geometry(T, V, S_max, N, &g);
     if (rc != CTC_B200_OK) return rc;
     if (!lattice || lattice_bytes < g.lat_utt_stride * sizeof(float) * (size_t)utt_count)
         return CTC_B200_WORKSPACE_TOO_SMALL;
@@ -118,6 +226,21 @@ int launch_fused(const float* acts, const int32_t* targets, const int32_t* tgt_o
     prm.utt_begin = utt_begin;
     prm.row_stride = g.RS;
     prm.chunk = g.chunk;
+    if (g.pipe) {
+        PipeParams pp;
+        pp.f = prm;
+        pp.R = g.R;
+        pp.H = g.G;
+        pp.NP = g.NP;
+        pp.D = g.D;
+        pp.rotate = env_int("CTC_B200_ROTATE", 1) ? num_sms() : 0;
+        switch (g.P) {
+            case 1: return launch_pipe_p<1>(pp, g, utt_count, st);
+            case 2: return launch_pipe_p<2>(pp, g, utt_count, st);
+            case 4: return launch_pipe_p<4>(pp, g, utt_count, st);
+        }
+        return CTC_B200_UNSUPPORTED;
+    }
     switch (g.P) {
         case 1: return launch_fused_p<1>(prm, g, utt_count, st);
         case 2: return launch_fused_p<2>(prm, g, utt_count, st);
@@ -156,8 +279,11 @@ const char* ctc_b200_last_cuda_error(void) { return cudaGetErrorString(g_last_cu
 int ctc_b200_get_geometry(int T, int n_utt, int V, int S_max, ctc_b200_geometry* out) {
     if (!out || n_utt < 0) return CTC_B200_INVALID_ARGUMENT;
     Geometry g;
-    int rc = pick_geometry(T, V, S_max, &g);
+    int rc = pick_geometry(T, V, S_max, n_utt, &g);
     if (rc != CTC_B200_OK) return rc;
+    out->kernel = g.pipe;
+    out->rec_warps = g.R;
+    out->grad_warps = g.G;
     out->pairs_per_thread = g.P;
     out->threads = g.NT;
     out->chunk = g.chunk;
@@ -269,7 +395,7 @@ int ctc_b200_session_create(int T, int N, int V, int S_max, int max_targets, int
     if (!s) return CTC_B200_INVALID_ARGUMENT;
     s->T = T; s->N = N; s->V = V; s->S_max = S_max; s->max_targets = max_targets;
     s->n_slices = std::max(1, std::min(n_slices, N));
-    int rc = pick_geometry(T, V, S_max, &s->geo);
+    int rc = pick_geometry(T, V, S_max, N, &s->geo);
     if (rc != CTC_B200_OK) { delete s; return rc; }
     const size_t nact = (size_t)T * N * V * sizeof(float);
     s->lattice_bytes = s->geo.lat_utt_stride * sizeof(float) * (size_t)N;

@@ -191,7 +191,7 @@ void scale_grad(torch::Tensor grad, const torch::Tensor& scale) {
 std::vector<int64_t> geometry(int64_t T, int64_t N, int64_t V, int64_t S_max) {
     ctc_b200_geometry g;
     check_status(ctc_b200_get_geometry((int)T, (int)N, (int)V, (int)S_max, &g), "ctc_b200_get_geometry");
-    return {g.pairs_per_thread, g.threads, g.chunk, g.row_stride, g.smem_bytes,
+    return {g.kernel, g.rec_warps, g.grad_warps, g.pairs_per_thread, g.threads, g.chunk, g.row_stride, g.smem_bytes,
             (int64_t)g.workspace_bytes};
 }
 

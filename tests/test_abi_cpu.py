@@ -40,13 +40,14 @@ def test_version_and_status_strings():
 
 def test_geometry_and_workspace():
     g = cabi.geometry(1000, 256, 48, 240)          # BASELINE config 2
-    assert g["pairs_per_thread"] == 1 and g["threads"] == 256 and g["threads"] % 32 == 0
+    P = g["pairs_per_thread"]
+    assert P in (1, 2, 4) and g["threads"] % 32 == 0 and g["threads"] * P >= 241
     assert g["row_stride"] % 4 == 0 and g["smem_bytes"] <= 227 * 1024
     assert g["workspace_bytes"] == 256 + 256 * 1000 * g["row_stride"] * 4
     assert cabi.workspace_bytes(1000, 256, 48, 240) == g["workspace_bytes"]
     g3 = cabi.geometry(4000, 64, 48, 800)          # BASELINE config 3
-    assert g3["threads"] == 832 and g3["smem_bytes"] <= 227 * 1024
-    assert cabi.geometry(100, 1, 48, 1500)["pairs_per_thread"] == 2
+    assert g3["threads"] * g3["pairs_per_thread"] >= 801 and g3["smem_bytes"] <= 227 * 1024
+    assert cabi.geometry(100, 1, 48, 1500)["threads"] <= 1024
     assert cabi.geometry(100, 1, 48, 4095)["pairs_per_thread"] == 4
     with pytest.raises(cabi.CtcB200Error) as e:
         cabi.geometry(100, 1, 48, 4096)

@@ -146,9 +146,9 @@ def test_forward_only_matches():
 
 
 def test_long_target_multiple_pairs_per_thread():
-    """S_max + 1 > 1024 lattice pairs: 2 pairs per thread."""
+    """S_max + 1 > 1024 lattice pairs: several pairs per thread, > 8 warps per CTA."""
     acts, tg, il, tl = synth.make_batch(2, 2600, 12, 1200, seed=9, fixed_lengths=True)
-    assert cabi.geometry(2600, 2, 12, 1200)["pairs_per_thread"] == 2
+    assert cabi.geometry(2600, 2, 12, 1200)["pairs_per_thread"] >= 2
     nll, grad, _ = run_engine(acts, tg, il, tl)
     orc = oracle.ctc_oracle_f64(acts.numpy(), tg.numpy(), il.numpy(), tl.numpy())
     assert_parity(nll, grad, orc["nll"], orc["grad"], what="P=2")
