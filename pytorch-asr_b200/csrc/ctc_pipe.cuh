@@ -220,6 +220,25 @@ ctc_pipe_kernel(const PipeParams pp) {
     using TrueT = std::integral_constant<bool, true>;
     using FalseT = std::integral_constant<bool, false>;
 
+#ifdef CTC_B200_PROFILE
+    // developer instrumentation: busy cycles of CTA 0 per role -> workspace header (u64 at +64):
+    // [0] REC warp 0, [1] helper 0, [2] helper 1, [3] wall, [4] iterations, [5] T_b,
+    // [6] helper 0 softmax part, [7] helper 0 gradient part
+    unsigned long long* prof = reinterpret_cast<unsigned long long*>(reinterpret_cast<char*>(p.status) + 64);
+    const bool prof_on = blockIdx.x == 0 && lane == 0 && (w == 0 || w == R || w == R + 1);
+    const int prof_slot = w == 0 ? 0 : (w == R ? 1 : 2);
+    long long prof_t0 = clock64();
+    const long long prof_start = prof_t0;
+#define PROF_BEGIN() do { prof_t0 = clock64(); } while (0)
+#define PROF_END() do { if (prof_on) atomicAdd(prof + prof_slot, (unsigned long long)(clock64() - prof_t0)); } while (0)
+#define PROF_MARK(slot) do { if (prof_on && w == R) { atomicAdd(prof + (slot), (unsigned long long)(clock64() - prof_t1)); } prof_t1 = clock64(); } while (0)
+    long long prof_t1 = prof_t0;
+#else
+#define PROF_BEGIN() do {} while (0)
+#define PROF_END() do {} while (0)
+#define PROF_MARK(slot) do {} while (0)
+#endif
+
     if (is_rec) {
         // =============================================================================
         // REC
@@ -399,6 +418,7 @@ ctc_pipe_kernel(const PipeParams pp) {
         Ring ring_lp2(NL), ring_part(NS);   // position of the chunk REC works on
         int e_buf = 0;
         for (int it = 0; it < nch + 2; ++it) {
+            PROF_BEGIN();
             const int k = it - 1;
             if (k >= 0 && k < nch) {
                 int tt0, rows;
@@ -408,7 +428,13 @@ ctc_pipe_kernel(const PipeParams pp) {
                     for (int r = 0; r < rows; ++r)
                         rec_step(FalseT{}, FalseT{}, tt0 + r, lp2c + r * Vs, nullptr, nullptr);
                 } else {
+#ifdef CTC_B200_PROFILE
+                    { long long tw = clock64();
+#endif
                     mbar_wait(bar_part + ring_part.slot, ring_part.parity);   // TMA data landed
+#ifdef CTC_B200_PROFILE
+                      if (prof_on) atomicAdd(prof + 9, (unsigned long long)(clock64() - tw)); }
+#endif
                     const float* stc = s_stage + (size_t)ring_part.slot * TC * RS;
                     float* ec = s_e + (size_t)e_buf * TC * ER;
                     int r = 0;
@@ -422,6 +448,10 @@ ctc_pipe_kernel(const PipeParams pp) {
                 }
                 ring_lp2.advance();
             }
+            PROF_END();
+#ifdef CTC_B200_PROFILE
+            if (prof_on) atomicAdd(prof + (it <= n1 ? 10 : 11), (unsigned long long)(clock64() - prof_t0));
+#endif
             __syncthreads();
             if (it == n1) {  // phase break (see the helper branch)
                 cluster_sync_all();
@@ -583,6 +613,8 @@ ctc_pipe_kernel(const PipeParams pp) {
             }
         }
         for (int it = 0; it < nch + 2; ++it) {
+            PROF_BEGIN();
+            PROF_MARK(8);
             if (hw == 0) {
                 const int ka = it + D + 1, kp = it + D;
                 const bool do_a = ka < nch, do_p = want_grad && it >= n1 + 1 && kp < nch;
@@ -593,18 +625,31 @@ ctc_pipe_kernel(const PipeParams pp) {
             if (it < nch) {                           // softmax of chunk `it`
                 int tt0, rows;
                 chunk_at(it, tt0, rows);
+#ifdef CTC_B200_PROFILE
+                { long long tw = clock64();
+#endif
                 mbar_wait(bar_acts + sm_a.slot, sm_a.parity);
+#ifdef CTC_B200_PROFILE
+                  if (prof_on && w == R) atomicAdd(prof + 12, (unsigned long long)(clock64() - tw)); }
+#endif
+#ifndef CTC_B200_NOHELP
                 for (int r = hw; r < rows; r += H)
                     softmax_row(s_lp2 + ((size_t)sm_a.slot * TC + r) * Vs);
+#endif
             }
             sm_a.advance();
+            PROF_MARK(6);
             const int kg = it - 2;
             if (kg >= 0) {
                 if (want_grad && kg >= n1 && kg < nch) {   // gradient rows of chunk it-2
                     int tt0, rows;
                     chunk_at(kg, tt0, rows);
                     const bool infeasible = s_ll[2] != 0.f;
+#ifndef CTC_B200_NOHELP
                     for (int r = hw; r < rows; r += H)
+#else
+                    for (int r = hw; r < 0; r += H)
+#endif
                         grad_row(s_e + ((size_t)gr_e * TC + r) * ER,
                                  s_lp2 + ((size_t)gr_a.slot * TC + r) * Vs,
                                  grad_b + (size_t)(tbase + tsign * (tt0 + r)) * frame_stride, infeasible);
@@ -613,6 +658,8 @@ ctc_pipe_kernel(const PipeParams pp) {
                 }
                 gr_a.advance();
             }
+            PROF_MARK(7);
+            PROF_END();
             __syncthreads();
             if (it == n1) {
                 // Phase break: my REC warps have stored every row the partner will consume,
@@ -629,6 +676,13 @@ ctc_pipe_kernel(const PipeParams pp) {
             }
         }
     }
+#ifdef CTC_B200_PROFILE
+    if (blockIdx.x == 0 && tid == 0) {
+        prof[3] = (unsigned long long)(clock64() - prof_start);
+        prof[4] = (unsigned long long)(nch + 2);
+        prof[5] = (unsigned long long)Tb;
+    }
+#endif
 }
 
 }  // namespace ctcb200
