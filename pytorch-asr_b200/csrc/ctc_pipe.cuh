@@ -8,17 +8,20 @@
 //
 //   warps [0, R)      REC   lattice recursion; P cell pairs per thread in registers;
 //                           one named barrier per step among the R warps (none if R=1)
-//   warps [R, R+H)    HELP  one chunk AHEAD: TMA bulk copies (cp.async.bulk +
-//                           mbarrier complete_tx) of the logit rows and of the
-//                           partner's lattice rows into shared-memory rings, fused
-//                           log_softmax in place;
-//                           two chunks BEHIND: occupancies -> per-class sums (prefix
-//                           sums over the class-sorted label cells) -> gradient rows,
-//                           written with coalesced 128-bit stores; zero fill of rows
-//                           t >= T_b
+//   warps [R, R+H)    HELP  AHEAD of REC: TMA bulk copies (cp.async.bulk + mbarrier
+//                           complete_tx) of the logit rows and of the partner's lattice
+//                           rows into shared-memory rings; fused log_softmax in place.
+//                           BEHIND REC: occupancies -> per-class sums (prefix sums over
+//                           the class-sorted label cells) -> gradient rows; zero fill of
+//                           rows t >= T_b.  A helper works on TWO frames at a time, one
+//                           per half-warp, so the two dependent chains overlap.
 //
 // One CTA barrier per chunk of TC frames hands the rings over; consumers of TMA data
 // wait on the ring slot's mbarrier.  Requires V % 4 == 0 (16-byte aligned logit rows).
+//
+// The kernel is latency-bound per warp (one in-order warp per role and SM
+// sub-partition), so the code keeps every per-step quantity in a loop-carried register
+// (pointers advance by a stride; nothing is re-derived from kernel parameters).
 #pragma once
 #include "ctc_kernels.cuh"
 
@@ -32,18 +35,24 @@ struct PipeParams {
     int rotate;    // CTAs per launch "layer" (= #SMs): co-resident CTAs rotate their warp roles
 };
 
+// class-sorted label cell k lives at float index ypad(k) of the eY row: one float4 of
+// padding per 16 cells makes "lane q owns cells [16q, 16q+16)" bank-conflict free
+__host__ __device__ __forceinline__ int ypad(int k) { return k + ((k >> 4) << 2); }
+
 struct PipeSmem {
-    int lab, cstart, lp2, e, stage, bnd, red, ll, bars, total;  // byte offsets
+    int lab, pos, cstart, fill, lp2, e, stage, bnd, red, ll, bars, total;  // byte offsets
     int Vs, ER, NL, NS;
     __host__ __device__ static int up(int x, int a) { return (x + a - 1) / a * a; }
     __host__ __device__ PipeSmem(int NP, int R, int V, int TC, int RS, int D) {
         Vs = up(V + 1, 4);
-        ER = 2 * NP + 4;  // [eB: NP][eY (class-sorted): NP] + 4 floats of bank skew per row
-        NL = D + 4;       // lp2 ring: issued D+1 chunks early .. gradient 2 chunks later
-        NS = D + 2;       // partner ring: issued D chunks early .. recursion 1 chunk later
+        ER = NP + ypad(NP) + 4;  // [eB: NP][eY (class-sorted, padded)] + 4 floats of bank skew
+        NL = D + 4;              // lp2 ring: issued D+1 chunks early .. gradient 2 chunks later
+        NS = D + 2;              // partner ring: issued D chunks early .. recursion 1 chunk later
         int o = 0;
         lab = o;    o += up(NP * 4, 16);
+        pos = o;    o += up(NP * 4, 16);
         cstart = o; o += up((V + 2) * 4, 16);
+        fill = o;   o += up((V + 2) * 4, 16);
         lp2 = o;    o += up(NL * TC * Vs * 4, 16);
         e = o;      o += up(2 * TC * ER * 4, 16);
         stage = o;  o += up(NS * TC * RS * 4, 16);
@@ -85,6 +94,20 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned by
                  ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async_smem() {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+// sum / max over the 16 lanes of a half-warp (xor offsets < 16 stay inside the half)
+__device__ __forceinline__ float half_sum(float x) {
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+    return x;
+}
+__device__ __forceinline__ float half_max(float x) {
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) x = fmaxf(x, __shfl_xor_sync(0xffffffffu, x, o));
+    return x;
+}
 
 struct Ring {  // incrementally maintained (slot, phase parity) of a ring of n mbarrier slots
     int slot, n;
@@ -117,7 +140,9 @@ ctc_pipe_kernel(const PipeParams pp) {
     const PipeSmem lay(NP, R, V, TC, RS, D);
     const int Vs = lay.Vs, ER = lay.ER, NL = lay.NL, NS = lay.NS;
     int* s_lab = reinterpret_cast<int*>(smem_raw + lay.lab);
+    int* s_pos = reinterpret_cast<int*>(smem_raw + lay.pos);
     int* s_cstart = reinterpret_cast<int*>(smem_raw + lay.cstart);
+    int* s_fill = reinterpret_cast<int*>(smem_raw + lay.fill);
     float* s_lp2 = reinterpret_cast<float*>(smem_raw + lay.lp2);
     float* s_e = reinterpret_cast<float*>(smem_raw + lay.e);
     float* s_stage = reinterpret_cast<float*>(smem_raw + lay.stage);
@@ -145,11 +170,10 @@ ctc_pipe_kernel(const PipeParams pp) {
     if (want_grad && !is_rec) {
         const int nrows = T - Tb;
         const int mine = (nrows + (rev ? 0 : 1)) >> 1;  // rows Tb+rev, Tb+rev+2, ...
-        const int first = Tb + (rev ? 1 : 0);
-        for (int r = hw; r < mine; r += H) {
-            float4* g4 = reinterpret_cast<float4*>(grad_b + (size_t)(first + 2 * r) * frame_stride);
-            for (int c = lane; c < V4; c += 32) g4[c] = make_float4(0.f, 0.f, 0.f, 0.f);
-        }
+        float* g = grad_b + (size_t)(Tb + (rev ? 1 : 0) + 2 * hw) * frame_stride;
+        const size_t ginc = 2 * (size_t)H * frame_stride;
+        for (int r = hw; r < mine; r += H, g += ginc)
+            for (int c = lane; c < V4; c += 32) reinterpret_cast<float4*>(g)[c] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
     if (Tb == 0) {  // torch: empty input => 0 for an empty target, +inf otherwise
         if (!rev && tid == 0)
@@ -168,6 +192,7 @@ ctc_pipe_kernel(const PipeParams pp) {
             }
         }
         s_lab[i] = c;
+        s_pos[i] = i;  // padding pairs park their kNeg at sorted slot i >= S
     }
     for (int v = tid; v < V + 2; v += NT) s_cstart[v] = 0;
     for (int i = tid; i < 2 * (R + 1); i += NT) s_bnd[i] = make_float2(kNeg, 0.f);
@@ -181,7 +206,8 @@ ctc_pipe_kernel(const PipeParams pp) {
     if (want_grad)
         for (int i = tid; i < S; i += NT) atomicAdd(&s_cstart[s_lab[i] + 1], 1);
     __syncthreads();
-    if (want_grad && w == 0) {  // exclusive scan of the class histogram
+    if (want_grad && w == 0) {
+        // exclusive scan of the class histogram: s_cstart[v] = #labels of class < v
         int carry = 0;
         for (int base = 0; base < V + 1; base += 32) {
             const int v = base + lane;
@@ -191,8 +217,25 @@ ctc_pipe_kernel(const PipeParams pp) {
                 const int y = __shfl_up_sync(0xffffffffu, inc, o);
                 if (lane >= o) inc += y;
             }
-            if (v < V + 1) s_cstart[v] = carry + inc;  // = #labels of class < v
+            if (v < V + 1) { s_cstart[v] = carry + inc; s_fill[v] = carry + inc; }
             carry += __shfl_sync(0xffffffffu, inc, 31);
+        }
+        __syncwarp();
+        // class-sorted position of every label, equal labels in sweep order (deterministic):
+        // 32 labels per round, lanes with the same class rank themselves with match.any
+        for (int base = 0; base < S; base += 32) {
+            const int i = base + lane;
+            const int c = (i < S) ? s_lab[i] : -1 - lane;
+            const unsigned peers = __match_any_sync(0xffffffffu, c);
+            const int rank = __popc(peers & ((1u << lane) - 1u));
+            int first = 0;
+            if (i < S) first = s_fill[c];
+            __syncwarp();
+            if (i < S) {
+                s_pos[i] = first + rank;
+                if (rank == 0) s_fill[c] = first + __popc(peers);
+            }
+            __syncwarp();
         }
     }
     __syncthreads();
@@ -217,13 +260,9 @@ ctc_pipe_kernel(const PipeParams pp) {
         else { tt0 = n_store + (c - n1) * TC; rows = want_grad ? min(TC, Tb - tt0) : 1; }
     };
 
-    using TrueT = std::integral_constant<bool, true>;
-    using FalseT = std::integral_constant<bool, false>;
-
 #ifdef CTC_B200_PROFILE
     // developer instrumentation: busy cycles of CTA 0 per role -> workspace header (u64 at +64):
-    // [0] REC warp 0, [1] helper 0, [2] helper 1, [3] wall, [4] iterations, [5] T_b,
-    // [6] helper 0 softmax part, [7] helper 0 gradient part
+    // [0] REC warp 0, [1] helper 0, [2] helper 1, [3] wall, [4] iterations, [5] T_b
     unsigned long long* prof = reinterpret_cast<unsigned long long*>(reinterpret_cast<char*>(p.status) + 64);
     const bool prof_on = blockIdx.x == 0 && lane == 0 && (w == 0 || w == R || w == R + 1);
     const int prof_slot = w == 0 ? 0 : (w == R ? 1 : 2);
@@ -231,12 +270,9 @@ ctc_pipe_kernel(const PipeParams pp) {
     const long long prof_start = prof_t0;
 #define PROF_BEGIN() do { prof_t0 = clock64(); } while (0)
 #define PROF_END() do { if (prof_on) atomicAdd(prof + prof_slot, (unsigned long long)(clock64() - prof_t0)); } while (0)
-#define PROF_MARK(slot) do { if (prof_on && w == R) { atomicAdd(prof + (slot), (unsigned long long)(clock64() - prof_t1)); } prof_t1 = clock64(); } while (0)
-    long long prof_t1 = prof_t0;
 #else
 #define PROF_BEGIN() do {} while (0)
 #define PROF_END() do {} while (0)
-#define PROF_MARK(slot) do {} while (0)
 #endif
 
     if (is_rec) {
@@ -244,8 +280,8 @@ ctc_pipe_kernel(const PipeParams pp) {
         // REC
         // =============================================================================
         const int i0 = tid * P;
-        int lab[P], pos[P];
-        bool skip[P], selB[P], selY[P];
+        int lab[P], ysl[P];
+        bool skip[P], selB[P], selY[P], vB[P], vY[P];
         float aB[P], aY[P];
         const int jB0 = S - i0;                            // partner pair index of my first blank
         const int pw_hi = max(jB0, 0) / (32 * P);          // at most two partner warps per thread
@@ -255,165 +291,88 @@ ctc_pipe_kernel(const PipeParams pp) {
             const int i = i0 + k;
             lab[k] = s_lab[i];
             skip[k] = (i >= 1 && i < S && lab[k] != s_lab[i - 1]);
-            pos[k] = i;                                    // padding pairs park their kNeg at slot i >= S
-            if (want_grad && i < S) {                      // deterministic rank inside the class
-                int r = 0;
-                for (int j = 0; j < i; ++j) r += (s_lab[j] == lab[k]) ? 1 : 0;
-                pos[k] = s_cstart[lab[k]] + r;
-            }
+            ysl[k] = NP + ypad(s_pos[i]);                  // where my label cell goes in an e row
             selB[k] = max(jB0 - k, 0) / (32 * P) == pw_hi;
             selY[k] = max(jB0 - 1 - k, 0) / (32 * P) == pw_hi;
+            vB[k] = i <= S;
+            vY[k] = i < S;
             aB[k] = kNeg;
             aY[k] = kNeg;
         }
         if (tid == 0) aB[0] = 0.0f;  // virtual row "-1": log(1) in front of the first blank
         float off = 0.0f;            // this warp's exact integer offset (true = off + a)
         bool fresh = (w != 0);       // warp has not received any real value yet
-        int par = 0;
         float ll_int = 0.f, ll_frac = 0.f;
         // thread / warp activity windows in sweep steps (widened by P pairs, see above)
         const unsigned win_store = (i0 - P <= S) ? (unsigned)(C + 3 * P) : 0u;   // (tt - i0 + P) < win
         const unsigned win_cons = (i0 <= S) ? (unsigned)(C + P) : 0u;            // (tt - i0) < win
         const int w_first = (32 * P * w - P <= S) ? 32 * P * w - P : 0x3fffffff;
         const int w_last = C + 32 * P * w + 32 * P - 1 + P;
+        // loop-carried shared-memory pointers for the warp-to-warp boundary (double buffered)
+        float2* bnd_rd = s_bnd + w;              // slot 0 is the constant (kNeg, 0)
+        float2* bnd_wr = s_bnd + (R + 1) + w + 1;
+        const bool lane0 = lane == 0, lane31 = (lane == 31) && R > 1;
+        const int nbar = 32 * R;
+        const ptrdiff_t row_inc = (ptrdiff_t)tsign * RS;
 
-        auto rec_step = [&](auto consume_tag, auto first_tag, int tt, const float* lp2,
-                            const float* st, float* erow) {
-            constexpr bool CONSUME = decltype(consume_tag)::value;
-            constexpr bool FIRST = decltype(first_tag)::value;
-            const bool wact = (tt >= w_first) && (tt <= w_last);
-            float eBv[P], eYv[P];   // combined log2 occupancies (FIRST: fractional parts)
-            float nBv[P], nYv[P];   // FIRST only: exact integer parts
-            if (CONSUME) {
+        // keep per-step constants in registers (the compiler would otherwise re-derive them
+        // from the kernel parameters inside the loops; every such reload is an exposed
+        // latency for a single in-order warp)
+        int wg_i = want_grad ? 1 : 0, vs_i = Vs, rs_i = RS, er_i = ER, np_i = NP;
+        asm volatile("" : "+r"(wg_i), "+r"(vs_i), "+r"(rs_i), "+r"(er_i), "+r"(np_i));
+        const bool wg = wg_i != 0;
+        const ptrdiff_t row_step = (ptrdiff_t)tsign * rs_i;
+
+        auto renorm = [&]() {
+            // exact integer renormalisation keeps |a| small (fp32 accuracy at long T)
+            float m = kNeg;
 #pragma unroll
-                for (int k = 0; k < P; ++k) { eBv[k] = kNeg; eYv[k] = kNeg; nBv[k] = 0.f; nYv[k] = 0.f; }
-            }
-            if (wact) {
-                const float lpb = lp2[blank];
-                float am1 = __shfl_up_sync(0xffffffffu, aY[P - 1], 1);
-                float2 bq = make_float2(kNeg, 0.f);
-                if (lane == 0) bq = s_bnd[par * (R + 1) + w];  // slot 0 is the constant (kNeg, 0)
-                if (fresh) {
-                    const float bv = __shfl_sync(0xffffffffu, bq.x, 0);
-                    const float bo = __shfl_sync(0xffffffffu, bq.y, 0);
-                    if (bv > kRealThresh) { off = bo; fresh = false; }
-                }
-                if (lane == 0) am1 = bq.x + (bq.y - off);
-                float lpl[P];
+            for (int k = 0; k < P; ++k) m = fmaxf(m, fmaxf(aB[k], aY[k]));
+            m = warp_max(m);
+            if (m > kRealThresh) {
+                const float sh = rintf(m);
 #pragma unroll
                 for (int k = 0; k < P; ++k) {
-                    lpl[k] = lp2[lab[k]];
-                    const float x = lse2(aB[k], am1);
-                    const float yin = skip[k] ? x : aB[k];
-                    const float ynew = lpl[k] + lse2(aY[k], yin);
-                    am1 = aY[k];
-                    aB[k] = lpb + x;
-                    aY[k] = ynew;
+                    aB[k] = fmaxf(aB[k] - sh, kNeg);
+                    aY[k] = fmaxf(aY[k] - sh, kNeg);
                 }
-                // exact integer renormalisation keeps |a| small (fp32 accuracy at long T)
-                if ((tt & kRenormMask) == kRenormMask) {
-                    float m = kNeg;
-#pragma unroll
-                    for (int k = 0; k < P; ++k) m = fmaxf(m, fmaxf(aB[k], aY[k]));
-                    m = warp_max(m);
-                    if (m > kRealThresh) {
-                        const float sh = rintf(m);
-#pragma unroll
-                        for (int k = 0; k < P; ++k) {
-                            aB[k] = fmaxf(aB[k] - sh, kNeg);
-                            aY[k] = fmaxf(aY[k] - sh, kNeg);
-                        }
-                        off += sh;
-                        fresh = false;
-                    }
-                }
-                if (R > 1 && lane == 31) s_bnd[(par ^ 1) * (R + 1) + w + 1] = make_float2(aY[P - 1], off);
-
-                if (!CONSUME) {
-                    if (want_grad || tt == n_store - 1) {
-                        float* row = lat_b + (size_t)(tbase + tsign * tt) * RS;
-                        if ((unsigned)(tt - i0 + P) < win_store) {
-                            store_vec<P>(row + i0, aB);
-                            store_vec<P>(row + NP + i0, aY);
-                        }
-                        if (lane == 0) row[2 * NP + w] = off;
-                    }
-                } else if ((unsigned)(tt - i0) < win_cons) {
-                    // a + partner - lp + (offsets - ll): the integer parts combine exactly
-                    const float nhi = off + st[2 * NP + pw_hi], nlo = off + st[2 * NP + pw_lo];
-                    if (FIRST) {
-#pragma unroll
-                        for (int k = 0; k < P; ++k) {
-                            if (i0 + k <= S) { eBv[k] = (aB[k] + st[jB0 - k]) - lpb; nBv[k] = selB[k] ? nhi : nlo; }
-                            if (i0 + k < S) { eYv[k] = (aY[k] + st[NP + jB0 - 1 - k]) - lpl[k]; nYv[k] = selY[k] ? nhi : nlo; }
-                        }
-                    } else {
-                        const float chi = (nhi - ll_int) - ll_frac, clo = (nlo - ll_int) - ll_frac;
-                        const float bhi = chi - lpb, blo = clo - lpb;
-#pragma unroll
-                        for (int k = 0; k < P; ++k) {
-                            if (i0 + k <= S) eBv[k] = (aB[k] + st[jB0 - k]) + (selB[k] ? bhi : blo);
-                            if (i0 + k < S) eYv[k] = (aY[k] + st[NP + jB0 - 1 - k]) + ((selY[k] ? chi : clo) - lpl[k]);
-                        }
-                    }
-                }
+                off += sh;
+                fresh = false;
             }
-            if (CONSUME) {
-                if (FIRST) {
-                    // log-likelihood from the first combined row, ll = ll_int + ll_frac with an
-                    // exact integer pivot: ll_int = max(n + rint(e)), ll_frac = log2 sum 2^(e + n - ll_int)
-                    float pm = kNeg;
-#pragma unroll
-                    for (int k = 0; k < P; ++k) {
-                        if (eBv[k] > kRealThresh) pm = fmaxf(pm, nBv[k] + rintf(eBv[k]));
-                        if (eYv[k] > kRealThresh) pm = fmaxf(pm, nYv[k] + rintf(eYv[k]));
-                    }
-                    pm = warp_max(pm);
-                    if (R > 1) {
-                        if (lane == 0) s_red[w] = pm;
-                        named_bar_sync(1, 32 * R);
-                        for (int i = 0; i < R; ++i) pm = fmaxf(pm, s_red[i]);
-                        named_bar_sync(1, 32 * R);
-                    }
-                    const bool infeasible = !(pm > kRealThresh);
-                    ll_int = infeasible ? 0.f : pm;
-                    float z = 0.f;
-#pragma unroll
-                    for (int k = 0; k < P; ++k) {
-                        eBv[k] = (eBv[k] > kRealThresh) ? eBv[k] + (nBv[k] - ll_int) : kNeg;
-                        eYv[k] = (eYv[k] > kRealThresh) ? eYv[k] + (nYv[k] - ll_int) : kNeg;
-                        z += ex2f(eBv[k]) + ex2f(eYv[k]);
-                    }
-                    z = warp_sum(z);
-                    if (R > 1) {
-                        if (lane == 0) s_red[w] = z;
-                        named_bar_sync(1, 32 * R);
-                        z = 0.f;
-                        for (int i = 0; i < R; ++i) z += s_red[i];
-                        named_bar_sync(1, 32 * R);
-                    }
-                    ll_frac = infeasible ? 0.f : lg2f(z);
-#pragma unroll
-                    for (int k = 0; k < P; ++k) { eBv[k] -= ll_frac; eYv[k] -= ll_frac; }
-                    if (tid == 0) {
-                        s_ll[2] = infeasible ? 1.f : 0.f;
-                        if (!rev) {
-                            float out;
-                            if (infeasible) out = p.zero_infinity ? 0.0f : CUDART_INF_F;
-                            else out = (float)(-((double)ll_int + (double)ll_frac) * kLn2);
-                            p.nll[b] = out;
-                        }
-                    }
-                }
-                if (want_grad) {
-#pragma unroll
-                    for (int k = 0; k < P; ++k) erow[NP + pos[k]] = eYv[k];
-                    store_vec<P>(erow + i0, eBv);
-                }
-            }
-            par ^= 1;
-            if (R > 1) named_bar_sync(1, 32 * R);
         };
+        // one recursion step on registers: a[t] <- a[t-1].  STEADY: the warp has real values
+        // and renormalises at chunk ends, so neither test is compiled into the step.
+        auto advance = [&](auto steady_tag, int tt, const float* lp2, float& lpb, float (&lpl)[P]) {
+            constexpr bool STEADY = decltype(steady_tag)::value;
+            lpb = lp2[blank];
+            float am1 = __shfl_up_sync(0xffffffffu, aY[P - 1], 1);
+            float2 bq = make_float2(kNeg, 0.f);
+            if (lane0) bq = *bnd_rd;
+            if (!STEADY && fresh) {
+                const float bv = __shfl_sync(0xffffffffu, bq.x, 0);
+                const float bo = __shfl_sync(0xffffffffu, bq.y, 0);
+                if (bv > kRealThresh) { off = bo; fresh = false; }
+            }
+            if (lane0) am1 = bq.x + (bq.y - off);
+#pragma unroll
+            for (int k = 0; k < P; ++k) {
+                lpl[k] = lp2[lab[k]];
+                const float x = lse2(aB[k], am1);
+                const float yin = skip[k] ? x : aB[k];
+                const float ynew = lpl[k] + lse2(aY[k], yin);
+                am1 = aY[k];
+                aB[k] = lpb + x;
+                aY[k] = ynew;
+            }
+            if (!STEADY && (tt & kRenormMask) == kRenormMask) renorm();
+            if (lane31) *bnd_wr = make_float2(aY[P - 1], off);
+        };
+        auto end_step = [&]() {
+            float2* t = bnd_rd; bnd_rd = bnd_wr - 1; bnd_wr = t + 1;   // flip the double buffer
+            if (R > 1) named_bar_sync(1, nbar);
+        };
+        using TrueT = std::integral_constant<bool, true>;
+        using FalseT = std::integral_constant<bool, false>;
 
         Ring ring_lp2(NL), ring_part(NS);   // position of the chunk REC works on
         int e_buf = 0;
@@ -423,35 +382,186 @@ ctc_pipe_kernel(const PipeParams pp) {
             if (k >= 0 && k < nch) {
                 int tt0, rows;
                 chunk_at(k, tt0, rows);
-                const float* lp2c = s_lp2 + (size_t)ring_lp2.slot * TC * Vs;
+                const int tt_end = tt0 + rows - 1;
+                // steady chunk: the warp is active for every row and already holds real values
+                const bool steady = wg && !fresh && tt0 >= w_first && tt_end <= w_last;
+                const bool renorm_after = ((tt_end + 1) >> 3) != (tt0 >> 3);
+                const float* lp2 = s_lp2 + (size_t)ring_lp2.slot * TC * vs_i;
                 if (k < n1) {
-                    for (int r = 0; r < rows; ++r)
-                        rec_step(FalseT{}, FalseT{}, tt0 + r, lp2c + r * Vs, nullptr, nullptr);
+                    // ---- store chunk: rows go to HBM for the partner --------------------
+                    float* row = lat_b + (ptrdiff_t)(tbase + tsign * tt0) * rs_i + i0;
+                    float* offp = lat_b + (ptrdiff_t)(tbase + tsign * tt0) * rs_i + 2 * np_i + w;
+                    if (steady) {
+                        // whole rows of the warp are stored (cells outside the band hold kNeg
+                        // or finite junk nobody reads): no per-thread test on the step
+                        for (int r = 0; r < rows; ++r, lp2 += vs_i, row += row_step, offp += row_step) {
+                            float lpb, lpl[P];
+                            advance(TrueT{}, tt0 + r, lp2, lpb, lpl);
+                            store_vec<P>(row, aB);
+                            store_vec<P>(row + np_i, aY);
+                            if (lane0) *offp = off;
+                            end_step();
+                        }
+                        if (renorm_after) renorm();
+                    } else {
+                        for (int r = 0; r < rows; ++r, lp2 += vs_i, row += row_step, offp += row_step) {
+                            const int tt = tt0 + r;
+                            if (tt >= w_first && tt <= w_last) {
+                                float lpb, lpl[P];
+                                advance(FalseT{}, tt, lp2, lpb, lpl);
+                                if (wg || tt == n_store - 1) {
+                                    if ((unsigned)(tt - i0 + P) < win_store) {
+                                        store_vec<P>(row, aB);
+                                        store_vec<P>(row + np_i, aY);
+                                    }
+                                    if (lane0) *offp = off;
+                                }
+                            }
+                            end_step();
+                        }
+                    }
                 } else {
-#ifdef CTC_B200_PROFILE
-                    { long long tw = clock64();
-#endif
+                    // ---- consume chunk: combine with the partner's stored rows ----------
                     mbar_wait(bar_part + ring_part.slot, ring_part.parity);   // TMA data landed
-#ifdef CTC_B200_PROFILE
-                      if (prof_on) atomicAdd(prof + 9, (unsigned long long)(clock64() - tw)); }
-#endif
-                    const float* stc = s_stage + (size_t)ring_part.slot * TC * RS;
-                    float* ec = s_e + (size_t)e_buf * TC * ER;
+                    const float* st = s_stage + (size_t)ring_part.slot * TC * rs_i;
+                    float* erow = s_e + (size_t)e_buf * TC * er_i;
+                    const float* stp = st + jB0;                 // partner blank of my pair q: stp[-q]
+                    const float* sto_hi = st + 2 * np_i + pw_hi; // partner warp offsets
+                    const float* sto_lo = st + 2 * np_i + pw_lo;
                     int r = 0;
-                    if (k == n1) { rec_step(TrueT{}, TrueT{}, tt0, lp2c, stc, ec); r = 1; }
-                    if (want_grad)
-                        for (; r < rows; ++r)
-                            rec_step(TrueT{}, FalseT{}, tt0 + r, lp2c + r * Vs, stc + (size_t)r * RS,
-                                     ec + (size_t)r * ER);
+                    if (k == n1) {
+                        // first combined row: also yields the log-likelihood.  ll = ll_int +
+                        // ll_frac with an exact integer pivot: ll_int = max(n + rint(e)),
+                        // ll_frac = log2 sum 2^(e + n - ll_int)
+                        const int tt = tt0;
+                        float eBv[P], eYv[P], nBv[P], nYv[P];
+#pragma unroll
+                        for (int q = 0; q < P; ++q) { eBv[q] = kNeg; eYv[q] = kNeg; nBv[q] = 0.f; nYv[q] = 0.f; }
+                        if (tt >= w_first && tt <= w_last) {
+                            float lpb, lpl[P];
+                            advance(FalseT{}, tt, lp2, lpb, lpl);
+                            if ((unsigned)(tt - i0) < win_cons) {
+                                const float nhi = off + *sto_hi, nlo = off + *sto_lo;
+#pragma unroll
+                                for (int q = 0; q < P; ++q) {
+                                    if (vB[q]) { eBv[q] = (aB[q] + stp[-q]) - lpb; nBv[q] = selB[q] ? nhi : nlo; }
+                                    if (vY[q]) { eYv[q] = (aY[q] + stp[np_i - 1 - q]) - lpl[q]; nYv[q] = selY[q] ? nhi : nlo; }
+                                }
+                            }
+                        }
+                        float pm = kNeg;
+#pragma unroll
+                        for (int q = 0; q < P; ++q) {
+                            if (eBv[q] > kRealThresh) pm = fmaxf(pm, nBv[q] + rintf(eBv[q]));
+                            if (eYv[q] > kRealThresh) pm = fmaxf(pm, nYv[q] + rintf(eYv[q]));
+                        }
+                        pm = warp_max(pm);
+                        if (R > 1) {
+                            if (lane0) s_red[w] = pm;
+                            named_bar_sync(1, nbar);
+                            for (int i = 0; i < R; ++i) pm = fmaxf(pm, s_red[i]);
+                            named_bar_sync(1, nbar);
+                        }
+                        const bool infeasible = !(pm > kRealThresh);
+                        ll_int = infeasible ? 0.f : pm;
+                        float z = 0.f;
+#pragma unroll
+                        for (int q = 0; q < P; ++q) {
+                            eBv[q] = (eBv[q] > kRealThresh) ? eBv[q] + (nBv[q] - ll_int) : kNeg;
+                            eYv[q] = (eYv[q] > kRealThresh) ? eYv[q] + (nYv[q] - ll_int) : kNeg;
+                            z += ex2f(eBv[q]) + ex2f(eYv[q]);
+                        }
+                        z = warp_sum(z);
+                        if (R > 1) {
+                            if (lane0) s_red[w] = z;
+                            named_bar_sync(1, nbar);
+                            z = 0.f;
+                            for (int i = 0; i < R; ++i) z += s_red[i];
+                            named_bar_sync(1, nbar);
+                        }
+                        ll_frac = infeasible ? 0.f : lg2f(z);
+                        if (tid == 0) {
+                            s_ll[2] = infeasible ? 1.f : 0.f;
+                            if (!rev) {
+                                float out;
+                                if (infeasible) out = p.zero_infinity ? 0.0f : CUDART_INF_F;
+                                else out = (float)(-((double)ll_int + (double)ll_frac) * kLn2);
+                                p.nll[b] = out;
+                            }
+                        }
+                        if (wg) {
+#pragma unroll
+                            for (int q = 0; q < P; ++q) {
+                                eBv[q] -= ll_frac;
+                                erow[ysl[q]] = eYv[q] - ll_frac;
+                            }
+                            store_vec<P>(erow + i0, eBv);
+                        }
+                        end_step();
+                        r = 1; lp2 += vs_i; stp += rs_i; sto_hi += rs_i; sto_lo += rs_i; erow += er_i;
+                    }
+                    if (wg) {
+                        // a + partner - lp + (offsets - ll): the integer parts combine exactly
+                        // The partner values are loaded BEFORE the recursion step (they do not depend
+                        // on it), so their shared-memory latency hides behind the MUFU chain.
+                        float pb[P], py[P], ohi, olo;
+                        auto fetch = [&]() {
+#pragma unroll
+                            for (int q = 0; q < P; ++q) { pb[q] = stp[-q]; py[q] = stp[np_i - 1 - q]; }
+                            ohi = *sto_hi;
+                            olo = *sto_lo;
+                        };
+                        auto combine = [&](int tt, float lpb, const float (&lpl)[P], float (&eBv)[P], float (&eYv)[P]) {
+                            if ((unsigned)(tt - i0) < win_cons) {
+                                const float chi = ((off + ohi) - ll_int) - ll_frac;
+                                const float clo = ((off + olo) - ll_int) - ll_frac;
+                                const float bhi = chi - lpb, blo = clo - lpb;
+#pragma unroll
+                                for (int q = 0; q < P; ++q) {   // padding pairs may have loaded junk: vB / vY guard them
+                                    if (vB[q]) eBv[q] = (aB[q] + pb[q]) + (selB[q] ? bhi : blo);
+                                    if (vY[q]) eYv[q] = (aY[q] + py[q]) + ((selY[q] ? chi : clo) - lpl[q]);
+                                }
+                            }
+                        };
+                        if (steady) {
+                            for (; r < rows; ++r, lp2 += vs_i, stp += rs_i, sto_hi += rs_i, sto_lo += rs_i, erow += er_i) {
+                                float eBv[P], eYv[P], lpb, lpl[P];
+#pragma unroll
+                                for (int q = 0; q < P; ++q) { eBv[q] = kNeg; eYv[q] = kNeg; }
+                                fetch();
+                                advance(TrueT{}, tt0 + r, lp2, lpb, lpl);
+                                combine(tt0 + r, lpb, lpl, eBv, eYv);
+#pragma unroll
+                                for (int q = 0; q < P; ++q) erow[ysl[q]] = eYv[q];
+                                store_vec<P>(erow + i0, eBv);
+                                end_step();
+                            }
+                            if (renorm_after) renorm();
+                        } else {
+                            for (; r < rows; ++r, lp2 += vs_i, stp += rs_i, sto_hi += rs_i, sto_lo += rs_i, erow += er_i) {
+                                const int tt = tt0 + r;
+                                float eBv[P], eYv[P];
+#pragma unroll
+                                for (int q = 0; q < P; ++q) { eBv[q] = kNeg; eYv[q] = kNeg; }
+                                if (tt >= w_first && tt <= w_last) {
+                                    float lpb, lpl[P];
+                                    fetch();
+                                    advance(FalseT{}, tt, lp2, lpb, lpl);
+                                    combine(tt, lpb, lpl, eBv, eYv);
+                                }
+#pragma unroll
+                                for (int q = 0; q < P; ++q) erow[ysl[q]] = eYv[q];
+                                store_vec<P>(erow + i0, eBv);
+                                end_step();
+                            }
+                        }
+                    }
                     ring_part.advance();
                     e_buf ^= 1;
                 }
                 ring_lp2.advance();
             }
             PROF_END();
-#ifdef CTC_B200_PROFILE
-            if (prof_on) atomicAdd(prof + (it <= n1 ? 10 : 11), (unsigned long long)(clock64() - prof_t0));
-#endif
             __syncthreads();
             if (it == n1) {  // phase break (see the helper branch)
                 cluster_sync_all();
@@ -462,141 +572,128 @@ ctc_pipe_kernel(const PipeParams pp) {
         // =============================================================================
         // HELP: TMA producer, fused log_softmax, gradient rows
         // =============================================================================
-        // ---- TMA issue: one lane per piece; piece = (row r, kind) ----------------------
-        //   kind 0: logits row of chunk ka          -> lp2 ring slot
-        //   kind 1/2/3: partner blank plane segment / label plane segment / warp offsets
-        //               of chunk kp                  -> partner ring slot
-        const int prow = lane >> 2, pkind = lane & 3;     // TC <= 8 rows x 4 kinds = 32 lanes
+        const int half = lane >> 4, q16 = lane & 15;   // a helper handles two frames at a time
+
+        // ---- TMA issue of one chunk: one bulk copy per row ------------------------------
+        //   lanes 0..7  : logits row `lane` of chunk ka              -> lp2 ring slot
+        //   lanes 8..15 : the partner's whole lattice row of chunk kp -> partner ring slot
+        //   (whole rows: regions the partner never wrote are copied but never read)
         auto issue_chunk = [&](int ka, int slot_a, int kp, int slot_p) {
-            // ka / kp < 0: nothing of that kind to issue this time
-            unsigned bytes = 0;
-            const float* src = nullptr;
-            float* dst = nullptr;
-            if (pkind == 0) {
-                if (ka >= 0) {
-                    int tt0, rows;
-                    chunk_at(ka, tt0, rows);
-                    if (prow < rows) {
-                        src = acts_b + (size_t)(tbase + tsign * (tt0 + prow)) * frame_stride;
-                        dst = s_lp2 + ((size_t)slot_a * TC + prow) * Vs;
-                        bytes = (unsigned)V * 4u;
-                    }
-                }
-            } else if (kp >= 0) {
-                int tt0, rows;
-                chunk_at(kp, tt0, rows);
-                if (prow < rows) {
-                    const int tt = tt0 + prow;
-                    // my in-band pairs (widened by P) <-> the partner pairs they map to
-                    const int mlo = max(S - (Tb - tt) - P, 0), mhi = min(tt + P, S);
-                    const int plo = max(S - 1 - mhi, 0) & ~3, phi = (S - mlo) | 3;
-                    const float* srow = lat_b + (size_t)(tbase + tsign * tt) * RS;
-                    float* drow = s_stage + ((size_t)slot_p * TC + prow) * RS;
-                    if (pkind == 3) {
-                        src = srow + 2 * NP; dst = drow + 2 * NP; bytes = (unsigned)(RS - 2 * NP) * 4u;
-                    } else if (phi >= plo) {
-                        const int o = (pkind == 2 ? NP : 0) + plo;
-                        src = srow + o; dst = drow + o; bytes = (unsigned)(phi - plo + 1) * 4u;
-                    }
-                }
-            }
-            // expected transaction bytes per mbarrier, then the copies
-            unsigned ba = pkind == 0 ? bytes : 0u, bp = pkind == 0 ? 0u : bytes;
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                ba += __shfl_xor_sync(0xffffffffu, ba, o);
-                bp += __shfl_xor_sync(0xffffffffu, bp, o);
-            }
+            const int prow = lane & 7;
+            int rows_a = 0, rows_p = 0, tta = 0, ttp = 0;
+            if (ka >= 0) chunk_at(ka, tta, rows_a);
+            if (kp >= 0) chunk_at(kp, ttp, rows_p);
             if (lane == 0) {
-                if (ka >= 0) mbar_expect_tx(bar_acts + slot_a, ba);
-                if (kp >= 0) mbar_expect_tx(bar_part + slot_p, bp);
+                if (ka >= 0) mbar_expect_tx(bar_acts + slot_a, (unsigned)(rows_a * V) * 4u);
+                if (kp >= 0) mbar_expect_tx(bar_part + slot_p, (unsigned)(rows_p * RS) * 4u);
             }
             __syncwarp();
-            if (bytes) bulk_g2s(dst, src, bytes, pkind == 0 ? bar_acts + slot_a : bar_part + slot_p);
+            if (lane < 8) {
+                if (prow < rows_a)
+                    bulk_g2s(s_lp2 + ((size_t)slot_a * TC + prow) * Vs,
+                             acts_b + (size_t)(tbase + tsign * (tta + prow)) * frame_stride,
+                             (unsigned)V * 4u, bar_acts + slot_a);
+            } else if (lane < 16) {
+                if (prow < rows_p)
+                    bulk_g2s(s_stage + ((size_t)slot_p * TC + prow) * RS,
+                             lat_b + (ptrdiff_t)(tbase + tsign * (ttp + prow)) * RS,
+                             (unsigned)RS * 4u, bar_part + slot_p);
+            }
         };
 
-        // ---- fused log_softmax of one staged row, in place (full warp) ----------------
-        auto softmax_row = [&](float* row) {
+        // ---- fused log_softmax, in place, of two staged rows (one per half-warp) -------
+        auto softmax2 = [&](float* row, bool act) {
             float4* row4 = reinterpret_cast<float4*>(row);
-            if (V4 <= 32) {  // the whole row is one float4 per lane
-                float4 q = make_float4(-CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F);
-                if (lane < V4) q = row4[lane];
-                const float m = warp_max(fmaxf(fmaxf(q.x, q.y), fmaxf(q.z, q.w)));
-                q.x = (q.x - m) * kLog2e; q.y = (q.y - m) * kLog2e;
-                q.z = (q.z - m) * kLog2e; q.w = (q.w - m) * kLog2e;
-                const float lz = lg2f(warp_sum((ex2f(q.x) + ex2f(q.y)) + (ex2f(q.z) + ex2f(q.w))));
-                if (lane < V4)
-                    row4[lane] = make_float4(fmaxf(q.x - lz, kNeg), fmaxf(q.y - lz, kNeg),
-                                             fmaxf(q.z - lz, kNeg), fmaxf(q.w - lz, kNeg));
+            if (V4 <= 16) {  // the whole row is one float4 per lane of the half-warp
+                float4 x = make_float4(-CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F);
+                if (q16 < V4) x = row4[q16];
+                const float m = half_max(fmaxf(fmaxf(x.x, x.y), fmaxf(x.z, x.w)));
+                x.x = (x.x - m) * kLog2e; x.y = (x.y - m) * kLog2e;
+                x.z = (x.z - m) * kLog2e; x.w = (x.w - m) * kLog2e;
+                const float lz = lg2f(half_sum((ex2f(x.x) + ex2f(x.y)) + (ex2f(x.z) + ex2f(x.w))));
+                if (act && q16 < V4)
+                    row4[q16] = make_float4(fmaxf(x.x - lz, kNeg), fmaxf(x.y - lz, kNeg),
+                                            fmaxf(x.z - lz, kNeg), fmaxf(x.w - lz, kNeg));
             } else {
                 float m = -CUDART_INF_F, z = 0.f;
-                for (int c = lane; c < V4; c += 32) {
-                    const float4 q = row4[c];
-                    m = fmaxf(m, fmaxf(fmaxf(q.x, q.y), fmaxf(q.z, q.w)));
+                for (int c = q16; c < V4; c += 16) {
+                    const float4 x = row4[c];
+                    m = fmaxf(m, fmaxf(fmaxf(x.x, x.y), fmaxf(x.z, x.w)));
                 }
-                m = warp_max(m);
-                for (int c = lane; c < V4; c += 32) {
-                    float4 q = row4[c];
-                    q.x = (q.x - m) * kLog2e; q.y = (q.y - m) * kLog2e;
-                    q.z = (q.z - m) * kLog2e; q.w = (q.w - m) * kLog2e;
-                    z += (ex2f(q.x) + ex2f(q.y)) + (ex2f(q.z) + ex2f(q.w));
-                    row4[c] = q;
+                m = half_max(m);
+                for (int c = q16; c < V4; c += 16) {
+                    const float4 x = row4[c];
+                    z += (ex2f((x.x - m) * kLog2e) + ex2f((x.y - m) * kLog2e)) +
+                         (ex2f((x.z - m) * kLog2e) + ex2f((x.w - m) * kLog2e));
                 }
-                const float lz = lg2f(warp_sum(z));
-                for (int c = lane; c < V4; c += 32) {
-                    const float4 q = row4[c];
-                    row4[c] = make_float4(fmaxf(q.x - lz, kNeg), fmaxf(q.y - lz, kNeg),
-                                          fmaxf(q.z - lz, kNeg), fmaxf(q.w - lz, kNeg));
-                }
+                const float lz = lg2f(half_sum(z));
+                if (act)
+                    for (int c = q16; c < V4; c += 16) {
+                        const float4 x = row4[c];
+                        row4[c] = make_float4(fmaxf((x.x - m) * kLog2e - lz, kNeg), fmaxf((x.y - m) * kLog2e - lz, kNeg),
+                                              fmaxf((x.z - m) * kLog2e - lz, kNeg), fmaxf((x.w - m) * kLog2e - lz, kNeg));
+                    }
             }
-            if (lane == 0) row[V] = kNeg;  // what padding pairs gather
+            if (act && q16 == 0) row[V] = kNeg;  // what padding pairs gather
         };
 
-        // ---- gradient row: occupancies -> class sums -> softmax - occupancy ----------
-        //   blank cells: plain sum.  label cells are stored class-sorted, so the sum of
-        //   class v is PS[cstart[v+1]] - PS[cstart[v]] of their exclusive prefix sums PS.
-        auto grad_row = [&](float* erow, float* lp2row, float* g, bool infeasible) {
+        // ---- gradient of two frames (one per half-warp) ---------------------------------
+        //   blank cells: plain sum.  Label cells are stored class-sorted (padded layout
+        //   ypad), lane q of the half owns 16 consecutive sorted cells per 256-cell round;
+        //   the sum of class v is PS[cstart[v+1]] - PS[cstart[v]] of the exclusive prefix
+        //   sums PS, which overwrite the occupancy exponents in place.
+        auto grad2 = [&](float* erow, const float* lp2row, float* g, bool act, bool infeasible) {
             if (infeasible) {
                 const float fill = p.zero_infinity ? 0.0f : CUDART_NAN_F;
-                for (int c = lane; c < V4; c += 32)
-                    reinterpret_cast<float4*>(g)[c] = make_float4(fill, fill, fill, fill);
+                if (act) for (int v = q16; v < V; v += 16) g[v] = fill;
                 return;
             }
-            float4* eB4 = reinterpret_cast<float4*>(erow);
-            float4* eY4 = reinterpret_cast<float4*>(erow + NP);
-            float bs = 0.f, carry = 0.f;
-            for (int c = lane; c * 4 <= S; c += 32) {           // blanks 0..S (padding holds kNeg)
-                const float4 q = eB4[c];
-                bs += (ex2f(q.x) + ex2f(q.y)) + (ex2f(q.z) + ex2f(q.w));
+            const float4* eB4 = reinterpret_cast<const float4*>(erow);
+            float bs = 0.f;
+            for (int c = q16; c * 4 <= S; c += 16) {            // blanks 0..S (padding holds kNeg)
+                const float4 x = eB4[c];
+                bs += (ex2f(x.x) + ex2f(x.y)) + (ex2f(x.z) + ex2f(x.w));
             }
-            bs = warp_sum(bs);
-            for (int base = 0; base < S; base += 128) {         // labels: 128 cells per round
-                const int c = (base >> 2) + lane;
-                float4 q = make_float4(kNeg, kNeg, kNeg, kNeg);
-                if (c * 4 < NP) q = eY4[c];                     // slots in [S, NP) hold kNeg -> 0
-                const float o0 = ex2f(q.x), o1 = o0 + ex2f(q.y), o2 = o1 + ex2f(q.z), o3 = o2 + ex2f(q.w);
-                float inc = o3;                                 // inclusive scan of the lane totals
+            bs = half_sum(bs);
+            float carry = 0.f;                                  // labels: 256 sorted cells per round
+            float* eY = erow + NP;
+            for (int base = 0; base < S; base += 256) {
+                const int k0 = base + 16 * q16;                 // my 16 consecutive sorted cells
+                float4* c4 = reinterpret_cast<float4*>(eY + ypad(k0));
+                float o[16];
+                const bool in = k0 < NP;                        // cells in [S, NP) hold kNeg -> 0
 #pragma unroll
-                for (int o = 1; o < 32; o <<= 1) {
-                    const float y = __shfl_up_sync(0xffffffffu, inc, o);
-                    if (lane >= o) inc += y;
+                for (int j = 0; j < 4; ++j) {
+                    float4 x = make_float4(kNeg, kNeg, kNeg, kNeg);
+                    if (in) x = c4[j];
+                    o[4 * j] = ex2f(x.x); o[4 * j + 1] = ex2f(x.y); o[4 * j + 2] = ex2f(x.z); o[4 * j + 3] = ex2f(x.w);
                 }
-                const float ex = carry + (inc - o3);            // exclusive prefix of this lane
-                if (c * 4 < NP) eY4[c] = make_float4(ex, ex + o0, ex + o1, ex + o2);   // PS[4c..4c+3]
-                carry += __shfl_sync(0xffffffffu, inc, 31);
+                float run = 0.f;                                // exclusive prefix inside my 16 cells
+#pragma unroll
+                for (int j = 0; j < 16; ++j) { const float t = o[j]; o[j] = run; run += t; }
+                float inc = run;                                // inclusive scan over the 16 lanes
+#pragma unroll
+                for (int s = 1; s < 16; s <<= 1) {
+                    const float y = __shfl_up_sync(0xffffffffu, inc, s, 16);
+                    if (q16 >= s) inc += y;
+                }
+                const float ex = carry + (inc - run);
+                if (in && act) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        c4[j] = make_float4(ex + o[4 * j], ex + o[4 * j + 1], ex + o[4 * j + 2], ex + o[4 * j + 3]);
+                }
+                carry += __shfl_sync(0xffffffffu, inc, 15, 16);
             }
             __syncwarp();
-            const float* PS = erow + NP;                        // PS[k] = sum of sorted cells < k
-            for (int v = lane; v < V; v += 32) {
-                const int k0 = s_cstart[v], k1 = s_cstart[v + 1];
-                const float hi = (k1 < S) ? PS[k1] : carry;     // PS[S] = total
-                const float lo = (k0 < S) ? PS[k0] : carry;
-                const float occ = (hi - lo) + (v == blank ? bs : 0.f);
-                lp2row[v] = gscale * (ex2f(lp2row[v]) - occ);
-            }
-            __syncwarp();
-            for (int c = lane; c < V4; c += 32)                 // coalesced 128-bit row store
-                reinterpret_cast<float4*>(g)[c] = reinterpret_cast<const float4*>(lp2row)[c];
+            if (act)
+                for (int v = q16; v < V; v += 16) {
+                    const int k0 = s_cstart[v], k1 = s_cstart[v + 1];
+                    const float hi = (k1 < S) ? eY[ypad(k1)] : carry;   // PS[S] = total
+                    const float lo = (k0 < S) ? eY[ypad(k0)] : carry;
+                    const float occ = (hi - lo) + (v == blank ? bs : 0.f);
+                    g[v] = gscale * (ex2f(lp2row[v]) - occ);
+                }
         };
 
         // ---- the helper schedule ---------------------------------------------------------
@@ -604,9 +701,11 @@ ctc_pipe_kernel(const PipeParams pp) {
         //                  softmax chunk it;  gradient rows of chunk it-2.
         // (REC runs chunk it-1.)  Partner rows of the first D+1 consume chunks cannot be
         // requested before the partner CTA wrote them: they are issued at the phase break.
+        // The last helper issues the logit copies, helper 0 the partner copies.
+        const bool iss_acts = hw == H - 1, iss_part = hw == 0;
         Ring iss_a(NL), iss_p(NS), sm_a(NL), gr_a(NL);
         int gr_e = 0;
-        if (hw == 0) {
+        if (iss_acts) {
             for (int k = 0; k <= D; ++k) {            // prologue: logits of chunks 0..D
                 if (k < nch) issue_chunk(k, iss_a.slot, -1, 0);
                 iss_a.advance();
@@ -614,58 +713,49 @@ ctc_pipe_kernel(const PipeParams pp) {
         }
         for (int it = 0; it < nch + 2; ++it) {
             PROF_BEGIN();
-            PROF_MARK(8);
-            if (hw == 0) {
+            {
                 const int ka = it + D + 1, kp = it + D;
-                const bool do_a = ka < nch, do_p = want_grad && it >= n1 + 1 && kp < nch;
+                const bool do_a = iss_acts && ka < nch;
+                const bool do_p = iss_part && want_grad && it >= n1 + 1 && kp < nch;
                 if (do_a || do_p) issue_chunk(do_a ? ka : -1, iss_a.slot, do_p ? kp : -1, iss_p.slot);
                 iss_a.advance();
                 if (it >= n1 + 1) iss_p.advance();
             }
-            if (it < nch) {                           // softmax of chunk `it`
+            if (it < nch) {                           // softmax of chunk `it`, two rows per pass
                 int tt0, rows;
                 chunk_at(it, tt0, rows);
-#ifdef CTC_B200_PROFILE
-                { long long tw = clock64();
-#endif
                 mbar_wait(bar_acts + sm_a.slot, sm_a.parity);
-#ifdef CTC_B200_PROFILE
-                  if (prof_on && w == R) atomicAdd(prof + 12, (unsigned long long)(clock64() - tw)); }
-#endif
-#ifndef CTC_B200_NOHELP
-                for (int r = hw; r < rows; r += H)
-                    softmax_row(s_lp2 + ((size_t)sm_a.slot * TC + r) * Vs);
-#endif
+                float* base = s_lp2 + (size_t)sm_a.slot * TC * Vs;
+                for (int r0 = 2 * hw; r0 < rows; r0 += 2 * H) {
+                    const int r = r0 + half;
+                    softmax2(base + min(r, rows - 1) * Vs, r < rows);
+                }
+                fence_proxy_async_smem();   // generic writes to the slot precede its next TMA fill
             }
             sm_a.advance();
-            PROF_MARK(6);
             const int kg = it - 2;
             if (kg >= 0) {
                 if (want_grad && kg >= n1 && kg < nch) {   // gradient rows of chunk it-2
                     int tt0, rows;
                     chunk_at(kg, tt0, rows);
                     const bool infeasible = s_ll[2] != 0.f;
-#ifndef CTC_B200_NOHELP
-                    for (int r = hw; r < rows; r += H)
-#else
-                    for (int r = hw; r < 0; r += H)
-#endif
-                        grad_row(s_e + ((size_t)gr_e * TC + r) * ER,
-                                 s_lp2 + ((size_t)gr_a.slot * TC + r) * Vs,
-                                 grad_b + (size_t)(tbase + tsign * (tt0 + r)) * frame_stride, infeasible);
+                    for (int r0 = 2 * hw; r0 < rows; r0 += 2 * H) {
+                        const int r = min(r0 + half, rows - 1);
+                        grad2(s_e + ((size_t)gr_e * TC + r) * ER, s_lp2 + ((size_t)gr_a.slot * TC + r) * Vs,
+                              grad_b + (size_t)(tbase + tsign * (tt0 + r)) * frame_stride,
+                              r0 + half < rows, infeasible);
+                    }
                     gr_e ^= 1;
-                    fence_proxy_async();   // my generic writes to the lp2 slot precede its next TMA fill
                 }
                 gr_a.advance();
             }
-            PROF_MARK(7);
             PROF_END();
             __syncthreads();
             if (it == n1) {
                 // Phase break: my REC warps have stored every row the partner will consume,
                 // and (after the cluster barrier) vice versa.
                 cluster_sync_all();
-                if (hw == 0) {
+                if (iss_part) {
                     fence_proxy_async();
                     for (int k = n1; k <= n1 + D; ++k) {
                         if (k < nch && (want_grad || k == n1)) issue_chunk(-1, 0, k, iss_p.slot);

@@ -15,5 +15,4 @@ for wl in sys.argv[1:] or ["C1", "C2"]:
     c = prob.ws[64:64 + 8*14].cpu().view(torch.int64).tolist()
     it = max(c[4], 1)
     print(wl, cabi.geometry(acts.shape[0], acts.shape[1], acts.shape[2], prob.S_max))
-    print(f"  CTA0 T_b={c[5]} iterations={c[4]} total={c[3]} cyc ({c[3]/max(c[5],1):.0f}/step) | busy per iteration: REC {c[0]/it:.0f}  HELP0 {c[1]/it:.0f} (issue {c[8]/it:.0f} softmax {c[6]/it:.0f} grad {c[7]/it:.0f})  HELP1 {c[2]/it:.0f}  | wall per iteration {c[3]/it:.0f}")
-    print(f"  REC: mbar_wait total {c[9]}  store-phase busy total {c[10]}  consume-phase busy total {c[11]} | HELP0 mbar_wait total {c[12]} of busy {c[1]}")
+    print(f"  CTA0 T_b={c[5]} iterations={c[4]} total={c[3]} cyc ({c[3]/max(c[5],1):.0f}/step) | busy per iteration: REC {c[0]/it:.0f}  HELP0 {c[1]/it:.0f}  HELP1 {c[2]/it:.0f}  | wall per iteration {c[3]/it:.0f}")
