@@ -16,6 +16,8 @@
 #include <ATen/cuda/CUDAContext.h>
 #include <c10/cuda/CUDAGuard.h>
 
+#include <cstdarg>
+#include <cstdio>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -28,15 +30,29 @@ void check_status(int rc, const char* what) {
     if (rc == CTC_B200_OK) return;
     std::string msg = std::string(what) + ": " + ctc_b200_status_string(rc);
     if (rc == CTC_B200_CUDA_ERROR) msg += std::string(" (") + ctc_b200_last_cuda_error() + ")";
-    TORCH_CHECK(false, msg);
+    TORCH_CHECK(false, msg.c_str());
+}
+
+// Error messages are formatted with vsnprintf and handed to TORCH_CHECK as ONE const char*:
+// in this toolchain any std::ostringstream instantiated inside an extension translation
+// unit that includes the torch headers crashes (c10::str goes through one), so the
+// multi-argument form of TORCH_CHECK must not be used here.
+[[noreturn]] void fail(const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    TORCH_CHECK(false, buf);
+    throw std::runtime_error(buf);  // not reached
 }
 
 size_t up16(size_t x) { return (x + 15) / 16 * 16; }
 
 std::vector<int64_t> lengths_to_host(const torch::Tensor& t, int64_t N, const char* name) {
-    TORCH_CHECK(t.dim() == 1 && t.size(0) == N, name, " must have shape [N=", N, "]");
-    TORCH_CHECK(t.scalar_type() == torch::kInt32 || t.scalar_type() == torch::kInt64, name,
-                " must be int32 or int64");
+    if (!(t.dim() == 1 && t.size(0) == N)) fail("%s must have shape [N=%lld]", name, (long long)N);
+    if (!(t.scalar_type() == torch::kInt32 || t.scalar_type() == torch::kInt64))
+        fail("%s must be int32 or int64", name);
     torch::Tensor c = t.to(torch::kCPU, torch::kInt64).contiguous();  // syncs iff CUDA resident
     const int64_t* p = c.data_ptr<int64_t>();
     return std::vector<int64_t>(p, p + N);
@@ -54,7 +70,6 @@ std::vector<torch::Tensor> forward(const torch::Tensor& acts, const torch::Tenso
     TORCH_CHECK(acts.scalar_type() == torch::kFloat32, "ctc_b200: acts must be float32");
     TORCH_CHECK(acts.dim() == 3, "ctc_b200: acts must be [T, N, V]");
     TORCH_CHECK(reduction >= 0 && reduction <= 2, "ctc_b200: bad reduction");
-    const c10::cuda::CUDAGuard guard(acts.device());
     torch::Tensor x = acts.contiguous();
     const int64_t T = x.size(0), N = x.size(1), V = x.size(2);
     TORCH_CHECK(blank >= 0 && blank < V, "ctc_b200: blank must be in label range");
@@ -64,10 +79,11 @@ std::vector<torch::Tensor> forward(const torch::Tensor& acts, const torch::Tenso
     const std::vector<int64_t> tl = lengths_to_host(target_lengths, N, "target_lengths");
     int64_t S_max = 0, total = 0;
     for (int64_t b = 0; b < N; ++b) {
-        TORCH_CHECK(il[b] >= 0 && il[b] <= T, "Expected input_lengths to have value at most ", T,
-                    ", but got value ", il[b]);
-        TORCH_CHECK(tl[b] >= 0, "Expected target_lengths to have value at least 0, but got value ",
-                    tl[b]);
+        if (!(il[b] >= 0 && il[b] <= T))
+            fail("Expected input_lengths to have value at most %lld, but got value %lld", (long long)T,
+                 (long long)il[b]);
+        if (tl[b] < 0)
+            fail("Expected target_lengths to have value at least 0, but got value %lld", (long long)tl[b]);
         S_max = std::max(S_max, tl[b]);
         total += tl[b];
     }
@@ -82,8 +98,25 @@ std::vector<torch::Tensor> forward(const torch::Tensor& acts, const torch::Tenso
         TORCH_CHECK(targets.size(0) >= total, "ctc_b200: concatenated targets shorter than sum(target_lengths)");
     }
 
-    // ---- one pinned staging block: [targets | offsets | in_lens | tgt_lens | scale] ----
     const bool tg_on_host = !targets.is_cuda();
+    if (tg_on_host) {   // host-resident labels (the reference's case) are validated here, for free
+        torch::Tensor tc = targets.contiguous();
+        auto check = [&](auto* src) {
+            const int64_t stride = padded ? tc.size(1) : 0;
+            for (int64_t b = 0, k = 0; b < N; ++b)
+                for (int64_t j = 0; j < tl[b]; ++j, ++k) {
+                    const int64_t c = padded ? (int64_t)src[b * stride + j] : (int64_t)src[k];
+                    if (!(c >= 0 && c < V))
+                        fail("ctc_b200: target label %lld outside [0, %lld)", (long long)c, (long long)V);
+                }
+        };
+        if (tc.scalar_type() == torch::kInt32) check(tc.data_ptr<int32_t>());
+        else check(tc.data_ptr<int64_t>());
+    }
+    // every argument check is done; from here on work is enqueued on acts' device
+    const c10::cuda::CUDAGuard guard(acts.device());
+
+    // ---- one pinned staging block: [targets | offsets | in_lens | tgt_lens | scale] ----
     const size_t o_tg = 0;
     const size_t o_off = up16((size_t)std::max<int64_t>(total, 1) * 4);
     const size_t o_il = o_off + up16((size_t)N * 4);
@@ -121,9 +154,6 @@ std::vector<torch::Tensor> forward(const torch::Tensor& acts, const torch::Tenso
         };
         if (tc.scalar_type() == torch::kInt32) put(tc.data_ptr<int32_t>());
         else put(tc.data_ptr<int64_t>());
-        for (int64_t k = 0; k < total; ++k)
-            TORCH_CHECK(h_tg[k] >= 0 && h_tg[k] < V, "ctc_b200: target label ", h_tg[k],
-                        " outside [0, ", V, ")");
     } else {
         // CUDA-resident targets: pack on the device (rare path; torch syncs here as well)
         if (padded) {

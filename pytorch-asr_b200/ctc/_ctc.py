@@ -75,7 +75,9 @@ class _CTCFunction(torch.autograd.Function):
     def forward(ctx, acts, targets, input_lengths, target_lengths, blank, reduction,
                 zero_infinity, group):
         native = load_native()
-        want_grad = bool(acts.requires_grad) and torch.is_grad_enabled()
+        # (grad mode is off inside Function.forward; needs_input_grad is what says whether
+        # backward will be asked for d loss / d acts)
+        want_grad = bool(ctx.needs_input_grad[0])
         loss, nll, grad, out2 = native.forward(acts, targets, input_lengths, target_lengths,
                                                int(blank), int(reduction), bool(zero_infinity),
                                                want_grad)
@@ -85,9 +87,12 @@ class _CTCFunction(torch.autograd.Function):
         if group is not None and reduction != 0:
             loss, ctx.world_scale = global_loss(out2, nll.numel(), reduction, group)
         ctx.save_for_backward(grad)
-        ctx.mark_non_differentiable(nll)
+        # second output: per-utterance nll for logging, never differentiated (a view, so that
+        # for reduction='none' it is a different tensor object from the differentiable output)
+        nll_info = nll.view_as(nll)
+        ctx.mark_non_differentiable(nll_info)
         out = nll if reduction == 0 else loss
-        return out, nll
+        return out, nll_info
 
     @staticmethod
     def backward(ctx, grad_out, _grad_nll):

@@ -23,7 +23,7 @@ sources = ["csrc/ctc_binding.cc"]
 include_dirs = [str(here.parent / "include"), os.path.join(cuda_home, "include")]
 extra_compile_args = ["-std=c++17", "-O2", "-w", "-fPIC"]
 library_dirs = [str(here / "torch_asr"), os.path.join(cuda_home, "lib64")]
-libraries = ["ctc_b200", "cudart", "c10_cuda", "torch_cuda"]
+libraries = ["ctc_b200", "c10_cuda", "torch_cuda"]
 
 setup(
     name="torch_asr",
