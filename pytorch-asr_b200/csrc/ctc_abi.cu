@@ -181,6 +181,7 @@ int launch_pipe_pt(const PipeParams& pp, const Geometry& g, int n_utt, cudaStrea
 template <int P>
 int launch_pipe_p(const PipeParams& pp, const Geometry& g, int n_utt, cudaStream_t st) {
     if (g.NT <= 128) return launch_pipe_pt<P, 128, 4>(pp, g, n_utt, st);
+    if (g.NT <= 160) return launch_pipe_pt<P, 160, 4>(pp, g, n_utt, st);
     if (g.NT <= 256) return launch_pipe_pt<P, 256, 2>(pp, g, n_utt, st);
     if (g.NT <= 512) return launch_pipe_pt<P, 512, 1>(pp, g, n_utt, st);
     return launch_pipe_pt<P, 1024, 1>(pp, g, n_utt, st);

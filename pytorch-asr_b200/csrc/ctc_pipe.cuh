@@ -93,6 +93,11 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned by
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
+// make `bar` observe the completion of all cp.async copies this thread issued so far; counts
+// as one of the barrier's expected arrivals (the logits barriers expect 32: one per lane)
+__device__ __forceinline__ void cp_async_arrive(uint64_t* bar) {
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async_smem() {
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -198,7 +203,8 @@ ctc_pipe_kernel(const PipeParams pp) {
     for (int i = tid; i < 2 * (R + 1); i += NT) s_bnd[i] = make_float2(kNeg, 0.f);
     if (tid == 0) {
         s_ll[0] = 0.f; s_ll[1] = 0.f; s_ll[2] = 0.f;
-        for (int i = 0; i < NL + NS; ++i) mbar_init(bar_acts + i, 1);
+        for (int i = 0; i < NL; ++i) mbar_init(bar_acts + i, 32);   // 32 lanes' cp.async
+        for (int i = 0; i < NS; ++i) mbar_init(bar_part + i, 1);    // one TMA producer
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         fence_proxy_async();
     }
@@ -270,7 +276,10 @@ ctc_pipe_kernel(const PipeParams pp) {
     const long long prof_start = prof_t0;
 #define PROF_BEGIN() do { prof_t0 = clock64(); } while (0)
 #define PROF_END() do { if (prof_on) atomicAdd(prof + prof_slot, (unsigned long long)(clock64() - prof_t0)); } while (0)
+#define PROF_SEC(slot) do { if (prof_on && w == R) atomicAdd(prof + (slot), (unsigned long long)(clock64() - prof_t1)); prof_t1 = clock64(); } while (0)
+    long long prof_t1 = prof_t0;
 #else
+#define PROF_SEC(slot) do {} while (0)
 #define PROF_BEGIN() do {} while (0)
 #define PROF_END() do {} while (0)
 #endif
@@ -423,7 +432,10 @@ ctc_pipe_kernel(const PipeParams pp) {
                 } else {
                     // ---- consume chunk: combine with the partner's stored rows ----------
                     mbar_wait(bar_part + ring_part.slot, ring_part.parity);   // TMA data landed
-                    const float* st = s_stage + (size_t)ring_part.slot * TC * rs_i;
+                    // the chunk was staged as one block in frame order: for the reversed sweep
+                    // its rows run backwards, so start at the last one and step by -RS
+                    const float* st = s_stage + ((size_t)ring_part.slot * TC + (rev ? rows - 1 : 0)) * rs_i;
+                    const int st_step = (int)row_step;
                     float* erow = s_e + (size_t)e_buf * TC * er_i;
                     const float* stp = st + jB0;                 // partner blank of my pair q: stp[-q]
                     const float* sto_hi = st + 2 * np_i + pw_hi; // partner warp offsets
@@ -498,7 +510,7 @@ ctc_pipe_kernel(const PipeParams pp) {
                             store_vec<P>(erow + i0, eBv);
                         }
                         end_step();
-                        r = 1; lp2 += vs_i; stp += rs_i; sto_hi += rs_i; sto_lo += rs_i; erow += er_i;
+                        r = 1; lp2 += vs_i; stp += st_step; sto_hi += st_step; sto_lo += st_step; erow += er_i;
                     }
                     if (wg) {
                         // a + partner - lp + (offsets - ll): the integer parts combine exactly
@@ -524,7 +536,7 @@ ctc_pipe_kernel(const PipeParams pp) {
                             }
                         };
                         if (steady) {
-                            for (; r < rows; ++r, lp2 += vs_i, stp += rs_i, sto_hi += rs_i, sto_lo += rs_i, erow += er_i) {
+                            for (; r < rows; ++r, lp2 += vs_i, stp += st_step, sto_hi += st_step, sto_lo += st_step, erow += er_i) {
                                 float eBv[P], eYv[P], lpb, lpl[P];
 #pragma unroll
                                 for (int q = 0; q < P; ++q) { eBv[q] = kNeg; eYv[q] = kNeg; }
@@ -538,7 +550,7 @@ ctc_pipe_kernel(const PipeParams pp) {
                             }
                             if (renorm_after) renorm();
                         } else {
-                            for (; r < rows; ++r, lp2 += vs_i, stp += rs_i, sto_hi += rs_i, sto_lo += rs_i, erow += er_i) {
+                            for (; r < rows; ++r, lp2 += vs_i, stp += st_step, sto_hi += st_step, sto_lo += st_step, erow += er_i) {
                                 const int tt = tt0 + r;
                                 float eBv[P], eYv[P];
 #pragma unroll
@@ -574,30 +586,37 @@ ctc_pipe_kernel(const PipeParams pp) {
         // =============================================================================
         const int half = lane >> 4, q16 = lane & 15;   // a helper handles two frames at a time
 
-        // ---- TMA issue of one chunk: one bulk copy per row ------------------------------
-        //   lanes 0..7  : logits row `lane` of chunk ka              -> lp2 ring slot
-        //   lanes 8..15 : the partner's whole lattice row of chunk kp -> partner ring slot
-        //   (whole rows: regions the partner never wrote are copied but never read)
+        // ---- staging of one chunk -------------------------------------------------------------
+        //   logits rows of chunk ka : cp.async (LDGSTS, 16 B per lane and copy) by all 32 lanes,
+        //                             completion signalled on the slot's mbarrier
+        //   partner rows of chunk kp: ONE TMA bulk copy (the rows of a chunk are contiguous in
+        //                             the lattice); regions the partner never wrote are copied
+        //                             but never read
+        // per-lane (row, float4) position of its first logits copy; later copies are 32 float4 on
+        int a_r0 = 0, a_c0 = lane;
+        while (a_c0 >= V4) { a_c0 -= V4; ++a_r0; }
+        const ptrdiff_t a_inc = (ptrdiff_t)tsign * (ptrdiff_t)frame_stride;
         auto issue_chunk = [&](int ka, int slot_a, int kp, int slot_p) {
-            const int prow = lane & 7;
-            int rows_a = 0, rows_p = 0, tta = 0, ttp = 0;
-            if (ka >= 0) chunk_at(ka, tta, rows_a);
-            if (kp >= 0) chunk_at(kp, ttp, rows_p);
-            if (lane == 0) {
-                if (ka >= 0) mbar_expect_tx(bar_acts + slot_a, (unsigned)(rows_a * V) * 4u);
-                if (kp >= 0) mbar_expect_tx(bar_part + slot_p, (unsigned)(rows_p * RS) * 4u);
+            if (ka >= 0) {
+                int tt0, rows;
+                chunk_at(ka, tt0, rows);
+                float* dst = s_lp2 + (size_t)slot_a * TC * Vs;
+                const float* src = acts_b + (ptrdiff_t)(tbase + tsign * tt0) * (ptrdiff_t)frame_stride;
+                for (int r = a_r0, c = a_c0; r < rows;) {
+                    cp_async16(dst + r * Vs + 4 * c, src + r * a_inc + 4 * c);
+                    c += 32;
+                    while (c >= V4) { c -= V4; ++r; }
+                }
+                cp_async_arrive(bar_acts + slot_a);
             }
-            __syncwarp();
-            if (lane < 8) {
-                if (prow < rows_a)
-                    bulk_g2s(s_lp2 + ((size_t)slot_a * TC + prow) * Vs,
-                             acts_b + (size_t)(tbase + tsign * (tta + prow)) * frame_stride,
-                             (unsigned)V * 4u, bar_acts + slot_a);
-            } else if (lane < 16) {
-                if (prow < rows_p)
-                    bulk_g2s(s_stage + ((size_t)slot_p * TC + prow) * RS,
-                             lat_b + (ptrdiff_t)(tbase + tsign * (ttp + prow)) * RS,
-                             (unsigned)RS * 4u, bar_part + slot_p);
+            if (kp >= 0 && lane == 0) {
+                int tt0, rows;
+                chunk_at(kp, tt0, rows);
+                uint64_t* bar = bar_part + slot_p;
+                const int t_lo = rev ? tbase - (tt0 + rows - 1) : tt0;
+                mbar_expect_tx(bar, (unsigned)(rows * RS) * 4u);
+                bulk_g2s(s_stage + (size_t)slot_p * TC * RS, lat_b + (ptrdiff_t)t_lo * RS,
+                         (unsigned)(rows * RS) * 4u, bar);
             }
         };
 
@@ -702,7 +721,18 @@ ctc_pipe_kernel(const PipeParams pp) {
         // (REC runs chunk it-1.)  Partner rows of the first D+1 consume chunks cannot be
         // requested before the partner CTA wrote them: they are issued at the phase break.
         // The last helper issues the logit copies, helper 0 the partner copies.
-        const bool iss_acts = hw == H - 1, iss_part = hw == 0;
+        // Work of one iteration = TMA issue + softmax passes + gradient passes (a pass = two
+        // rows).  Dealing: H=1 all; H=2 (TMA partner, S0, G0 | TMA logits, S1, G1);
+        // H>=3 (TMA, S0 | G0, S1 | G1 ...): softmax passes go to helpers 0/1, gradient passes
+        // to the last two helpers, the TMA issue to helper 0.
+        int wgh_i = want_grad ? 1 : 0;
+        asm volatile("" : "+r"(wgh_i));                  // keep the flag in a register
+        const bool wgh = wgh_i != 0;
+        const bool iss_acts = H >= 3 ? hw == 0 : hw == H - 1, iss_part = hw == 0;
+        const int n_sm = min(H, 2), n_gr = min(H, 2), gr_base = H - n_gr;
+        const bool do_sm = hw < n_sm, do_gr = hw >= gr_base;
+        const int sm_first = 2 * hw, sm_step = 2 * n_sm;
+        const int gr_first = 2 * (hw - gr_base), gr_step = 2 * n_gr;
         Ring iss_a(NL), iss_p(NS), sm_a(NL), gr_a(NL);
         int gr_e = 0;
         if (iss_acts) {
@@ -713,33 +743,23 @@ ctc_pipe_kernel(const PipeParams pp) {
         }
         for (int it = 0; it < nch + 2; ++it) {
             PROF_BEGIN();
+            PROF_SEC(13);
             {
                 const int ka = it + D + 1, kp = it + D;
                 const bool do_a = iss_acts && ka < nch;
-                const bool do_p = iss_part && want_grad && it >= n1 + 1 && kp < nch;
+                const bool do_p = iss_part && wgh && it >= n1 + 1 && kp < nch;
                 if (do_a || do_p) issue_chunk(do_a ? ka : -1, iss_a.slot, do_p ? kp : -1, iss_p.slot);
                 iss_a.advance();
                 if (it >= n1 + 1) iss_p.advance();
             }
-            if (it < nch) {                           // softmax of chunk `it`, two rows per pass
-                int tt0, rows;
-                chunk_at(it, tt0, rows);
-                mbar_wait(bar_acts + sm_a.slot, sm_a.parity);
-                float* base = s_lp2 + (size_t)sm_a.slot * TC * Vs;
-                for (int r0 = 2 * hw; r0 < rows; r0 += 2 * H) {
-                    const int r = r0 + half;
-                    softmax2(base + min(r, rows - 1) * Vs, r < rows);
-                }
-                fence_proxy_async_smem();   // generic writes to the slot precede its next TMA fill
-            }
-            sm_a.advance();
+            // gradient first: its inputs are on chip already, the logits TMA gets more time
             const int kg = it - 2;
             if (kg >= 0) {
-                if (want_grad && kg >= n1 && kg < nch) {   // gradient rows of chunk it-2
+                if (do_gr && wgh && kg >= n1 && kg < nch) {   // gradient rows of chunk it-2
                     int tt0, rows;
                     chunk_at(kg, tt0, rows);
                     const bool infeasible = s_ll[2] != 0.f;
-                    for (int r0 = 2 * hw; r0 < rows; r0 += 2 * H) {
+                    for (int r0 = gr_first; r0 < rows; r0 += gr_step) {
                         const int r = min(r0 + half, rows - 1);
                         grad2(s_e + ((size_t)gr_e * TC + r) * ER, s_lp2 + ((size_t)gr_a.slot * TC + r) * Vs,
                               grad_b + (size_t)(tbase + tsign * (tt0 + r)) * frame_stride,
@@ -749,6 +769,20 @@ ctc_pipe_kernel(const PipeParams pp) {
                 }
                 gr_a.advance();
             }
+            PROF_SEC(10);
+            if (do_sm && it < nch) {                  // softmax of chunk `it`, two rows per pass
+                int tt0, rows;
+                chunk_at(it, tt0, rows);
+                mbar_wait(bar_acts + sm_a.slot, sm_a.parity);
+                PROF_SEC(7);
+                float* base = s_lp2 + (size_t)sm_a.slot * TC * Vs;
+                for (int r0 = sm_first; r0 < rows; r0 += sm_step) {
+                    const int r = r0 + half;
+                    softmax2(base + min(r, rows - 1) * Vs, r < rows);
+                }
+                PROF_SEC(8);
+            }
+            sm_a.advance();
             PROF_END();
             __syncthreads();
             if (it == n1) {
@@ -758,7 +792,7 @@ ctc_pipe_kernel(const PipeParams pp) {
                 if (iss_part) {
                     fence_proxy_async();
                     for (int k = n1; k <= n1 + D; ++k) {
-                        if (k < nch && (want_grad || k == n1)) issue_chunk(-1, 0, k, iss_p.slot);
+                        if (k < nch && (wgh || k == n1)) issue_chunk(-1, 0, k, iss_p.slot);
                         iss_p.advance();
                     }
                 }
