@@ -229,7 +229,7 @@ def main():
         cabi._check(prob.lib.ctc_b200_reduce_loss_f32(
             prob.nll.data_ptr(), prob.tgt_lens.data_ptr(), B, cabi.REDUCE_MEAN,
             prob.out2.data_ptr(), prob.loss.data_ptr(), st.cuda_stream), "reduce")
-        launches += 2
+        launches += 3 if geo["kernel"] == 2 else 2   # fused kernel (+ its fallback launch) + loss reduction
         if dist is not None:
             dist.all_reduce(prob.out2)
         e2.record(st)
@@ -292,7 +292,7 @@ def main():
             "geometry": geo, "loss": loss,
         },
         "roofline": {
-            "bound": "hbm", "kernel": "ctc_fused_kernel<1>", "achieved": ach_s, "peak": peak,
+            "bound": "hbm", "kernel": {2: "ctc_lin_kernel", 1: "ctc_pipe_kernel", 0: "ctc_fused_kernel"}[geo["kernel"]], "achieved": ach_s, "peak": peak,
             "unit": "GB/s", "frac": ach_s / peak, "traffic": _traffic(workload),
             "peak_source": peak_src, "kernel_ms": kern_ms,
             "algorithmic_bytes": bytes_s, "definition": "(S) logits read + grad write + one fp32 lattice written and read once, exact lengths",

@@ -26,6 +26,7 @@ def _newer(target, sources):
 def build_abi(force=False, verbose=False):
     out = os.path.join(HERE, "torch_asr", "libctc_b200.so")
     srcs = [os.path.join(HERE, "csrc", "ctc_abi.cu"), os.path.join(HERE, "csrc", "ctc_kernels.cuh"),
+            os.path.join(HERE, "csrc", "ctc_pipe.cuh"), os.path.join(HERE, "csrc", "ctc_lin.cuh"),
             os.path.join(HERE, "..", "include", "ctc_b200.h")]
     if force or _newer(out, srcs):
         nvcc = os.path.join(os.environ.get("CUDA_HOME", "/usr/local/cuda"), "bin", "nvcc")

@@ -5,6 +5,7 @@
 // libctc_b200.so with nvcc alone and is what a non-Python caller links.
 #include "ctc_kernels.cuh"
 #include "ctc_pipe.cuh"
+#include "ctc_lin.cuh"
 #include "../../include/ctc_b200.h"
 
 #include <algorithm>
@@ -36,11 +37,19 @@ inline int cuda_fail(cudaError_t e) {
     } while (0)
 
 struct Geometry {
-    int pipe;       // 1: warp-specialised kernel (ctc_pipe.cuh), 0: generic kernel (ctc_kernels.cuh)
+    int pipe;       // 2: linear-domain kernel (ctc_lin.cuh) with the log-domain pipe kernel as its
+                    //    per-utterance fallback, 1: log-domain pipe kernel (ctc_pipe.cuh),
+                    // 0: generic kernel (ctc_kernels.cuh)
     int P, NT, W, NP, chunk, RS, smem;
     int R, G, D;    // pipe only: recursion / gradient warps, fetch distance in chunks
     size_t lat_utt_stride;  // floats
+    // pipe == 2: geometry of the linear kernel (the fields above describe the fallback)
+    int lP, lNT, lNP, lchunk, lRS, lsmem, lR, lH, lD, lYS;
+    size_t l_lat_utt_stride;
+    size_t lattice_floats_per_utt() const { return pipe == 2 ? std::max(lat_utt_stride, l_lat_utt_stride) : lat_utt_stride; }
 };
+
+inline size_t flag_bytes(int n_utt) { return ((size_t)std::max(n_utt, 1) * 8 + 255) / 256 * 256; }
 
 int env_int(const char* name, int dflt) {
     const char* e = std::getenv(name);
@@ -122,6 +131,45 @@ bool pick_pipe(int T, int V, int pairs, int n_utt, Geometry* g) {
     return false;
 }
 
+// Linear-domain kernel: R recursion warps with P pairs per thread in registers (P = 8 covers 256
+// lattice slots per warp), H helper warps.  Needs S_max + P <= 32 * P * R slots (alignment shift).
+bool pick_lin(int T, int V, int S_max, int n_utt, Geometry* g) {
+    if (V % 4) return false;
+    int P = 8;
+    if (S_max + 1 <= 32) P = 1;
+    else if (S_max + 2 <= 64) P = 2;
+    else if (S_max + 4 <= 128) P = 4;
+    const int q = env_int("CTC_B200_LIN_PAIRS", 0);
+    if (q == 1 || q == 2 || q == 4 || q == 8) P = q;
+    int R = (S_max + P + 32 * P - 1) / (32 * P);
+    if (R > 1 && P != 8) { P = 8; R = (S_max + P + 32 * P - 1) / (32 * P); }   // several warps: P = 8 only
+    int H = env_int("CTC_B200_HELPERS", 0);
+    if (H < 1 || H > 8) H = V > 256 ? 4 : 2;
+    const int NT = 32 * (R + H);
+    if (NT > 1024) return false;
+    const int NP = 32 * P * R;
+    const int RS = lin_row_stride(NP, P);
+    const int YS = V <= 60 ? 64 : 0;   // fixed emission-ring row stride (an immediate in the kernel)
+    const int tc_env = env_int("CTC_B200_CHUNK", 0), d_env = env_int("CTC_B200_DIST", 0);
+    const int cand[4][2] = {{4, 1}, {2, 2}, {2, 1}, {1, 1}};
+    for (int pass = 0; pass < 2; ++pass) {
+        for (int ci = 0; ci < 4; ++ci) {
+            int TC = cand[ci][0], D = cand[ci][1];
+            if (tc_env == 1 || tc_env == 2 || tc_env == 4) TC = tc_env;   // the kernel unrolls 4 rows
+            if (d_env >= 1 && d_env <= 4) D = d_env;
+            PipeSmem lay(NP, R, V, TC, RS, D, YS);
+            const int need = std::max(1, std::min(4, (2 * std::max(n_utt, 1) + kNumSmsHint - 1) / kNumSmsHint));
+            const int limit = pass == 0 ? std::min(kMaxSmemBytes, 227 * 1024 / need - 2048) : kMaxSmemBytes;
+            if (lay.total > limit) continue;
+            g->lP = P; g->lNT = NT; g->lNP = NP; g->lchunk = TC; g->lRS = RS; g->lsmem = lay.total;
+            g->lR = R; g->lH = H; g->lD = D; g->lYS = YS;
+            g->l_lat_utt_stride = (size_t)std::max(T, 1) * (size_t)RS;
+            return true;
+        }
+    }
+    return false;
+}
+
 int num_sms() {
     static int n = -1;
     if (n < 0) {
@@ -139,9 +187,13 @@ int pick_geometry(int T, int V, int S_max, int n_utt, Geometry* g) {
     if (T < 0 || V < 1 || S_max < 0) return CTC_B200_INVALID_ARGUMENT;
     const int pairs = S_max + 1;
     if (pairs > 4096) return CTC_B200_UNSUPPORTED;  // targets longer than 4095 labels
-    const char* force = std::getenv("CTC_B200_KERNEL");
+    const char* force = std::getenv("CTC_B200_KERNEL");   // g: generic, p: log-domain pipe, default: linear
     const bool want_generic = force && force[0] == 'g';
-    if (!want_generic && pick_pipe(T, V, pairs, n_utt, g)) return CTC_B200_OK;
+    const bool want_pipe = force && force[0] == 'p';
+    if (!want_generic && pick_pipe(T, V, pairs, n_utt, g)) {
+        if (!want_pipe && pick_lin(T, V, S_max, n_utt, g)) g->pipe = 2;
+        return CTC_B200_OK;
+    }
     return pick_generic(T, V, pairs, g);
 }
 
@@ -187,11 +239,44 @@ int launch_pipe_p(const PipeParams& pp, const Geometry& g, int n_utt, cudaStream
     return launch_pipe_pt<P, 1024, 1>(pp, g, n_utt, st);
 }
 
+template <int P, int RC, int YS, int MAXT, int MINB>
+int launch_lin_pt(const PipeParams& pp, int* flags, const Geometry& g, int n_utt, cudaStream_t st) {
+    static int configured_smem = -1;
+    if (g.lsmem > configured_smem) {
+        CTC_CUDA(cudaFuncSetAttribute(ctc_lin_kernel<P, RC, YS, MAXT, MINB>,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, g.lsmem));
+        configured_smem = g.lsmem;
+    }
+    ctc_lin_kernel<P, RC, YS, MAXT, MINB><<<dim3(2 * n_utt), dim3(g.lNT), g.lsmem, st>>>(pp, flags);
+    CTC_CUDA(cudaGetLastError());
+    return CTC_B200_OK;
+}
+
+// One recursion warp (the common case): every stride of the kernel is a compile-time constant.
+template <int P>
+int launch_lin_r1(const PipeParams& pp, int* flags, const Geometry& g, int n_utt, cudaStream_t st) {
+    if (g.lYS == 64) {
+        // 96 threads (2 helpers): 4 CTAs per SM leave 168 registers per thread
+        if (g.lNT <= 96) return launch_lin_pt<P, 1, 64, 96, 4>(pp, flags, g, n_utt, st);
+        return g.lNT <= 128 ? launch_lin_pt<P, 1, 64, 128, 4>(pp, flags, g, n_utt, st)
+                            : launch_lin_pt<P, 1, 64, 256, 2>(pp, flags, g, n_utt, st);
+    }
+    return g.lNT <= 128 ? launch_lin_pt<P, 1, 0, 128, 4>(pp, flags, g, n_utt, st)
+                        : launch_lin_pt<P, 1, 0, 256, 2>(pp, flags, g, n_utt, st);
+}
+
+// Several recursion warps (targets longer than 248 labels): P = 8, run-time strides.
+int launch_lin_rn(const PipeParams& pp, int* flags, const Geometry& g, int n_utt, cudaStream_t st) {
+    if (g.lNT <= 256) return launch_lin_pt<8, 0, 0, 256, 2>(pp, flags, g, n_utt, st);
+    if (g.lNT <= 512) return launch_lin_pt<8, 0, 0, 512, 1>(pp, flags, g, n_utt, st);
+    return launch_lin_pt<8, 0, 0, 1024, 1>(pp, flags, g, n_utt, st);
+}
+
 int launch_fused(const float* acts, const int32_t* targets, const int32_t* tgt_offsets,
                  const int32_t* in_lens, const int32_t* tgt_lens, int T, int N, int V, int S_max,
                  int blank, int zero_infinity, int utt_begin, int utt_count, float* nll,
                  float* grad, const float* grad_scale, float* lattice, size_t lattice_bytes,
-                 int* status_word, cudaStream_t st) {
+                 int* status_word, int* flags, cudaStream_t st) {
     if (!acts || !targets || !tgt_offsets || !in_lens || !tgt_lens || !nll || !status_word)
         return CTC_B200_INVALID_ARGUMENT;
     if (T < 0 || N < 0 || V < 1 || blank < 0 || blank >= V || utt_begin < 0 || utt_count < 0 ||
@@ -201,8 +286,9 @@ int launch_fused(const float* acts, const int32_t* targets, const int32_t* tgt_o
     Geometry g;
     int rc = pick_geometry(T, V, S_max, N, &g);
     if (rc != CTC_B200_OK) return rc;
-    if (!lattice || lattice_bytes < g.lat_utt_stride * sizeof(float) * (size_t)utt_count)
+    if (!lattice || lattice_bytes < g.lattice_floats_per_utt() * sizeof(float) * (size_t)utt_count)
         return CTC_B200_WORKSPACE_TOO_SMALL;
+    if (g.pipe == 2 && !flags) return CTC_B200_INVALID_ARGUMENT;
     if ((reinterpret_cast<uintptr_t>(lattice) & 15) || (reinterpret_cast<uintptr_t>(acts) & 15) ||
         (grad && (reinterpret_cast<uintptr_t>(grad) & 15)))
         return CTC_B200_INVALID_ARGUMENT;
@@ -227,9 +313,40 @@ int launch_fused(const float* acts, const int32_t* targets, const int32_t* tgt_o
     prm.utt_begin = utt_begin;
     prm.row_stride = g.RS;
     prm.chunk = g.chunk;
+    if (g.pipe == 2) {
+        // linear-domain kernel; `flags` ([2 * utt_count], indexed from utt_begin) marks the utterances
+        // whose posterior-mass check failed, which the log-domain kernel below then recomputes
+        PipeParams lp;
+        lp.f = prm;
+        lp.f.lat_utt_stride = (long long)g.l_lat_utt_stride;
+        lp.f.row_stride = g.lRS;
+        lp.f.chunk = g.lchunk;
+        lp.R = g.lR;
+        lp.H = g.lH;
+        lp.NP = g.lNP;
+        lp.D = g.lD;
+        // co-resident CTAs rotate their warp roles only when the CTA has a multiple of 4 warps (else
+        // consecutive CTAs already start on different SM sub-partitions)
+        lp.rotate = (env_int("CTC_B200_ROTATE", 1) && (g.lNT / 32) % 4 == 0) ? num_sms() : 0;
+        lp.redo = nullptr;
+        int* fl = flags - 2 * (ptrdiff_t)utt_begin;   // kernels index flags by absolute utterance
+        if (g.lR == 1) {
+            switch (g.lP) {
+                case 1: rc = launch_lin_r1<1>(lp, fl, g, utt_count, st); break;
+                case 2: rc = launch_lin_r1<2>(lp, fl, g, utt_count, st); break;
+                case 4: rc = launch_lin_r1<4>(lp, fl, g, utt_count, st); break;
+                case 8: rc = launch_lin_r1<8>(lp, fl, g, utt_count, st); break;
+                default: rc = CTC_B200_UNSUPPORTED;
+            }
+        } else {
+            rc = g.lP == 8 ? launch_lin_rn(lp, fl, g, utt_count, st) : CTC_B200_UNSUPPORTED;
+        }
+        if (rc != CTC_B200_OK) return rc;
+    }
     if (g.pipe) {
         PipeParams pp;
         pp.f = prm;
+        pp.redo = g.pipe == 2 ? flags - 2 * (ptrdiff_t)utt_begin : nullptr;
         pp.R = g.R;
         pp.H = g.G;
         pp.NP = g.NP;
@@ -282,15 +399,18 @@ int ctc_b200_get_geometry(int T, int n_utt, int V, int S_max, ctc_b200_geometry*
     Geometry g;
     int rc = pick_geometry(T, V, S_max, n_utt, &g);
     if (rc != CTC_B200_OK) return rc;
+    const bool lin = g.pipe == 2;
     out->kernel = g.pipe;
-    out->rec_warps = g.R;
-    out->grad_warps = g.G;
-    out->pairs_per_thread = g.P;
-    out->threads = g.NT;
-    out->chunk = g.chunk;
-    out->row_stride = g.RS;
-    out->smem_bytes = g.smem;
-    out->workspace_bytes = kHeaderBytes + g.lat_utt_stride * sizeof(float) * (size_t)n_utt;
+    out->rec_warps = lin ? g.lR : g.R;
+    out->grad_warps = lin ? g.lH : g.G;
+    out->pairs_per_thread = lin ? g.lP : g.P;
+    out->threads = lin ? g.lNT : g.NT;
+    out->chunk = lin ? g.lchunk : g.chunk;
+    out->row_stride = lin ? g.lRS : g.RS;
+    out->smem_bytes = lin ? g.lsmem : g.smem;
+    // [256 B header: status word][redo flags: 2 ints per utterance][lattice]
+    out->workspace_bytes = kHeaderBytes + flag_bytes(n_utt) +
+                           g.lattice_floats_per_utt() * sizeof(float) * (size_t)n_utt;
     return CTC_B200_OK;
 }
 
@@ -308,13 +428,15 @@ int ctc_b200_fwd_bwd_range_f32(const float* acts, const int32_t* targets,
                                int blank, int zero_infinity, int utt_begin, int utt_count,
                                float* nll, float* grad, const float* grad_scale,
                                void* workspace, size_t workspace_bytes, void* stream) {
-    if (!workspace || workspace_bytes < (size_t)kHeaderBytes) return CTC_B200_WORKSPACE_TOO_SMALL;
+    const size_t head = (size_t)kHeaderBytes + flag_bytes(utt_count);
+    if (!workspace || workspace_bytes < head) return CTC_B200_WORKSPACE_TOO_SMALL;
     if (reinterpret_cast<uintptr_t>(workspace) & 255) return CTC_B200_INVALID_ARGUMENT;
     char* ws = static_cast<char*>(workspace);
     return launch_fused(acts, targets, tgt_offsets, in_lens, tgt_lens, T, N, V, S_max, blank,
                         zero_infinity, utt_begin, utt_count, nll, grad, grad_scale,
-                        reinterpret_cast<float*>(ws + kHeaderBytes), workspace_bytes - kHeaderBytes,
-                        reinterpret_cast<int*>(ws), static_cast<cudaStream_t>(stream));
+                        reinterpret_cast<float*>(ws + head), workspace_bytes - head,
+                        reinterpret_cast<int*>(ws), reinterpret_cast<int*>(ws + kHeaderBytes),
+                        static_cast<cudaStream_t>(stream));
 }
 
 int ctc_b200_fwd_bwd_f32(const float* acts, const int32_t* targets, const int32_t* tgt_offsets,
@@ -375,6 +497,7 @@ struct ctc_b200_session {
     float* d_grad = nullptr;
     float* d_lattice = nullptr;
     size_t lattice_bytes = 0;
+    int* d_flags = nullptr;    // [2 * N] redo flags of the linear kernel
     char* d_small = nullptr;   // [targets | tgt_off | in_lens | tgt_lens | scale]
     char* h_small = nullptr;   // pinned mirror
     size_t small_bytes = 0;
@@ -399,7 +522,7 @@ int ctc_b200_session_create(int T, int N, int V, int S_max, int max_targets, int
     int rc = pick_geometry(T, V, S_max, N, &s->geo);
     if (rc != CTC_B200_OK) { delete s; return rc; }
     const size_t nact = (size_t)T * N * V * sizeof(float);
-    s->lattice_bytes = s->geo.lat_utt_stride * sizeof(float) * (size_t)N;
+    s->lattice_bytes = s->geo.lattice_floats_per_utt() * sizeof(float) * (size_t)N;
     s->small_bytes = align_up((size_t)std::max(max_targets, 1) * 4, 16) + 4 * align_up((size_t)N * 4, 16);
     s->res_bytes = 16 + (size_t)N * 4;
     cudaError_t e = cudaSuccess;
@@ -407,6 +530,7 @@ int ctc_b200_session_create(int T, int N, int V, int S_max, int max_targets, int
     ok(cudaMalloc(&s->d_acts, nact));
     ok(cudaMalloc(&s->d_grad, nact));
     ok(cudaMalloc(&s->d_lattice, s->lattice_bytes));
+    ok(cudaMalloc(&s->d_flags, flag_bytes(N)));
     ok(cudaMalloc(&s->d_small, s->small_bytes));
     ok(cudaMalloc(&s->d_res, s->res_bytes));
     ok(cudaMallocHost(&s->h_small, s->small_bytes));
@@ -428,7 +552,7 @@ int ctc_b200_session_destroy(ctc_b200_session* s) {
     for (auto ev : s->ev) if (ev) cudaEventDestroy(ev);
     if (s->s_copy) cudaStreamDestroy(s->s_copy);
     if (s->s_comp) cudaStreamDestroy(s->s_comp);
-    cudaFree(s->d_acts); cudaFree(s->d_grad); cudaFree(s->d_lattice);
+    cudaFree(s->d_acts); cudaFree(s->d_grad); cudaFree(s->d_lattice); cudaFree(s->d_flags);
     cudaFree(s->d_small); cudaFree(s->d_res);
     if (s->h_small) cudaFreeHost(s->h_small);
     if (s->h_res) cudaFreeHost(s->h_res);
@@ -499,11 +623,11 @@ int ctc_b200_session_run_host_f32(ctc_b200_session* s, const float* acts_host,
         CTC_CUDA(cudaStreamWaitEvent(s->s_comp, s->ev[k], 0));
         int rc = launch_fused(s->d_acts, d_tg, d_off, d_il, d_tl, T, N, V, s->S_max, blank,
                               zero_infinity, b0, b1 - b0, d_nll, want_grad ? s->d_grad : nullptr,
-                              d_sc, s->d_lattice + (size_t)b0 * s->geo.lat_utt_stride,
-                              s->lattice_bytes - (size_t)b0 * s->geo.lat_utt_stride * sizeof(float),
-                              d_status, s->s_comp);
+                              d_sc, s->d_lattice + (size_t)b0 * s->geo.lattice_floats_per_utt(),
+                              s->lattice_bytes - (size_t)b0 * s->geo.lattice_floats_per_utt() * sizeof(float),
+                              d_status, s->d_flags + 2 * (size_t)b0, s->s_comp);
         if (rc != CTC_B200_OK) return rc;
-        ++launches;
+        launches += s->geo.pipe == 2 ? 2 : 1;
     }
     ctc_reduce_loss_kernel<<<1, 256, 0, s->s_comp>>>(
         d_nll, d_tl, N, reduction == CTC_B200_REDUCE_MEAN ? 1 : 2, d_out2, nullptr);

@@ -33,6 +33,7 @@ struct PipeParams {
     int NP;        // lattice pair slots = 32 * P * R
     int D;         // fetch distance in chunks
     int rotate;    // CTAs per launch "layer" (= #SMs): co-resident CTAs rotate their warp roles
+    const int* redo;  // [2 * N] or nullptr: run only utterances the linear kernel flagged (ctc_lin.cuh)
 };
 
 // class-sorted label cell k lives at float index ypad(k) of the eY row: one float4 of
@@ -43,8 +44,8 @@ struct PipeSmem {
     int lab, pos, cstart, fill, lp2, e, stage, bnd, red, ll, bars, total;  // byte offsets
     int Vs, ER, NL, NS;
     __host__ __device__ static int up(int x, int a) { return (x + a - 1) / a * a; }
-    __host__ __device__ PipeSmem(int NP, int R, int V, int TC, int RS, int D) {
-        Vs = up(V + 1, 4);
+    __host__ __device__ PipeSmem(int NP, int R, int V, int TC, int RS, int D, int ys = 0) {
+        Vs = ys > 0 ? ys : up(V + 1, 4);   // ys: fixed row stride of the emission ring (ctc_lin.cuh)
         ER = NP + ypad(NP) + 4;  // [eB: NP][eY (class-sorted, padded)] + 4 floats of bank skew
         NL = D + 4;              // lp2 ring: issued D+1 chunks early .. gradient 2 chunks later
         NS = D + 2;              // partner ring: issued D chunks early .. recursion 1 chunk later
@@ -137,6 +138,8 @@ ctc_pipe_kernel(const PipeParams pp) {
     const int tid = w * 32 + lane;
     const int b = p.utt_begin + (blockIdx.x >> 1);
     const bool rev = (blockIdx.x & 1) != 0;
+    // fallback mode: both CTAs of the cluster leave unless the linear kernel flagged the utterance
+    if (pp.redo != nullptr && (pp.redo[2 * b] | pp.redo[2 * b + 1]) == 0) return;
     const int T = p.T, N = p.N, V = p.V, blank = p.blank;
     const int RS = p.row_stride, TC = p.chunk, D = pp.D;
     const bool is_rec = w < R;

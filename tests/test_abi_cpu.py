@@ -41,14 +41,17 @@ def test_version_and_status_strings():
 def test_geometry_and_workspace():
     g = cabi.geometry(1000, 256, 48, 240)          # BASELINE config 2
     P = g["pairs_per_thread"]
-    assert P in (1, 2, 4) and g["threads"] % 32 == 0 and g["threads"] * P >= 241
+    assert g["kernel"] == 2 and P == 8 and g["rec_warps"] == 1     # linear kernel, one recursion warp
+    assert g["threads"] % 32 == 0 and 32 * g["rec_warps"] * P >= 241 + P - 1
     assert g["row_stride"] % 4 == 0 and g["smem_bytes"] <= 227 * 1024
-    assert g["workspace_bytes"] == 256 + 256 * 1000 * g["row_stride"] * 4
+    # [256 B header][2 redo flags per utterance, 256-byte granules][lattice of the wider kernel]
+    assert g["workspace_bytes"] == 256 + 2048 + 256 * 1000 * g["row_stride"] * 4
     assert cabi.workspace_bytes(1000, 256, 48, 240) == g["workspace_bytes"]
     g3 = cabi.geometry(4000, 64, 48, 800)          # BASELINE config 3
-    assert g3["threads"] * g3["pairs_per_thread"] >= 801 and g3["smem_bytes"] <= 227 * 1024
+    assert 32 * g3["rec_warps"] * g3["pairs_per_thread"] >= 801 + 7 and g3["smem_bytes"] <= 227 * 1024
     assert cabi.geometry(100, 1, 48, 1500)["threads"] <= 1024
-    assert cabi.geometry(100, 1, 48, 4095)["pairs_per_thread"] == 4
+    assert cabi.geometry(100, 1, 48, 4095)["pairs_per_thread"] in (4, 8)
+    assert cabi.geometry(100, 4, 177, 30)["kernel"] == 0           # V % 4 != 0: generic kernel
     with pytest.raises(cabi.CtcB200Error) as e:
         cabi.geometry(100, 1, 48, 4096)
     assert e.value.status == cabi.UNSUPPORTED

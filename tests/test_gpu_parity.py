@@ -260,7 +260,8 @@ def test_host_session_matches_device_path():
     nll = torch.empty(16)
     grad = torch.empty_like(acts)
     loss = ses.run(acts.pin_memory(), tg, il, tl, reduction="mean", nll_out=nll, grad_out=grad)
-    assert ses.last_launches() == 4
+    per_slice = 2 if cabi.geometry(200, 16, 48, int(tl.max()))["kernel"] == 2 else 1
+    assert ses.last_launches() == 3 * per_slice + 1
     ref = oracle.torch_reference(acts, tg, il, tl, reduction="mean")
     assert abs(loss - float(ref["loss"])) <= NLL_RTOL * abs(float(ref["loss"]))
     np.testing.assert_array_equal(nll.numpy(), nll_d)
