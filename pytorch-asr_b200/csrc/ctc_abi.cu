@@ -157,7 +157,8 @@ bool pick_lin(int T, int V, int S_max, int n_utt, Geometry* g) {
             int TC = cand[ci][0], D = cand[ci][1];
             if (tc_env == 1 || tc_env == 2 || tc_env == 4) TC = tc_env;   // the kernel unrolls 4 rows
             if (d_env >= 1 && d_env <= 4) D = d_env;
-            PipeSmem lay(NP, R, V, TC, RS, D, YS);
+            const int VO = YS > 0 ? YS : PipeSmem::up(V + 1, 4);
+            PipeSmem lay(NP, R, V, TC, RS, D, YS, R * (VO + 32));
             const int need = std::max(1, std::min(4, (2 * std::max(n_utt, 1) + kNumSmsHint - 1) / kNumSmsHint));
             const int limit = pass == 0 ? std::min(kMaxSmemBytes, 227 * 1024 / need - 2048) : kMaxSmemBytes;
             if (lay.total > limit) continue;

@@ -35,11 +35,12 @@
 namespace ctcb200 {
 
 constexpr int kLinTarget = 32;          // a thread's largest cell is renormalised to ~2^32
-constexpr int kLinK = 40;               // a thread's scale is at most 2^40 below the scale of the thread under it
+constexpr int kLinInMax = 96;           // what the neighbour hands up stays below 2^96 in my scale
 constexpr int kLinFresh = -(1 << 24);   // exponent of a thread that has not received anything yet
 constexpr int kLinHmax = 44;            // clamp of the combine exponent (no overflow of p * 2^h)
 constexpr float kMassTol = 3.0e-5f;     // |sum of occupancies - 1| per frame
 constexpr int kLinNone = -(1 << 28);    // exponent of a term that is exactly zero
+constexpr float kQ31 = 2147483648.0f;   // label occupancies are accumulated as Q1.31 fixed point
 
 __device__ __forceinline__ int clamp_exp(int e) { return max(min(e, 127), -127); }
 // 2^e for e in [-126, 127]; 0 for e <= -127 (flush); 2^127 above
@@ -104,8 +105,11 @@ ctc_lin_kernel(const PipeParams pp, int* __restrict__ flags) {
     const bool is_rec = w < R;
     const int hw = w - R;  // helper index (>= 0 for helpers)
 
-    const PipeSmem lay(NP, R, V, TC, RS, D, YS);
-    const int Vs = YS > 0 ? YS : lay.Vs, ER = NP + ypad(NP) + 4, NL = lay.NL, NS = lay.NS;
+    // occupancy row of one frame: per recursion warp [class sums: VO][blank partial sums: 32]
+    const int VO = YS > 0 ? YS : PipeSmem::up(V + 1, 4);
+    const int OW = VO + 32, ER = R * OW;
+    const PipeSmem lay(NP, R, V, TC, RS, D, YS, ER);
+    const int Vs = YS > 0 ? YS : lay.Vs, NL = lay.NL, NS = lay.NS;
     int* s_lab = reinterpret_cast<int*>(smem_raw + lay.lab);
     int* s_pos = reinterpret_cast<int*>(smem_raw + lay.pos);
     int* s_cstart = reinterpret_cast<int*>(smem_raw + lay.cstart);
@@ -159,7 +163,6 @@ ctc_lin_kernel(const PipeParams pp, int* __restrict__ flags) {
     for (int s = tid; s < NP; s += NT) {
         const int i = s - delta;
         int c = V;  // padding pairs gather the zero slot of the y row
-        int ps = (i < 0) ? S + s : s;   // padding label cells park their zeros behind the sorted ones
         if (i >= 0 && i < S) {
             c = rev ? tg[S - 1 - i] : tg[i];
             if (c < 0 || c >= V) {
@@ -168,10 +171,9 @@ ctc_lin_kernel(const PipeParams pp, int* __restrict__ flags) {
             }
         }
         s_lab[s] = c;
-        s_pos[s] = ps;
     }
-    for (int v = tid; v < V + 2; v += NT) s_cstart[v] = 0;
     for (int i = tid; i < 2 * (R + 1); i += NT) s_bnd[i] = make_float2(0.f, 0.f);
+    for (int i = tid; i < 2 * TC * ER; i += NT) s_e[i] = 0.f;   // occupancy accumulators start at 0
     if (tid == 0) {
         s_flag[0] = 0; s_flag[1] = 0;
         for (int i = 0; i < NL; ++i) mbar_init(bar_acts + i, 32);   // 32 lanes' cp.async
@@ -180,42 +182,6 @@ ctc_lin_kernel(const PipeParams pp, int* __restrict__ flags) {
         fence_proxy_async();
     }
     __syncthreads();
-    if (want_grad)
-        for (int i = tid; i < S; i += NT) atomicAdd(&s_cstart[s_lab[i + delta] + 1], 1);
-    __syncthreads();
-    if (want_grad && w == 0) {
-        // exclusive scan of the class histogram: s_cstart[v] = #labels of class < v
-        int carry = 0;
-        for (int base = 0; base < V + 1; base += 32) {
-            const int v = base + lane;
-            int inc = (v < V + 1) ? s_cstart[v] : 0;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const int y = __shfl_up_sync(0xffffffffu, inc, o);
-                if (lane >= o) inc += y;
-            }
-            if (v < V + 1) { s_cstart[v] = carry + inc; s_fill[v] = carry + inc; }
-            carry += __shfl_sync(0xffffffffu, inc, 31);
-        }
-        __syncwarp();
-        // class-sorted position of every label, equal labels in sweep order (deterministic)
-        for (int base = 0; base < S; base += 32) {
-            const int i = base + lane;
-            const int c = (i < S) ? s_lab[i + delta] : -1 - lane;
-            const unsigned peers = __match_any_sync(0xffffffffu, c);
-            const int rank = __popc(peers & ((1u << lane) - 1u));
-            int first = 0;
-            if (i < S) first = s_fill[c];
-            __syncwarp();
-            if (i < S) {
-                s_pos[i + delta] = first + rank;
-                if (rank == 0) s_fill[c] = first + __popc(peers);
-            }
-            __syncwarp();
-        }
-    }
-    __syncthreads();
-
     // ---- sweep geometry (see ctc_pipe.cuh; identical band logic, pair i = slot - delta) ------
     const int C = max(Tb - S, -1);
     const int Tm = Tb >> 1;
@@ -230,6 +196,24 @@ ctc_lin_kernel(const PipeParams pp, int* __restrict__ flags) {
         else { tt0 = n_store + (c - n1) * TC; rows = want_grad ? min(TC, Tb - tt0) : 1; }
     };
 
+#ifdef CTC_B200_PROFILE
+    // developer instrumentation: busy cycles of CTA 0 -> workspace header (u64 at +64):
+    // [0/1] REC phase 1/2, [2/3] helper 0 phase 1/2, [4/5] helper 1 phase 1/2, [6] wall, [7] iterations,
+    // [8] issue [9] gradient [10] logits wait [11] softmax of helper 0 (both phases)
+    unsigned long long* prof = reinterpret_cast<unsigned long long*>(reinterpret_cast<char*>(p.status) + 64);
+    const bool prof_on = blockIdx.x == 0 && lane == 0 && (w == 0 || w == R || w == R + 1);
+    const int prof_role = w == 0 ? 0 : (w == R ? 2 : 4);
+    long long prof_t0 = clock64(), prof_t1 = prof_t0;
+    const long long prof_start = prof_t0;
+#define LPROF_BEGIN() do { prof_t0 = clock64(); prof_t1 = prof_t0; } while (0)
+#define LPROF_END(phase2) do { if (prof_on) atomicAdd(prof + prof_role + ((phase2) ? 1 : 0), (unsigned long long)(clock64() - prof_t0)); } while (0)
+#define LPROF_SEC(slot) do { if (prof_on && w == R) atomicAdd(prof + (slot), (unsigned long long)(clock64() - prof_t1)); prof_t1 = clock64(); } while (0)
+#else
+#define LPROF_BEGIN() do {} while (0)
+#define LPROF_END(phase2) do {} while (0)
+#define LPROF_SEC(slot) do {} while (0)
+#endif
+
     if (is_rec) {
         // =============================================================================
         // REC: lattice recursion on probabilities
@@ -238,8 +222,8 @@ ctc_lin_kernel(const PipeParams pp, int* __restrict__ flags) {
         const int i0 = s0 - delta;       // my first pair (may be negative: leading padding)
         float skf[P];                    // 1 if label cell k also takes the skip transition, else 0
         const float* yk[P];              // &y[label k] in row 0 of the current chunk of the emission ring
-        float* ek[P];                    // class-sorted position of label cell k in row 0 of the e chunk
-        int lab[P], ysl[P];
+        unsigned* ok[P];                 // &occupancy[label k] in row 0 of the current occupancy chunk
+        int lab[P];
         bool vB[P], vY[P];
         float aB[P], aY[P];
 #pragma unroll
@@ -247,7 +231,6 @@ ctc_lin_kernel(const PipeParams pp, int* __restrict__ flags) {
             const int i = i0 + k;
             lab[k] = s_lab[s0 + k];
             skf[k] = (i >= 1 && i < S && lab[k] != s_lab[s0 + k - 1]) ? 1.0f : 0.0f;
-            ysl[k] = NP + ypad(s_pos[s0 + k]);   // where my label cell goes in an e row
             vB[k] = i >= 0 && i <= S;
             vY[k] = i >= 0 && i < S;
             aB[k] = 0.f;
@@ -284,42 +267,48 @@ ctc_lin_kernel(const PipeParams pp, int* __restrict__ flags) {
         const bool wg = wg_i != 0;
         const int row_step = tsign * RS;
         int u = -i0;                     // sweep step minus my first pair: tt - i0
+        int rn_par = 0;
 
         // Renormalisation, every min(P, 4) steps, off the dependent chain.  Every thread wants its
-        // largest cell at 2^kLinTarget; in addition no thread may sit more than 2^kLinK below the
-        // thread under it (a prefix maximum over the lanes of  exponent + K * thread), so that a value
-        // handed up by the neighbour never overflows the receiver's scale: the per-step exchange
-        // then needs neither a test nor a branch.  Threads whose pairs can all no longer finish are
-        // cleared; threads nothing has reached yet inherit a scale from below.
+        // largest cell at 2^kLinTarget.  What the thread UNDER me can hand up during the next period
+        // is bounded by the largest cell of its top min(P, 4) pairs (a value moves one pair per step)
+        // times 3^4, so I also keep my scale high enough for that bound to stay below 2^kLinInMax: the
+        // per-step exchange then needs neither a test nor a branch, and neighbouring threads are
+        // otherwise free to sit at very different scales (steep lattices: peaky, blank-dominated
+        // logits).  Threads whose pairs can all no longer finish are cleared; a thread nothing has
+        // reached yet takes its scale from below just before the first value arrives.
+        constexpr int PT = P < 4 ? P : 4;
         auto renorm = [&]() {
-            float m = 0.f;
+            float m = 0.f, mt = 0.f;
 #pragma unroll
-            for (int k = 0; k < P; ++k) m = fmaxf(m, fmaxf(aB[k], aY[k]));
-            const bool gone = u - (P - 1) > c_i + 1;          // even my last pair is dead
-            const bool live = m > 0.f && !gone;
-            int h = (live ? off + expo(m) : kLinFresh) + kLinK * tid;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const int y = __shfl_up_sync(0xffffffffu, h, o);
-                if (lane >= o) h = max(h, y);
+            for (int k = 0; k < P; ++k) {
+                const float c = fmaxf(aB[k], aY[k]);
+                m = fmaxf(m, c);
+                if (k >= P - PT) mt = fmaxf(mt, c);
             }
-            if constexpr (RC != 1) {
-                if (R > 1) {                                   // carry the prefix maximum across warps
-                    int* red = reinterpret_cast<int*>(s_red);
-                    if (lane == 31) red[w] = h;
-                    named_bar_sync(1, nbar);
-                    for (int i = 0; i < w; ++i) h = max(h, red[i]);
-                    named_bar_sync(1, nbar);
-                }
+            const bool kill = u - (P - 1) > c_i + 1;           // even my last pair is dead
+            const int e_me = (m > 0.f && !kill) ? off + expo(m) : kLinFresh;
+            const int e_top = (mt > 0.f && !kill) ? off + expo(mt) : kLinFresh;
+            int e_in = __shfl_up_sync(0xffffffffu, e_top, 1);
+            if constexpr (RC == 1) {
+                if (lane0) e_in = kLinFresh;
+            } else {
+                int* red = reinterpret_cast<int*>(s_red) + (rn_par ? 32 : 0);   // double buffered
+                rn_par ^= 1;
+                if (lane == 31) red[w + 1] = e_top;
+                if (tid == 0) red[0] = kLinFresh;
+                if (R > 1) named_bar_sync(1, nbar);
+                if (lane0) e_in = red[w];
             }
-            const int g = h - kLinK * tid;
-            const int noff = g < kLinFresh / 2 ? kLinFresh : g - kLinTarget;
-            const int sh = live ? max(noff - off, -126) : 0;   // cells *= 2^-sh
-            float f = sh > 126 ? 0.f : __int_as_float((127 - sh) << 23);
-            if (gone) f = 0.f;
+            const int want = max(e_me - kLinTarget, e_in + 7 - kLinInMax);
+            const int noff = want < kLinFresh / 2 ? kLinFresh : want;
+            int sh = noff - off;                               // cells *= 2^-sh
+            const bool reset = noff == kLinFresh || off == kLinFresh || sh > 126 || kill;
+            sh = max(sh, -126);
+            const float f = reset ? 0.f : __int_as_float((127 - sh) << 23);
 #pragma unroll
             for (int k = 0; k < P; ++k) { aB[k] *= f; aY[k] *= f; }
-            off = live ? off + sh : noff;
+            off = reset ? noff : off + sh;
         };
         // one recursion step: a[t] <- a[t-1]; xs / ins = the cells BEFORE the emission (scale `off`);
         // yo = float offset of this step's row inside the chunk of the emission ring
@@ -360,9 +349,10 @@ ctc_lin_kernel(const PipeParams pp, int* __restrict__ flags) {
 
         Ring ring_y(NL), ring_part(NS);   // position of the chunk REC works on
         int e_buf = 0;
-        renorm();                         // hands every thread above pair 0 its initial scale
+        renorm();                         // normalises the start value
         for (int it = 0; it < nch + 2; ++it) {
             const int k = it - 1;
+            LPROF_BEGIN();
             if (k >= 0 && k < nch) {
                 int tt0, rows;
                 chunk_at(k, tt0, rows);
@@ -399,10 +389,13 @@ ctc_lin_kernel(const PipeParams pp, int* __restrict__ flags) {
                     // ---- consume chunk: combine with the partner's stored rows ----------
                     mbar_wait(bar_part + ring_part.slot, ring_part.parity);   // TMA data landed
                     const float* st = s_stage + ((size_t)ring_part.slot * TC + (rev ? rows - 1 : 0)) * RS;
-                    float* erow = s_e + (size_t)e_buf * TC * ER;
+                    // occupancies: label cells are ADDED to their class slot as Q1.31 fixed point with
+                    // native shared-memory integer atomics (order-independent, hence bit-reproducible;
+                    // quantum 4.7e-10); blank cells are summed per thread in fp32
+                    float* orow = s_e + (size_t)e_buf * TC * ER + w * OW;
 #pragma unroll
-                    for (int q = 0; q < P; ++q) ek[q] = erow + ysl[q];
-                    float* eb = erow + s0;
+                    for (int q = 0; q < P; ++q) ok[q] = reinterpret_cast<unsigned*>(orow) + lab[q];
+                    float* obl = orow + VO + lane;
                     const float* stp = st + (hasX ? X * P : 0);         // partner thread's P blanks
                     const int* sto = reinterpret_cast<const int*>(st + 2 * NP) + (hasX ? X : 0);
                     float pb[P], py[P];    // partner cells matching my blank k / label k
@@ -489,12 +482,13 @@ ctc_lin_kernel(const PipeParams pp, int* __restrict__ flags) {
                             if (!rev) p.nll[b] = bad ? 0.f : (float)(-((double)E0 + (double)log2f(z)) * kLn2);
                         }
                         if (wg) {
+                            float bsum = 0.f;
 #pragma unroll
                             for (int q = 0; q < P; ++q) {
-                                tB[q] *= rz;
-                                ek[q][0] = tY[q] * rz;
+                                bsum += tB[q] * rz;
+                                atomicAdd(ok[q], __float2uint_rn(tY[q] * (rz * kQ31)));
                             }
-                            store_row<P>(eb, tB);
+                            *obl = bsum;
                         }
                         end_step();
                         stp += row_step;
@@ -513,22 +507,28 @@ ctc_lin_kernel(const PipeParams pp, int* __restrict__ flags) {
                                 float xs[P], ins[P];
                                 fetch();
                                 advance(yb_ptr, r * Vs, xs, ins);
-                                if ((unsigned)u < win_cons) {
+                                    if ((unsigned)u < win_cons) {
                                     // occupancy = a * p~ * 2^(off + o - E0) / z   (exact exponents); cells
                                     // outside [0, S] are exact zeros on my side, partner vectors are finite
+                                    // (label cells directly in Q1.31 units)
                                     const float sb = pow2c(min(off + ob - E0, kLinHmax)) * rz;
-                                    const float sy = hasX1 ? pow2c(min(off + oy - E0, kLinHmax)) * rz : 0.f;
+                                    const float sq = sb * kQ31;
+                                    const float sy = hasX1 ? pow2c(min(off + oy - E0, kLinHmax)) * (rz * kQ31) : 0.f;
 #pragma unroll
                                     for (int q = 0; q < P; ++q) {
                                         gB[q] = aB[q] * (pb[q] * sb);
-                                        if (q + 1 < P) gY[q] = aY[q] * (py[q] * sb);
+                                        if (q + 1 < P) gY[q] = aY[q] * (py[q] * sq);
                                     }
                                     if (hasX1) gY[P - 1] = aY[P - 1] * (py[P - 1] * sy);
                                 }
                             }
+                            float bsum = 0.f;
 #pragma unroll
-                            for (int q = 0; q < P; ++q) ek[q][r * ER] = gY[q];
-                            store_row<P>(eb + r * ER, gB);
+                            for (int q = 0; q < P; ++q) {
+                                bsum += gB[q];
+                                atomicAdd(ok[q] + r * ER, __float2uint_rn(gY[q]));
+                            }
+                            obl[r * ER] = bsum;
                             stp += row_step;
                             sto += row_step;
                             end_step();
@@ -541,6 +541,7 @@ ctc_lin_kernel(const PipeParams pp, int* __restrict__ flags) {
                 }
                 ring_y.advance();
             }
+            LPROF_END(k >= n1);
             __syncthreads();
             if (it == n1) {  // phase break (see the helper branch)
                 cluster_sync_all();
@@ -551,20 +552,54 @@ ctc_lin_kernel(const PipeParams pp, int* __restrict__ flags) {
         // =============================================================================
         // HELP: staging producer, fused softmax, gradient rows
         // =============================================================================
-        const int half = lane >> 4, q16 = lane & 15;   // a helper handles two frames at a time
-        int a_r0 = 0, a_c0 = lane;
-        while (a_c0 >= V4) { a_c0 -= V4; ++a_r0; }
+        // Helpers [0, nA) are "A": logits staging + softmax; helpers [nA, H) are "B": partner staging
+        // + gradient rows (H == 1: one warp does both).  A helper owns F = TC / n frames of every
+        // chunk and works on all of them AT ONCE, a group of G = 32 / F lanes per frame, so that one
+        // pass of short shuffle trees (log2 G levels) finishes the chunk.
+        const int nA = H >= 2 ? H / 2 : 1, nB = H >= 2 ? H - nA : 1;
+        const bool isA = H == 1 || hw < nA, isB = H == 1 || hw >= nA;
+        const int ha = hw, hb = H == 1 ? 0 : hw - nA;
+        const int FA = max(TC / nA, 1), FB = max(TC / nB, 1);
+        auto group_sum = [&](float x, int G) {
+            for (int o = G >> 1; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+            return x;
+        };
+        auto group_max = [&](float x, int G) {
+            for (int o = G >> 1; o > 0; o >>= 1) x = fmaxf(x, __shfl_xor_sync(0xffffffffu, x, o));
+            return x;
+        };
+
+        // ---- staging of one chunk ---------------------------------------------------------
+        //   logits rows of chunk ka: cp.async, 16 B per lane and copy; a lane's (row, column) of its
+        //   first two copies never change, so they are computed once
         const ptrdiff_t a_inc = (ptrdiff_t)tsign * (ptrdiff_t)frame_stride;
+        const int n4 = TC * V4;
+        int cp_dst[2], cp_row[2];
+        ptrdiff_t cp_src[2];
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            const int idx = lane + 32 * j, r = idx / V4, c = idx - r * V4;
+            cp_row[j] = idx < n4 ? r : 0x7fffffff;
+            cp_dst[j] = r * Vs + 4 * c;
+            cp_src[j] = r * a_inc + 4 * c;
+        }
         auto issue_chunk = [&](int ka, int slot_a, int kp, int slot_p) {
             if (ka >= 0) {
                 int tt0, rows;
                 chunk_at(ka, tt0, rows);
                 float* dst = s_y + (size_t)slot_a * TC * Vs;
                 const float* src = acts_b + (ptrdiff_t)(tbase + tsign * tt0) * (ptrdiff_t)frame_stride;
-                for (int r = a_r0, c = a_c0; r < rows;) {
-                    cp_async16(dst + r * Vs + 4 * c, src + r * a_inc + 4 * c);
-                    c += 32;
+#pragma unroll
+                for (int j = 0; j < 2; ++j)
+                    if (cp_row[j] < rows) cp_async16(dst + cp_dst[j], src + cp_src[j]);
+                if (n4 > 64) {
+                    int r = 64 / V4, c = 64 - r * V4 + lane;
                     while (c >= V4) { c -= V4; ++r; }
+                    while (r < rows) {
+                        cp_async16(dst + r * Vs + 4 * c, src + r * a_inc + 4 * c);
+                        c += 32;
+                        while (c >= V4) { c -= V4; ++r; }
+                    }
                 }
                 cp_async_arrive(bar_acts + slot_a);
             }
@@ -579,108 +614,107 @@ ctc_lin_kernel(const PipeParams pp, int* __restrict__ flags) {
             }
         };
 
-        // ---- fused softmax, in place, of two staged rows (one per half-warp) ------------
-        auto softmax2 = [&](float* row, bool act) {
-            float4* row4 = reinterpret_cast<float4*>(row);
-            if (V4 <= 16) {  // the whole row is one float4 per lane of the half-warp
-                float4 x = make_float4(-CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F);
-                if (q16 < V4) x = row4[q16];
-                const float m = half_max(fmaxf(fmaxf(x.x, x.y), fmaxf(x.z, x.w)));
-                x.x = ex2f((x.x - m) * kLog2e); x.y = ex2f((x.y - m) * kLog2e);
-                x.z = ex2f((x.z - m) * kLog2e); x.w = ex2f((x.w - m) * kLog2e);
-                const float rs = 1.0f / half_sum((x.x + x.y) + (x.z + x.w));
-                if (act && q16 < V4) row4[q16] = make_float4(x.x * rs, x.y * rs, x.z * rs, x.w * rs);
-            } else {
-                float m = -CUDART_INF_F, z = 0.f;
-                for (int c = q16; c < V4; c += 16) {
-                    const float4 x = row4[c];
-                    m = fmaxf(m, fmaxf(fmaxf(x.x, x.y), fmaxf(x.z, x.w)));
-                }
-                m = half_max(m);
-                for (int c = q16; c < V4; c += 16) {
-                    float4 x = row4[c];
-                    x.x = ex2f((x.x - m) * kLog2e); x.y = ex2f((x.y - m) * kLog2e);
-                    x.z = ex2f((x.z - m) * kLog2e); x.w = ex2f((x.w - m) * kLog2e);
-                    z += (x.x + x.y) + (x.z + x.w);
-                    if (act) row4[c] = x;
-                }
-                const float rs = 1.0f / half_sum(z);
-                __syncwarp();
-                if (act)
-                    for (int c = q16; c < V4; c += 16) {
-                        const float4 x = row4[c];
-                        row4[c] = make_float4(x.x * rs, x.y * rs, x.z * rs, x.w * rs);
-                    }
-            }
-            if (act && q16 == 0) row[V] = 0.f;  // what padding pairs gather
-        };
-
-        // ---- gradient of two frames (one per half-warp) ---------------------------------
-        //   e row = occupancies: [blank cells by slot: NP][label cells class-sorted, padded].
-        //   The sum of class v is PS[cstart[v+1]] - PS[cstart[v]] of the exclusive prefix sums
-        //   PS over the sorted label cells, which overwrite the occupancies in place.
-        //   sum of ALL occupancies of a frame must be 1: the posterior-mass check.
-        const int nb4 = (S + delta) / 4 + 1;                    // float4s covering blank slots 0..S+delta
-        auto grad2 = [&](float* erow, const float* yrow, float* g, bool act) {
-            const float4* eB4 = reinterpret_cast<const float4*>(erow);
-            float bs = 0.f;
-            for (int c = q16; c < nb4; c += 16) {
-                const float4 x = eB4[c];
-                bs += (x.x + x.y) + (x.z + x.w);
-            }
-            bs = half_sum(bs);
-            float carry = 0.f;                                  // labels: 256 sorted cells per round
-            float* eY = erow + NP;
-            for (int base = 0; base < S; base += 256) {
-                const int k0 = base + 16 * q16;                 // my 16 consecutive sorted cells
-                float4* c4 = reinterpret_cast<float4*>(eY + ypad(k0));
-                float o[16];
-                const bool in = k0 < NP;                        // cells in [S, NP) hold 0
+        // ---- fused softmax, in place, of my F frames of a chunk (a group of G lanes per frame) ----
+        const int V2 = V >> 1;
+        auto softmax_chunk = [&](float* base, int rows) {
+            const int G = 32 / FA, gl = lane & (G - 1), f = ha * FA + lane / G;
+            const bool act = f < rows;
+            float* row = base + min(f, rows - 1) * Vs;
+            float2* row2 = reinterpret_cast<float2*>(row);
+            if (V2 <= 4 * G) {      // at most 4 float2 per lane: the row stays in registers
+                float2 x[4];
+                float m = -CUDART_INF_F;
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
-                    float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (in) x = c4[j];
-                    o[4 * j] = x.x; o[4 * j + 1] = x.y; o[4 * j + 2] = x.z; o[4 * j + 3] = x.w;
+                    const int c = gl + j * G;
+                    x[j] = c < V2 ? row2[c] : make_float2(-CUDART_INF_F, -CUDART_INF_F);
+                    m = fmaxf(m, fmaxf(x[j].x, x[j].y));
                 }
-                float run = 0.f;                                // exclusive prefix inside my 16 cells
+                m = group_max(m, G);
+                float z = 0.f;
 #pragma unroll
-                for (int j = 0; j < 16; ++j) { const float t = o[j]; o[j] = run; run += t; }
-                float inc = run;                                // inclusive scan over the 16 lanes
-#pragma unroll
-                for (int s = 1; s < 16; s <<= 1) {
-                    const float y = __shfl_up_sync(0xffffffffu, inc, s, 16);
-                    if (q16 >= s) inc += y;
+                for (int j = 0; j < 4; ++j) {
+                    x[j].x = ex2f((x[j].x - m) * kLog2e);
+                    x[j].y = ex2f((x[j].y - m) * kLog2e);
+                    z += x[j].x + x[j].y;
                 }
-                const float ex = carry + (inc - run);
-                if (in && act) {
+                const float rs = 1.0f / group_sum(z, G);
+                if (act) {
 #pragma unroll
-                    for (int j = 0; j < 4; ++j)
-                        c4[j] = make_float4(ex + o[4 * j], ex + o[4 * j + 1], ex + o[4 * j + 2], ex + o[4 * j + 3]);
+                    for (int j = 0; j < 4; ++j) {
+                        const int c = gl + j * G;
+                        if (c < V2) row2[c] = make_float2(x[j].x * rs, x[j].y * rs);
+                    }
                 }
-                carry += __shfl_sync(0xffffffffu, inc, 15, 16);
+            } else {
+                float m = -CUDART_INF_F, z = 0.f;
+                for (int c = gl; c < V2; c += G) {
+                    const float2 x = row2[c];
+                    m = fmaxf(m, fmaxf(x.x, x.y));
+                }
+                m = group_max(m, G);
+                for (int c = gl; c < V2; c += G) {
+                    float2 x = row2[c];
+                    x.x = ex2f((x.x - m) * kLog2e);
+                    x.y = ex2f((x.y - m) * kLog2e);
+                    z += x.x + x.y;
+                    if (act) row2[c] = x;
+                }
+                const float rs = 1.0f / group_sum(z, G);
+                if (act)
+                    for (int c = gl; c < V2; c += G) {
+                        const float2 x = row2[c];
+                        row2[c] = make_float2(x.x * rs, x.y * rs);
+                    }
             }
-            __syncwarp();
-            if (act) {
-                if (!(fabsf((bs + carry) - 1.0f) <= kMassTol)) s_flag[0] = 1;   // NaN-safe
-                for (int v = q16; v < V; v += 16) {
-                    const int k0 = s_cstart[v], k1 = s_cstart[v + 1];
-                    const float hi = (k1 < S) ? eY[ypad(k1)] : carry;   // PS[S] = total
-                    const float lo = (k0 < S) ? eY[ypad(k0)] : carry;
-                    const float occ = (hi - lo) + (v == blank ? bs : 0.f);
-                    g[v] = gscale * (yrow[v] - occ);
-                }
-            }
+            if (act && gl == 0) row[V] = 0.f;  // what padding pairs gather
         };
 
-        // ---- the helper schedule (identical to ctc_pipe.cuh) -----------------------------
+        // ---- gradient rows of my F frames of a chunk (a group of G lanes per frame) ---------------
+        //   occupancy row = per recursion warp [class sums, Q1.31: VO][blank partial sums, fp32: 32].
+        //   The row is read, cleared for its next use, and turned into gscale * (softmax - occupancy).
+        //   The sum of ALL occupancies of a frame must be 1: the posterior-mass check.
+        auto grad_chunk = [&](float* obase, const float* ybase, int tt0, int rows) {
+            const int G = 32 / FB, gl = lane & (G - 1), f = hb * FB + lane / G;
+            const bool act = f < rows;
+            const int fr = min(f, rows - 1);
+            float* orow = obase + fr * ER;
+            const float2* y2 = reinterpret_cast<const float2*>(ybase + fr * Vs);
+            float2* g2 = reinterpret_cast<float2*>(grad_b + (size_t)(tbase + tsign * (tt0 + fr)) * frame_stride);
+            float bs = 0.f;
+            for (int i = gl; i < 32 * R; i += G) bs += orow[(i >> 5) * OW + VO + (i & 31)];
+            bs = group_sum(bs, G);
+            float tot = 0.f;
+            for (int c = gl; c < V2; c += G) {
+                float2 o = make_float2(0.f, 0.f);
+                for (int rw = 0; rw < R; ++rw) {
+                    uint2* p2 = reinterpret_cast<uint2*>(orow + rw * OW) + c;
+                    const uint2 x = *p2;
+                    o.x += __uint2float_rn(x.x) * (1.0f / kQ31);
+                    o.y += __uint2float_rn(x.y) * (1.0f / kQ31);
+                    if (act) *p2 = make_uint2(0u, 0u);
+                }
+                tot += o.x + o.y;
+                if ((blank >> 1) == c) {
+                    if (blank & 1) o.y += bs; else o.x += bs;
+                }
+                const float2 y = y2[c];
+                if (act) g2[c] = make_float2(gscale * (y.x - o.x), gscale * (y.y - o.y));
+            }
+            tot = group_sum(tot, G) + bs;
+            if (act && !(fabsf(tot - 1.0f) <= kMassTol)) s_flag[0] = 1;   // NaN-safe
+        };
+
+        // ---- the helper schedule -----------------------------------------------------------
+        // Iteration `it`:  issue { logits of chunk it+D+1 (A0), partner rows of chunk it+D (B0) };
+        //                  softmax of chunk it (A);  gradient rows of chunk it-2 (B).
+        // (REC runs chunk it-1.)  Partner rows of the first D+1 consume chunks cannot be requested
+        // before the partner CTA wrote them: they are issued at the phase break.
         int wgh_i = want_grad ? 1 : 0;
         asm volatile("" : "+r"(wgh_i));
         const bool wgh = wgh_i != 0;
-        const bool iss_acts = H >= 3 ? hw == 0 : hw == H - 1, iss_part = hw == 0;
-        const int n_sm = min(H, 2), n_gr = min(H, 2), gr_base = H - n_gr;
-        const bool do_sm = hw < n_sm, do_gr = hw >= gr_base;
-        const int sm_first = 2 * hw, sm_step = 2 * n_sm;
-        const int gr_first = 2 * (hw - gr_base), gr_step = 2 * n_gr;
+        const bool iss_acts = isA && ha == 0, iss_part = isB && hb == 0;
+        const bool do_sm = isA && ha * FA < TC, do_gr = isB && hb * FB < TC;
         Ring iss_a(NL), iss_p(NS), sm_a(NL), gr_a(NL);
         int gr_e = 0;
         if (iss_acts) {
@@ -690,6 +724,7 @@ ctc_lin_kernel(const PipeParams pp, int* __restrict__ flags) {
             }
         }
         for (int it = 0; it < nch + 2; ++it) {
+            LPROF_BEGIN();
             {
                 const int ka = it + D + 1, kp = it + D;
                 const bool do_a = iss_acts && ka < nch;
@@ -698,31 +733,28 @@ ctc_lin_kernel(const PipeParams pp, int* __restrict__ flags) {
                 iss_a.advance();
                 if (it >= n1 + 1) iss_p.advance();
             }
+            LPROF_SEC(8);
             const int kg = it - 2;
             if (kg >= 0) {
                 if (do_gr && wgh && kg >= n1 && kg < nch && s_flag[1] == 0) {   // gradient rows of chunk it-2
                     int tt0, rows;
                     chunk_at(kg, tt0, rows);
-                    for (int r0 = gr_first; r0 < rows; r0 += gr_step) {
-                        const int r = min(r0 + half, rows - 1);
-                        grad2(s_e + ((size_t)gr_e * TC + r) * ER, s_y + ((size_t)gr_a.slot * TC + r) * Vs,
-                              grad_b + (size_t)(tbase + tsign * (tt0 + r)) * frame_stride, r0 + half < rows);
-                    }
+                    grad_chunk(s_e + (size_t)gr_e * TC * ER, s_y + (size_t)gr_a.slot * TC * Vs, tt0, rows);
                 }
                 if (kg >= n1) gr_e ^= 1;
                 gr_a.advance();
             }
-            if (do_sm && it < nch) {                  // softmax of chunk `it`, two rows per pass
+            LPROF_SEC(9);
+            if (do_sm && it < nch) {                  // softmax of chunk `it`
                 int tt0, rows;
                 chunk_at(it, tt0, rows);
                 mbar_wait(bar_acts + sm_a.slot, sm_a.parity);
-                float* base = s_y + (size_t)sm_a.slot * TC * Vs;
-                for (int r0 = sm_first; r0 < rows; r0 += sm_step) {
-                    const int r = r0 + half;
-                    softmax2(base + min(r, rows - 1) * Vs, r < rows);
-                }
+                LPROF_SEC(10);
+                softmax_chunk(s_y + (size_t)sm_a.slot * TC * Vs, rows);
             }
+            LPROF_SEC(11);
             sm_a.advance();
+            LPROF_END(it >= n1 + 1);
             __syncthreads();
             if (it == n1) {
                 // Phase break: my REC warps have stored every row the partner will consume,
@@ -739,6 +771,12 @@ ctc_lin_kernel(const PipeParams pp, int* __restrict__ flags) {
             }
         }
     }
+#ifdef CTC_B200_PROFILE
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        prof[6] = (unsigned long long)(clock64() - prof_start);
+        prof[7] = (unsigned long long)(nch + 2);
+    }
+#endif
     // every CTA reports whether its half passed; the log-domain kernel redoes flagged utterances
     __syncthreads();
     if (threadIdx.x == 0) flags[2 * b + (rev ? 1 : 0)] = s_flag[0];

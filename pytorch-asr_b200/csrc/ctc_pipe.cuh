@@ -44,9 +44,10 @@ struct PipeSmem {
     int lab, pos, cstart, fill, lp2, e, stage, bnd, red, ll, bars, total;  // byte offsets
     int Vs, ER, NL, NS;
     __host__ __device__ static int up(int x, int a) { return (x + a - 1) / a * a; }
-    __host__ __device__ PipeSmem(int NP, int R, int V, int TC, int RS, int D, int ys = 0) {
+    __host__ __device__ PipeSmem(int NP, int R, int V, int TC, int RS, int D, int ys = 0, int er = 0) {
         Vs = ys > 0 ? ys : up(V + 1, 4);   // ys: fixed row stride of the emission ring (ctc_lin.cuh)
-        ER = NP + ypad(NP) + 4;  // [eB: NP][eY (class-sorted, padded)] + 4 floats of bank skew
+        // [eB: NP][eY (class-sorted, padded)] + 4 floats of bank skew; er: occupancy row of ctc_lin.cuh
+        ER = er > 0 ? er : NP + ypad(NP) + 4;
         NL = D + 4;              // lp2 ring: issued D+1 chunks early .. gradient 2 chunks later
         NS = D + 2;              // partner ring: issued D chunks early .. recursion 1 chunk later
         int o = 0;
