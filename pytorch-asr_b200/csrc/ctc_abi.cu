@@ -132,7 +132,8 @@ bool pick_pipe(int T, int V, int pairs, int n_utt, Geometry* g) {
 }
 
 // Linear-domain kernel: R recursion warps with P pairs per thread in registers (P = 8 covers 256
-// lattice slots per warp), H helper warps.  Needs S_max + P <= 32 * P * R slots (alignment shift).
+// lattice slots per warp), R combine warps, H softmax / gradient warps.  Needs S_max + P <= 32 * P * R
+// slots (alignment shift).
 bool pick_lin(int T, int V, int S_max, int n_utt, Geometry* g) {
     if (V % 4) return false;
     int P = 8;
@@ -144,26 +145,26 @@ bool pick_lin(int T, int V, int S_max, int n_utt, Geometry* g) {
     int R = (S_max + P + 32 * P - 1) / (32 * P);
     if (R > 1 && P != 8) { P = 8; R = (S_max + P + 32 * P - 1) / (32 * P); }   // several warps: P = 8 only
     int H = env_int("CTC_B200_HELPERS", 0);
-    if (H < 1 || H > 8) H = V > 256 ? 4 : 2;
-    const int NT = 32 * (R + H);
+    if (!(H == 1 || H == 2 || H == 4 || H == 8)) H = V > 256 ? 4 : 2;
+    int NC = env_int("CTC_B200_COMB", 0);          // combine groups (warps per recursion warp)
+    if (NC < 1 || NC > 4) NC = R == 1 ? 2 : 1;
+    const int NT = 32 * ((1 + NC) * R + H);
     if (NT > 1024) return false;
     const int NP = 32 * P * R;
     const int RS = lin_row_stride(NP, P);
-    const int YS = V <= 60 ? 64 : 0;   // fixed emission-ring row stride (an immediate in the kernel)
-    const int tc_env = env_int("CTC_B200_CHUNK", 0), d_env = env_int("CTC_B200_DIST", 0);
-    const int cand[4][2] = {{4, 1}, {2, 2}, {2, 1}, {1, 1}};
+    const int YS = V <= 60 ? 80 : 0;   // fixed emission-ring row stride (an immediate in the kernel)
+    const int tc_env = env_int("CTC_B200_CHUNK", 0);
+    const int cand[3] = {4, 2, 1};
     for (int pass = 0; pass < 2; ++pass) {
-        for (int ci = 0; ci < 4; ++ci) {
-            int TC = cand[ci][0], D = cand[ci][1];
+        for (int ci = 0; ci < 3; ++ci) {
+            int TC = cand[ci];
             if (tc_env == 1 || tc_env == 2 || tc_env == 4) TC = tc_env;   // the kernel unrolls 4 rows
-            if (d_env >= 1 && d_env <= 4) D = d_env;
-            const int VO = YS > 0 ? YS : PipeSmem::up(V + 1, 4);
-            PipeSmem lay(NP, R, V, TC, RS, D, YS, R * (VO + 32));
+            LinSmem lay(NP, R, V, TC, RS, YS);
             const int need = std::max(1, std::min(4, (2 * std::max(n_utt, 1) + kNumSmsHint - 1) / kNumSmsHint));
-            const int limit = pass == 0 ? std::min(kMaxSmemBytes, 227 * 1024 / need - 2048) : kMaxSmemBytes;
+            const int limit = pass == 0 ? std::min(kMaxSmemBytes, 227 * 1024 / need - 1024) : kMaxSmemBytes;
             if (lay.total > limit) continue;
             g->lP = P; g->lNT = NT; g->lNP = NP; g->lchunk = TC; g->lRS = RS; g->lsmem = lay.total;
-            g->lR = R; g->lH = H; g->lD = D; g->lYS = YS;
+            g->lR = R; g->lH = H; g->lD = NC; g->lYS = YS;
             g->l_lat_utt_stride = (size_t)std::max(T, 1) * (size_t)RS;
             return true;
         }
@@ -256,11 +257,10 @@ int launch_lin_pt(const PipeParams& pp, int* flags, const Geometry& g, int n_utt
 // One recursion warp (the common case): every stride of the kernel is a compile-time constant.
 template <int P>
 int launch_lin_r1(const PipeParams& pp, int* flags, const Geometry& g, int n_utt, cudaStream_t st) {
-    if (g.lYS == 64) {
-        // 96 threads (2 helpers): 4 CTAs per SM leave 168 registers per thread
-        if (g.lNT <= 96) return launch_lin_pt<P, 1, 64, 96, 4>(pp, flags, g, n_utt, st);
-        return g.lNT <= 128 ? launch_lin_pt<P, 1, 64, 128, 4>(pp, flags, g, n_utt, st)
-                            : launch_lin_pt<P, 1, 64, 256, 2>(pp, flags, g, n_utt, st);
+    if (g.lYS == 80) {
+        if (g.lNT <= 128) return launch_lin_pt<P, 1, 80, 128, 4>(pp, flags, g, n_utt, st);
+        if (g.lNT <= 160) return launch_lin_pt<P, 1, 80, 160, 4>(pp, flags, g, n_utt, st);
+        return launch_lin_pt<P, 1, 80, 256, 2>(pp, flags, g, n_utt, st);
     }
     return g.lNT <= 128 ? launch_lin_pt<P, 1, 0, 128, 4>(pp, flags, g, n_utt, st)
                         : launch_lin_pt<P, 1, 0, 256, 2>(pp, flags, g, n_utt, st);

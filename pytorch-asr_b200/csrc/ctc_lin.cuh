@@ -1,12 +1,11 @@
 // ctc_lin.cuh -- the LINEAR-domain warp-specialised fused CTC kernel for sm_100a.
 //
 // Same decomposition as ctc_pipe.cuh (a 2-CTA cluster per utterance, the alpha CTA and the
-// time/label-reversed beta CTA meet in the middle, ONE fp32 lattice goes through HBM, REC /
-// HELP warp roles, TMA-staged rings), but the lattice recursion runs on PROBABILITIES, not on
-// log-probabilities:
+// time/label-reversed beta CTA meet in the middle, ONE fp32 lattice goes through HBM, TMA-staged
+// rings), but the lattice recursion runs on PROBABILITIES, not on log-probabilities:
 //
 //      x      = aB + aY_prev                       (blank cell, before the emission)
-//      inner  = aY + (skip ? x : aB)               (label cell, before the emission)
+//      inner  = aY + aB + skip * aY_prev           (label cell, before the emission)
 //      aB'    = y_blank * x ;  aY' = y_label * inner
 //
 // i.e. 5 FP32 instructions per cell pair and step and NO MUFU (the log-domain kernel spends
@@ -14,21 +13,36 @@
 // alpha * beta~ / P with beta~ the partner's PRE-emission value, so nothing is divided by y.
 //
 // Range: every THREAD keeps an exact power-of-two exponent `off` for its P pairs (true value =
-// a * 2^off).  Neighbour values are brought to the receiver's scale with one exact multiply;
-// a thread renormalises its cells to ~2^32 at every chunk end; an incoming value far above the
-// receiver's scale makes the receiver rescale first (warp-uniform rare branch).  Rows are
-// stored with their per-thread exponents ([blank plane][label plane][exponents]).
+// a * 2^off).  Neighbour values are brought to the receiver's scale with one exact multiply; a
+// thread renormalises its cells to ~2^32 every min(P, 4) steps and keeps its scale high enough
+// for whatever the thread under it can hand up in the meantime (see `renorm`).  Rows are stored
+// with their per-thread exponents ([blank plane][label plane][exponents]).
 //
 // Safety net: whatever the scaling loses (a cell flushed to zero, a clamped scale) shows up
-// as missing posterior mass.  The helpers check  |sum_s occupancy_t(s) - 1| <= kMassTol  for
+// as missing posterior mass.  The gradient warp checks |sum_s occupancy_t(s) - 1| <= kMassTol for
 // EVERY frame; an utterance that fails (or whose likelihood underflows to 0, which includes
 // every infeasible utterance) is flagged in `flags` and recomputed by the log-domain kernel
 // (ctc_pipe_kernel, launched right after with the same grid; clusters of unflagged utterances
 // exit at once).  The linear path is therefore exact to fp32 rounding or not used at all.
 //
+// Warp roles (R = recursion warps, 1 for targets up to 248 labels):
+//   [0, R)        REC   the lattice recursion and nothing else: one step = emission loads, one
+//                       shuffle pair, 5 FP32 per pair, one row out -- to HBM (first half of the
+//                       sweep, for the partner CTA) or to a shared-memory ring (second half)
+//   [R, 2R)       COMB  second half only: combines REC's rows with the partner's stored rows (TMA-staged)
+//                       into occupancies; NC groups of them share the rows of a chunk; label cells are ADDED to their class slot as Q1.31
+//                       fixed point with native shared-memory integer atomics (order-independent,
+//                       hence bit-reproducible); also the likelihood from the first combined row
+//   2R .. 2R+nA   SOFT  logits staging (cp.async + mbarrier) and the fused softmax, all frames of a
+//                       chunk at once (a group of lanes per frame)
+//   the rest      GRAD  gradient rows = gscale * (softmax - occupancy), posterior-mass check,
+//                       zero fill of rows t >= T_b
+// One CTA barrier per chunk of TC frames hands the rings over: in iteration `it` SOFT works on
+// chunk it, REC on chunk it-1, COMB on chunk it-2, GRAD on chunk it-3.
+//
 // Alignment trick: the alpha CTA shifts its lattice by delta = (P-1-S) mod P slots, so that the
-// P partner cells a consumer thread needs are exactly ONE partner thread's P cells, reversed:
-// 128-bit conflict-free shared-memory loads and a single partner exponent per thread.
+// P partner cells a thread needs are exactly ONE partner thread's P cells, reversed: 128-bit
+// conflict-free shared-memory loads and a single partner exponent per thread.
 #pragma once
 #include "ctc_pipe.cuh"
 
@@ -41,6 +55,7 @@ constexpr int kLinHmax = 44;            // clamp of the combine exponent (no ove
 constexpr float kMassTol = 3.0e-5f;     // |sum of occupancies - 1| per frame
 constexpr int kLinNone = -(1 << 28);    // exponent of a term that is exactly zero
 constexpr float kQ31 = 2147483648.0f;   // label occupancies are accumulated as Q1.31 fixed point
+constexpr int kLinYDist = 1;            // logits are requested kLinYDist + 1 chunks before their softmax
 
 __device__ __forceinline__ int clamp_exp(int e) { return max(min(e, 127), -127); }
 // 2^e for e in [-126, 127]; 0 for e <= -127 (flush); 2^127 above
@@ -49,11 +64,15 @@ __device__ __forceinline__ float pow2c(int e) { return __int_as_float((clamp_exp
 __device__ __forceinline__ int expo(float x) { return (__float_as_int(x) >> 23) - 127; }
 __device__ __forceinline__ int warp_max_i(int x) { return __reduce_max_sync(0xffffffffu, x); }
 
+// A plane of a lattice row holds thread t's P cells at [P * t, P * t + P) -- except for P = 8, where
+// the two 128-bit halves of a thread are split: cells 0..3 at [4 t, 4 t + 4), cells 4..7 at
+// [HS + 4 t, HS + 4 t + 4) with HS = half a plane.  Every 128-bit access of a warp then covers 512
+// contiguous bytes: no shared-memory bank conflicts, fully coalesced global stores.
 template <int P>
-__device__ __forceinline__ void store_row(float* dst, const float (&v)[P]) {
+__device__ __forceinline__ void store_row(float* dst, const float (&v)[P], int HS) {
     if constexpr (P == 8) {
         *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
-        *reinterpret_cast<float4*>(dst + 4) = make_float4(v[4], v[5], v[6], v[7]);
+        *reinterpret_cast<float4*>(dst + HS) = make_float4(v[4], v[5], v[6], v[7]);
     } else if constexpr (P == 4) {
         *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
     } else if constexpr (P == 2) {
@@ -64,10 +83,10 @@ __device__ __forceinline__ void store_row(float* dst, const float (&v)[P]) {
     }
 }
 template <int P>
-__device__ __forceinline__ void load_row(const float* src, float (&v)[P]) {
+__device__ __forceinline__ void load_row(const float* src, float (&v)[P], int HS) {
     if constexpr (P == 8) {
         const float4 a = *reinterpret_cast<const float4*>(src);
-        const float4 b = *reinterpret_cast<const float4*>(src + 4);
+        const float4 b = *reinterpret_cast<const float4*>(src + HS);
         v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
     } else if constexpr (P == 4) {
         const float4 a = *reinterpret_cast<const float4*>(src);
@@ -81,12 +100,45 @@ __device__ __forceinline__ void load_row(const float* src, float (&v)[P]) {
     }
 }
 
+// class slots of an occupancy row: V + 1 (padding pairs add their zeros to slot V), and a multiple
+// of 32 plus 16 so that the 4 frames of a chunk fall on alternating halves of the banks
+__host__ __device__ __forceinline__ int lin_occ_classes(int V) { return (V + 1 + 15) / 32 * 32 + 16; }
 // lattice row = [blank plane: NP][label plane: NP][per-thread exponents: NP / P]
 __host__ __device__ __forceinline__ int lin_row_stride(int NP, int P) { return 2 * NP + (NP / P + 3) / 4 * 4; }
 
+// Shared-memory carve-up, shared by host (size) and device (pointers).
+//   y:     NL x TC emission rows (Vs floats; slot V of a row holds 0 = what padding pairs gather)
+//   a:     2 x TC rows REC publishes in the second half of its sweep (row stride RS)
+//   stage: NS x TC partner lattice rows (TMA)
+//   occ:   2 x TC occupancy rows: per recursion warp [class sums, Q1.31: VO][blank partial sums: 32]
+struct LinSmem {
+    int lab, y, a, stage, occ, bnd, red, flag, bars, total;  // byte offsets
+    int Vs, VO, OW, ER, NL, NS;
+    __host__ __device__ static int up(int x, int a) { return (x + a - 1) / a * a; }
+    __host__ __device__ LinSmem(int NP, int R, int V, int TC, int RS, int ys) {
+        Vs = ys > 0 ? ys : up(V + 1, 4);
+        VO = ys > 0 ? 80 : lin_occ_classes(V);
+        OW = VO + 32;            // + 32 blank partial sums
+        ER = R * OW;
+        NL = kLinYDist + 5;      // requested kLinYDist+1 chunks early .. gradient 3 chunks later
+        NS = 3;                  // requested 2 chunks before COMB needs them
+        int o = 0;
+        lab = o;    o += up(NP * 4, 16);
+        y = o;      o += up(NL * TC * Vs * 4, 16);
+        a = o;      o += up(2 * TC * RS * 4, 16);
+        stage = o;  o += up(NS * TC * RS * 4, 16);
+        occ = o;    o += up(2 * TC * ER * 4, 16);
+        bnd = o;    o += up(2 * (R + 1) * 8, 16);
+        red = o;    o += 6 * 32 * 4;   // [0,64) renorm hand-over, [64..), [128..) reductions, [100,102) E0, 1/z
+        flag = o;   o += 16;
+        bars = o;   o += up((NL + NS) * 8, 16);
+        total = o;
+    }
+};
+
 // Template parameters: P pairs per thread; RC = number of recursion warps when it is known at
 // compile time (1: the common case S + P <= 32 * P, every stride becomes an immediate) or 0 for
-// "run time"; YS = floats per row of the emission ring (64 for V <= 60) or 0 for "run time".
+// "run time"; YS = floats per row of the emission ring (compile time) or 0 for "run time".
 template <int P, int RC, int YS, int MAXT, int MINB>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(MAXT, MINB)
 ctc_lin_kernel(const PipeParams pp, int* __restrict__ flags) {
@@ -97,35 +149,34 @@ ctc_lin_kernel(const PipeParams pp, int* __restrict__ flags) {
     const int lane = threadIdx.x & 31;
     const int shift = pp.rotate > 0 ? (int)((blockIdx.x / pp.rotate) * R) % NW : 0;
     const int w = ((int)(threadIdx.x >> 5) + NW - shift) % NW;   // role (virtual) warp id
-    const int tid = w * 32 + lane;
     const int b = p.utt_begin + (blockIdx.x >> 1);
     const bool rev = (blockIdx.x & 1) != 0;
     const int T = p.T, N = p.N, V = p.V, blank = p.blank;
-    const int RS = RC > 0 ? lin_row_stride(32 * P * RC, P) : p.row_stride, TC = p.chunk, D = pp.D;
-    const bool is_rec = w < R;
-    const int hw = w - R;  // helper index (>= 0 for helpers)
+    const int RS = RC > 0 ? lin_row_stride(32 * P * RC, P) : p.row_stride, TC = p.chunk;
+    const int NC = pp.D;           // combine groups: group g takes the rows r == g (mod NC) of a chunk
+    const bool is_rec = w < R, is_comb = w >= R && w < (1 + NC) * R;
+    const int hw = w - (1 + NC) * R;   // helper index (>= 0 for SOFT / GRAD warps)
+    const int cg = is_comb ? (w - R) / R : 0;
+    // REC and COMB warps share the thread <-> lattice slot mapping
+    const int tid = (is_comb ? (w - R) % R : w) * 32 + lane;
 
-    // occupancy row of one frame: per recursion warp [class sums: VO][blank partial sums: 32]
-    const int VO = YS > 0 ? YS : PipeSmem::up(V + 1, 4);
-    const int OW = VO + 32, ER = R * OW;
-    const PipeSmem lay(NP, R, V, TC, RS, D, YS, ER);
-    const int Vs = YS > 0 ? YS : lay.Vs, NL = lay.NL, NS = lay.NS;
+    const LinSmem lay(NP, R, V, TC, RS, YS);
+    const int Vs = YS > 0 ? YS : lay.Vs, VO = YS > 0 ? 80 : lay.VO, OW = VO + 32, ER = R * OW;
+    const int NL = lay.NL, NS = lay.NS;
     int* s_lab = reinterpret_cast<int*>(smem_raw + lay.lab);
-    int* s_pos = reinterpret_cast<int*>(smem_raw + lay.pos);
-    int* s_cstart = reinterpret_cast<int*>(smem_raw + lay.cstart);
-    int* s_fill = reinterpret_cast<int*>(smem_raw + lay.fill);
-    float* s_y = reinterpret_cast<float*>(smem_raw + lay.lp2);      // emission probabilities ring
-    float* s_e = reinterpret_cast<float*>(smem_raw + lay.e);
+    float* s_y = reinterpret_cast<float*>(smem_raw + lay.y);
+    float* s_a = reinterpret_cast<float*>(smem_raw + lay.a);
     float* s_stage = reinterpret_cast<float*>(smem_raw + lay.stage);
+    float* s_occ = reinterpret_cast<float*>(smem_raw + lay.occ);
     float2* s_bnd = reinterpret_cast<float2*>(smem_raw + lay.bnd);
-    float* s_red = reinterpret_cast<float*>(smem_raw + lay.red);
-    int* s_flag = reinterpret_cast<int*>(smem_raw + lay.ll);        // [0] redo, [1] no gradient rows
+    int* s_red = reinterpret_cast<int*>(smem_raw + lay.red);         // [6][32]
+    int* s_flag = reinterpret_cast<int*>(smem_raw + lay.flag);       // [0] redo, [1] no gradient rows
     uint64_t* bar_acts = reinterpret_cast<uint64_t*>(smem_raw + lay.bars);   // [NL]
     uint64_t* bar_part = bar_acts + NL;                                      // [NS]
 
     int Tb = p.in_lens[b], S = p.tgt_lens[b];
     if (Tb < 0 || Tb > T || S < 0 || S > NP - P) {
-        if (tid == 0) atomicOr(p.status, kStatusBadLength);
+        if (threadIdx.x == 0) atomicOr(p.status, kStatusBadLength);
         Tb = min(max(Tb, 0), T);
         S = min(max(S, 0), NP - P);
     }
@@ -135,19 +186,24 @@ ctc_lin_kernel(const PipeParams pp, int* __restrict__ flags) {
     const size_t frame_stride = (size_t)N * V;
     const float* acts_b = p.acts + (size_t)b * V;
     float* grad_b = want_grad ? p.grad + (size_t)b * V : nullptr;
-    const int V4 = V >> 2;
+    const int V4 = V >> 2, V2 = V >> 1;
 
-    // ---- helpers: mandatory zero fill of gradient rows t >= T_b (no compute) --------
-    if (want_grad && !is_rec) {
+    // helper roles: SOFT warps [0, nA), GRAD warps [nA, H); a single helper does both
+    const int nA = H >= 2 ? H / 2 : 1, nB = H >= 2 ? H - nA : 1;
+    const bool isA = hw >= 0 && (H == 1 || hw < nA), isB = hw >= 0 && (H == 1 || hw >= nA);
+    const int ha = hw, hb = H == 1 ? 0 : hw - nA;
+
+    // ---- GRAD warps: mandatory zero fill of gradient rows t >= T_b (no compute) --------
+    if (want_grad && isB) {
         const int nrows = T - Tb;
         const int mine = (nrows + (rev ? 0 : 1)) >> 1;  // rows Tb+rev, Tb+rev+2, ...
-        float* g = grad_b + (size_t)(Tb + (rev ? 1 : 0) + 2 * hw) * frame_stride;
-        const size_t ginc = 2 * (size_t)H * frame_stride;
-        for (int r = hw; r < mine; r += H, g += ginc)
+        float* g = grad_b + (size_t)(Tb + (rev ? 1 : 0) + 2 * hb) * frame_stride;
+        const size_t ginc = 2 * (size_t)nB * frame_stride;
+        for (int r = hb; r < mine; r += nB, g += ginc)
             for (int c = lane; c < V4; c += 32) reinterpret_cast<float4*>(g)[c] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
     if (Tb == 0) {  // torch: empty input => 0 for an empty target, +inf otherwise
-        if (tid == 0) {
+        if (threadIdx.x == 0) {
             flags[2 * b + (rev ? 1 : 0)] = 0;
             if (!rev) p.nll[b] = (S == 0 || p.zero_infinity) ? 0.0f : CUDART_INF_F;
         }
@@ -160,7 +216,7 @@ ctc_lin_kernel(const PipeParams pp, int* __restrict__ flags) {
     // label slot SS - 1 - s.
     const int SS = S + ((P - 1 - S) & (P - 1));
     const int delta = rev ? 0 : SS - S;
-    for (int s = tid; s < NP; s += NT) {
+    for (int s = threadIdx.x; s < NP; s += NT) {
         const int i = s - delta;
         int c = V;  // padding pairs gather the zero slot of the y row
         if (i >= 0 && i < S) {
@@ -172,9 +228,9 @@ ctc_lin_kernel(const PipeParams pp, int* __restrict__ flags) {
         }
         s_lab[s] = c;
     }
-    for (int i = tid; i < 2 * (R + 1); i += NT) s_bnd[i] = make_float2(0.f, 0.f);
-    for (int i = tid; i < 2 * TC * ER; i += NT) s_e[i] = 0.f;   // occupancy accumulators start at 0
-    if (tid == 0) {
+    for (int i = threadIdx.x; i < 2 * (R + 1); i += NT) s_bnd[i] = make_float2(0.f, 0.f);
+    for (int i = threadIdx.x; i < 2 * TC * ER; i += NT) s_occ[i] = 0.f;   // occupancy accumulators start at 0
+    if (threadIdx.x == 0) {
         s_flag[0] = 0; s_flag[1] = 0;
         for (int i = 0; i < NL; ++i) mbar_init(bar_acts + i, 32);   // 32 lanes' cp.async
         for (int i = 0; i < NS; ++i) mbar_init(bar_part + i, 1);    // one TMA producer
@@ -182,6 +238,7 @@ ctc_lin_kernel(const PipeParams pp, int* __restrict__ flags) {
         fence_proxy_async();
     }
     __syncthreads();
+
     // ---- sweep geometry (see ctc_pipe.cuh; identical band logic, pair i = slot - delta) ------
     const int C = max(Tb - S, -1);
     const int Tm = Tb >> 1;
@@ -191,48 +248,46 @@ ctc_lin_kernel(const PipeParams pp, int* __restrict__ flags) {
     const int n1 = (n_store + TC - 1) / TC;
     const int n2 = want_grad ? (Tb - n_store + TC - 1) / TC : (Tb > n_store ? 1 : 0);
     const int nch = n1 + n2;
+    const int n_it = nch + 3;      // SOFT chunk it, REC it-1, COMB it-2, GRAD it-3
     auto chunk_at = [&](int c, int& tt0, int& rows) {  // first sweep step / row count of chunk c
         if (c < n1) { tt0 = c * TC; rows = min(TC, n_store - tt0); }
         else { tt0 = n_store + (c - n1) * TC; rows = want_grad ? min(TC, Tb - tt0) : 1; }
     };
+    const int s0 = tid * P;          // my first slot (REC / COMB)
+    const int PW = P == 8 ? 4 : P;   // floats per thread in one contiguous piece of a plane
+    const int s0p = tid * PW;        // where my cells start inside a plane
+    const int HS = NP / 2;           // P == 8: distance between the two halves of a thread
+    const int i0 = s0 - delta;       // my first pair (may be negative: leading padding)
+    const int row_step = tsign * RS;
 
 #ifdef CTC_B200_PROFILE
     // developer instrumentation: busy cycles of CTA 0 -> workspace header (u64 at +64):
-    // [0/1] REC phase 1/2, [2/3] helper 0 phase 1/2, [4/5] helper 1 phase 1/2, [6] wall, [7] iterations,
-    // [8] issue [9] gradient [10] logits wait [11] softmax of helper 0 (both phases)
+    // [0/1] REC phase 1/2, [2/3] COMB, [4/5] SOFT 0, [6/7] GRAD 0, [8] wall, [9] iterations
     unsigned long long* prof = reinterpret_cast<unsigned long long*>(reinterpret_cast<char*>(p.status) + 64);
-    const bool prof_on = blockIdx.x == 0 && lane == 0 && (w == 0 || w == R || w == R + 1);
-    const int prof_role = w == 0 ? 0 : (w == R ? 2 : 4);
-    long long prof_t0 = clock64(), prof_t1 = prof_t0;
+    const int prof_role = w == 0 ? 0 : (w == R ? 2 : (hw == 0 ? 4 : (hw == nA ? 6 : -1)));
+    const bool prof_on = blockIdx.x == 0 && lane == 0 && prof_role >= 0;
+    long long prof_t0 = clock64();
     const long long prof_start = prof_t0;
-#define LPROF_BEGIN() do { prof_t0 = clock64(); prof_t1 = prof_t0; } while (0)
+#define LPROF_BEGIN() do { prof_t0 = clock64(); } while (0)
 #define LPROF_END(phase2) do { if (prof_on) atomicAdd(prof + prof_role + ((phase2) ? 1 : 0), (unsigned long long)(clock64() - prof_t0)); } while (0)
-#define LPROF_SEC(slot) do { if (prof_on && w == R) atomicAdd(prof + (slot), (unsigned long long)(clock64() - prof_t1)); prof_t1 = clock64(); } while (0)
 #else
 #define LPROF_BEGIN() do {} while (0)
 #define LPROF_END(phase2) do {} while (0)
-#define LPROF_SEC(slot) do {} while (0)
 #endif
 
     if (is_rec) {
         // =============================================================================
         // REC: lattice recursion on probabilities
         // =============================================================================
-        const int s0 = tid * P;          // my first slot
-        const int i0 = s0 - delta;       // my first pair (may be negative: leading padding)
         float skf[P];                    // 1 if label cell k also takes the skip transition, else 0
         const float* yk[P];              // &y[label k] in row 0 of the current chunk of the emission ring
-        unsigned* ok[P];                 // &occupancy[label k] in row 0 of the current occupancy chunk
         int lab[P];
-        bool vB[P], vY[P];
         float aB[P], aY[P];
 #pragma unroll
         for (int k = 0; k < P; ++k) {
             const int i = i0 + k;
             lab[k] = s_lab[s0 + k];
             skf[k] = (i >= 1 && i < S && lab[k] != s_lab[s0 + k - 1]) ? 1.0f : 0.0f;
-            vB[k] = i >= 0 && i <= S;
-            vY[k] = i >= 0 && i < S;
             aB[k] = 0.f;
             aY[k] = 0.f;
         }
@@ -242,21 +297,8 @@ ctc_lin_kernel(const PipeParams pp, int* __restrict__ flags) {
             for (int k = 0; k < P; ++k) if (i0 + k == 0) aB[k] = 1.0f;
             off = 0;
         }
-        // partner thread of my P cells (blank k <-> its blank P-1-k; label k <-> its label P-2-k,
-        // my last label <-> the last label of the thread below it)
-        const int M = (SS - (P - 1)) / P;
-        const int X = M - tid;
-        const bool hasX = X >= 0 && X < 32 * R, hasX1 = X >= 1 && X - 1 < 32 * R;
-        int E0 = 0;                      // integer part of log2 P(labels | logits)
-        float rz = 0.f;                  // 1 / mantissa sum: occupancy = a * p~ * 2^(off+o-E0) * rz
         // thread / warp activity windows in sweep steps (widened by P pairs, see ctc_pipe.cuh)
         unsigned win_store = (i0 - P <= S) ? (unsigned)(C + 3 * P) : 0u;   // (u + P) < win
-        unsigned win_cons = (i0 <= S && hasX) ? (unsigned)(C + P) : 0u;    // u < win
-        // per-step constants live in registers (the compiler would otherwise re-derive them from the
-        // kernel parameters inside the unrolled steps)
-        int wg_i = want_grad ? 1 : 0, c_i = C;
-        const int offd = 2 * NP + tid - s0;   // my exponent's position relative to my blank vector
-        asm volatile("" : "+r"(win_store), "+r"(win_cons), "+r"(wg_i), "+r"(c_i));
         const int iw = 32 * P * w - delta;   // first pair of my warp
         const int w_first = (iw - P <= S) ? iw - P : 0x3fffffff;
         const int w_last = C + iw + 32 * P - 1 + P;
@@ -264,8 +306,12 @@ ctc_lin_kernel(const PipeParams pp, int* __restrict__ flags) {
         float2* bnd_wr = s_bnd + (R + 1) + w + 1;
         const bool lane0 = lane == 0, lane31 = (lane == 31) && R > 1;
         const int nbar = 32 * R;
+        // per-step constants live in registers (the compiler would otherwise re-derive them from the
+        // kernel parameters inside the unrolled steps)
+        int wg_i = want_grad ? 1 : 0, c_i = C;
+        const int offd = 2 * NP + tid - s0p;  // my exponent's position relative to my blank vector
+        asm volatile("" : "+r"(win_store), "+r"(wg_i), "+r"(c_i));
         const bool wg = wg_i != 0;
-        const int row_step = tsign * RS;
         int u = -i0;                     // sweep step minus my first pair: tt - i0
         int rn_par = 0;
 
@@ -293,7 +339,7 @@ ctc_lin_kernel(const PipeParams pp, int* __restrict__ flags) {
             if constexpr (RC == 1) {
                 if (lane0) e_in = kLinFresh;
             } else {
-                int* red = reinterpret_cast<int*>(s_red) + (rn_par ? 32 : 0);   // double buffered
+                int* red = s_red + (rn_par ? 32 : 0);          // double buffered
                 rn_par ^= 1;
                 if (lane == 31) red[w + 1] = e_top;
                 if (tid == 0) red[0] = kLinFresh;
@@ -347,10 +393,10 @@ ctc_lin_kernel(const PipeParams pp, int* __restrict__ flags) {
         };
         auto warp_on = [&](int tt) { return RC == 1 ? true : (tt >= w_first && tt <= w_last); };
 
-        Ring ring_y(NL), ring_part(NS);   // position of the chunk REC works on
-        int e_buf = 0;
+        Ring ring_y(NL);                  // position of the chunk REC works on
+        int a_buf = 0;
         renorm();                         // normalises the start value
-        for (int it = 0; it < nch + 2; ++it) {
+        for (int it = 0; it < n_it; ++it) {
             const int k = it - 1;
             LPROF_BEGIN();
             if (k >= 0 && k < nch) {
@@ -361,10 +407,10 @@ ctc_lin_kernel(const PipeParams pp, int* __restrict__ flags) {
 #pragma unroll
                 for (int q = 0; q < P; ++q) yk[q] = ychunk + lab[q];
                 if (k < n1) {
-                    // ---- store chunk: pre-emission rows go to HBM for the partner ----------
+                    // ---- first half: pre-emission rows go to HBM for the partner ----------
                     // one running offset from the lattice base; everything else is an immediate
                     long long roff = (long long)(b - p.utt_begin) * p.lat_utt_stride +
-                                     (long long)(tbase + tsign * tt0) * RS + s0;
+                                     (long long)(tbase + tsign * tt0) * RS + s0p;
                     asm volatile("" : "+l"(roff));
                     float* row = p.lattice + roff;
                     const int last_r = (wg || k < n1 - 1) ? -1 : rows - 1;   // forward only: just the last row
@@ -375,8 +421,8 @@ ctc_lin_kernel(const PipeParams pp, int* __restrict__ flags) {
                             float xs[P], ins[P];
                             advance(yb_ptr, r * Vs, xs, ins);
                             if ((wg || r == last_r) && (unsigned)(u + P) < win_store) {
-                                store_row<P>(row, xs);
-                                store_row<P>(row + NP, ins);
+                                store_row<P>(row, xs, HS);
+                                store_row<P>(row + NP, ins, HS);
                                 *reinterpret_cast<int*>(row + offd) = off;
                             }
                         }
@@ -384,26 +430,112 @@ ctc_lin_kernel(const PipeParams pp, int* __restrict__ flags) {
                         end_step();
                         if (P < 4 && (r + 1) % P == 0 && r + 1 < rows) renorm();
                     }
-                    renorm();
                 } else {
-                    // ---- consume chunk: combine with the partner's stored rows ----------
-                    mbar_wait(bar_part + ring_part.slot, ring_part.parity);   // TMA data landed
-                    const float* st = s_stage + ((size_t)ring_part.slot * TC + (rev ? rows - 1 : 0)) * RS;
-                    // occupancies: label cells are ADDED to their class slot as Q1.31 fixed point with
-                    // native shared-memory integer atomics (order-independent, hence bit-reproducible;
-                    // quantum 4.7e-10); blank cells are summed per thread in fp32
-                    float* orow = s_e + (size_t)e_buf * TC * ER + w * OW;
+                    // ---- second half: post-emission rows go to the shared-memory ring for COMB ----
+                    float* arow = s_a + (size_t)a_buf * TC * RS + s0p;
 #pragma unroll
-                    for (int q = 0; q < P; ++q) ok[q] = reinterpret_cast<unsigned*>(orow) + lab[q];
-                    float* obl = orow + VO + lane;
-                    const float* stp = st + (hasX ? X * P : 0);         // partner thread's P blanks
-                    const int* sto = reinterpret_cast<const int*>(st + 2 * NP) + (hasX ? X : 0);
-                    float pb[P], py[P];    // partner cells matching my blank k / label k
+                    for (int r = 0; r < 4; ++r) {
+                        if (r >= rows) break;
+                        if (warp_on(tt0 + r)) {
+                            float xs[P], ins[P];
+                            advance(yb_ptr, r * Vs, xs, ins);
+                        }
+                        // (a warp outside the band publishes its zeros / stale cells: COMB masks them)
+                        store_row<P>(arow + r * RS, aB, HS);
+                        store_row<P>(arow + r * RS + NP, aY, HS);
+                        *reinterpret_cast<int*>(arow + r * RS + offd) = off;
+                        end_step();
+                        if (P < 4 && (r + 1) % P == 0 && r + 1 < rows) renorm();
+                    }
+                    a_buf ^= 1;
+                }
+                renorm();
+                ring_y.advance();
+            }
+            LPROF_END(k >= n1);
+            __syncthreads();
+            if (it == n1) {  // phase break (see the COMB branch)
+                cluster_sync_all();
+                __syncthreads();
+            }
+        }
+    } else if (is_comb) {
+        // =============================================================================
+        // COMB: occupancies of the second half = REC's row x the partner's stored row
+        // =============================================================================
+        const int wc = (w - R) % R;      // which recursion warp I shadow
+        int lab[P];
+        bool vB[P], vY[P];
+#pragma unroll
+        for (int k = 0; k < P; ++k) {
+            const int i = i0 + k;
+            lab[k] = s_lab[s0 + k];
+            vB[k] = i >= 0 && i <= S;
+            vY[k] = i >= 0 && i < S;
+        }
+        // partner thread of my P cells (blank k <-> its blank P-1-k; label k <-> its label P-2-k,
+        // my last label <-> the last label of the thread below it)
+        const int M = (SS - (P - 1)) / P;
+        const int X = M - tid;
+        const bool hasX = X >= 0 && X < 32 * R, hasX1 = X >= 1 && X - 1 < 32 * R;
+        const unsigned win_cons = (i0 <= S && hasX) ? (unsigned)(C + P) : 0u;    // (tt - i0) < win
+        const int offd = 2 * NP + tid - s0p;
+        const int nbar = 32 * R;
+        int E0 = 0;                      // integer part of log2 P(labels | logits)
+        float rz = 0.f;                  // 1 / mantissa sum: occupancy = a * p~ * 2^(off+o-E0) * rz
+        const bool iss_part = cg == 0 && wc == 0;   // this warp also requests the partner's rows (TMA)
+        auto issue_partner = [&](int kp, int slot) {
+            if (lane == 0) {
+                int tt0, rows;
+                chunk_at(kp, tt0, rows);
+                uint64_t* bar = bar_part + slot;
+                const int t_lo = rev ? tbase - (tt0 + rows - 1) : tt0;
+                mbar_expect_tx(bar, (unsigned)(rows * RS) * 4u);
+                bulk_g2s(s_stage + (size_t)slot * TC * RS, lat_b + (ptrdiff_t)t_lo * RS,
+                         (unsigned)(rows * RS) * 4u, bar);
+            }
+        };
+        Ring ring_part(NS), iss_p(NS);
+        int a_buf = 0, o_buf = 0;
+        for (int it = 0; it < n_it; ++it) {
+            LPROF_BEGIN();
+            // partner rows of chunk `it` (consumed in iteration it+2); the first two consume chunks
+            // are requested at the phase break
+            if (it >= n1 + 2 && it < nch && want_grad) {
+                if (iss_part) issue_partner(it, iss_p.slot);
+                iss_p.advance();
+            }
+            const int k = it - 2;
+            if (k >= n1 && k < nch) {
+                int tt0, rows;
+                chunk_at(k, tt0, rows);
+                // the chunk with the first combined row is done by group 0 alone (it yields E0 and
+                // 1/z, which the other groups pick up from shared memory one barrier later)
+                const bool first = k == n1;
+                if (k == n1 + 1 && cg > 0) { E0 = s_red[100]; rz = __int_as_float(s_red[101]); }
+                const int r_begin = first ? 0 : cg, r_inc = first ? 1 : NC;
+                if (!first || cg == 0) {
+                mbar_wait(bar_part + ring_part.slot, ring_part.parity);   // TMA data landed
+                const float* st = s_stage + (size_t)ring_part.slot * TC * RS;
+                const float* arow = s_a + (size_t)a_buf * TC * RS + s0p;
+                float* orow = s_occ + (size_t)o_buf * TC * ER + wc * OW;
+                unsigned* ocl = reinterpret_cast<unsigned*>(orow);
+                float* obl = orow + VO + lane;
+                for (int r = r_begin; r < rows; r += r_inc) {
+                    const int u = tt0 + r - i0;
+                    // the chunk was staged in frame order: the reversed sweep walks it backwards
+                    const float* str = st + (size_t)(rev ? rows - 1 - r : r) * RS;
+                    const float* stp = str + (hasX ? X * PW : 0);        // partner thread's P blanks
+                    const int* sto = reinterpret_cast<const int*>(str + 2 * NP) + (hasX ? X : 0);
+                    float aB[P], aY[P], pb[P], py[P];
+                    load_row<P>(arow + r * RS, aB, HS);
+                    load_row<P>(arow + r * RS + NP, aY, HS);
+                    const int off = *reinterpret_cast<const int*>(arow + r * RS + offd);
                     int ob, oy;            // partner exponents: of thread X and of thread X-1
-                    auto fetch = [&]() {
+                    {
                         float qb[P], qy[P];
-                        load_row<P>(stp, qb);
-                        load_row<P>(stp + NP, qy);
+                        load_row<P>(stp, qb, HS);
+                        load_row<P>(stp + NP, qy, HS);
                         ob = *sto;
 #pragma unroll
                         for (int q = 0; q < P; ++q) pb[q] = qb[P - 1 - q];
@@ -413,39 +545,32 @@ ctc_lin_kernel(const PipeParams pp, int* __restrict__ flags) {
                         // lane+1 of my warp talks to; lane 31 reads it itself
                         float yl = __shfl_down_sync(0xffffffffu, qy[P - 1], 1);
                         int ol = __shfl_down_sync(0xffffffffu, ob, 1);
-                        if (lane == 31 && hasX1) { yl = stp[NP - 1]; ol = sto[-1]; }
+                        if (lane == 31 && hasX1) { yl = stp[NP + (P == 8 ? HS : 0) - 1]; ol = sto[-1]; }
                         py[P - 1] = yl;
                         oy = ol;
-                    };
-                    int r0 = 0;
-                    if (k == n1) {
+                    }
+                    const bool in_win = (unsigned)u < win_cons;
+                    float bsum = 0.f;
+                    if (first && r == 0) {
                         // first combined row: also yields the likelihood P = sum_s a * p~.
                         // Exponent/mantissa form: E0 = max exponent of any term, z = sum of the
                         // terms scaled by 2^-E0; log2 P = E0 + log2 z.
                         float tB[P], tY[P];
                         int eB[P], eY[P];
 #pragma unroll
-                        for (int q = 0; q < P; ++q) { tB[q] = 0.f; tY[q] = 0.f; eB[q] = kLinNone; eY[q] = kLinNone; }
-                        if (warp_on(tt0)) {
-                            float xs[P], ins[P];
-                            fetch();
-                            advance(yb_ptr, 0, xs, ins);
-                            if ((unsigned)u < win_cons) {
-#pragma unroll
-                                for (int q = 0; q < P; ++q) {
-                                    if (vB[q] && aB[q] > 0.f && pb[q] > 0.f) {
-                                        const int ea = expo(aB[q]), ep = expo(pb[q]);
-                                        tB[q] = (aB[q] * pow2c(-ea)) * (pb[q] * pow2c(-ep));
-                                        eB[q] = ea + ep + off + ob;
-                                    }
-                                    const bool okY = q + 1 < P ? true : hasX1;
-                                    const int oq = q + 1 < P ? ob : oy;
-                                    if (vY[q] && okY && aY[q] > 0.f && py[q] > 0.f) {
-                                        const int ea = expo(aY[q]), ep = expo(py[q]);
-                                        tY[q] = (aY[q] * pow2c(-ea)) * (py[q] * pow2c(-ep));
-                                        eY[q] = ea + ep + off + oq;
-                                    }
-                                }
+                        for (int q = 0; q < P; ++q) {
+                            tB[q] = 0.f; tY[q] = 0.f; eB[q] = kLinNone; eY[q] = kLinNone;
+                            if (in_win && vB[q] && aB[q] > 0.f && pb[q] > 0.f) {
+                                const int ea = expo(aB[q]), ep = expo(pb[q]);
+                                tB[q] = (aB[q] * pow2c(-ea)) * (pb[q] * pow2c(-ep));
+                                eB[q] = ea + ep + off + ob;
+                            }
+                            const bool okY = q + 1 < P ? true : hasX1;
+                            const int oq = q + 1 < P ? ob : oy;
+                            if (in_win && vY[q] && okY && aY[q] > 0.f && py[q] > 0.f) {
+                                const int ea = expo(aY[q]), ep = expo(py[q]);
+                                tY[q] = (aY[q] * pow2c(-ea)) * (py[q] * pow2c(-ep));
+                                eY[q] = ea + ep + off + oq;
                             }
                         }
                         int em = kLinNone;
@@ -453,10 +578,10 @@ ctc_lin_kernel(const PipeParams pp, int* __restrict__ flags) {
                         for (int q = 0; q < P; ++q) em = max(em, max(eB[q], eY[q]));
                         em = warp_max_i(em);
                         if (R > 1) {
-                            if (lane0) reinterpret_cast<int*>(s_red)[w] = em;
-                            named_bar_sync(1, nbar);
-                            for (int i = 0; i < R; ++i) em = max(em, reinterpret_cast<int*>(s_red)[i]);
-                            named_bar_sync(1, nbar);
+                            if (lane == 0) s_red[64 + wc] = em;
+                            named_bar_sync(2, nbar);
+                            for (int i = 0; i < R; ++i) em = max(em, s_red[64 + i]);
+                            named_bar_sync(2, nbar);
                         }
                         const bool dead = em == kLinNone;      // no path survived (infeasible or underflow)
                         E0 = dead ? 0 : em;
@@ -469,96 +594,72 @@ ctc_lin_kernel(const PipeParams pp, int* __restrict__ flags) {
                         }
                         z = warp_sum(z);
                         if (R > 1) {
-                            if (lane0) s_red[w] = z;
-                            named_bar_sync(1, nbar);
+                            if (lane == 0) s_red[128 + wc] = __float_as_int(z);
+                            named_bar_sync(2, nbar);
                             z = 0.f;
-                            for (int i = 0; i < R; ++i) z += s_red[i];
-                            named_bar_sync(1, nbar);
+                            for (int i = 0; i < R; ++i) z += __int_as_float(s_red[128 + i]);
+                            named_bar_sync(2, nbar);
                         }
                         const bool bad = dead || !(z > 0.f) || !(z < 3.0e38f);
                         rz = bad ? 0.f : 1.0f / z;
                         if (tid == 0) {
+                            s_red[100] = E0;
+                            s_red[101] = __float_as_int(rz);
                             if (bad) { s_flag[0] = 1; s_flag[1] = 1; }
                             if (!rev) p.nll[b] = bad ? 0.f : (float)(-((double)E0 + (double)log2f(z)) * kLn2);
                         }
-                        if (wg) {
-                            float bsum = 0.f;
+                        if (want_grad) {
 #pragma unroll
                             for (int q = 0; q < P; ++q) {
                                 bsum += tB[q] * rz;
-                                atomicAdd(ok[q], __float2uint_rn(tY[q] * (rz * kQ31)));
+                                atomicAdd(ocl + r * ER + lab[q], __float2uint_rn(tY[q] * (rz * kQ31)));
                             }
-                            *obl = bsum;
                         }
-                        end_step();
-                        stp += row_step;
-                        sto += row_step;
-                        r0 = 1;
-                    }
-                    if (wg) {
+                    } else if (in_win) {
+                        // occupancy = a * p~ * 2^(off + o - E0) / z   (exact exponents); cells outside
+                        // [0, S] are exact zeros on REC's side, partner vectors are finite
+                        // (label cells directly in Q1.31 units)
+                        const float sb = pow2c(min(off + ob - E0, kLinHmax)) * rz;
+                        const float sq = sb * kQ31;
+                        const float sy = hasX1 ? pow2c(min(off + oy - E0, kLinHmax)) * (rz * kQ31) : 0.f;
 #pragma unroll
-                        for (int r = 0; r < 4; ++r) {
-                            if (r < r0) continue;
-                            if (r >= rows) break;
-                            float gB[P], gY[P];
-#pragma unroll
-                            for (int q = 0; q < P; ++q) { gB[q] = 0.f; gY[q] = 0.f; }
-                            if (warp_on(tt0 + r)) {
-                                float xs[P], ins[P];
-                                fetch();
-                                advance(yb_ptr, r * Vs, xs, ins);
-                                    if ((unsigned)u < win_cons) {
-                                    // occupancy = a * p~ * 2^(off + o - E0) / z   (exact exponents); cells
-                                    // outside [0, S] are exact zeros on my side, partner vectors are finite
-                                    // (label cells directly in Q1.31 units)
-                                    const float sb = pow2c(min(off + ob - E0, kLinHmax)) * rz;
-                                    const float sq = sb * kQ31;
-                                    const float sy = hasX1 ? pow2c(min(off + oy - E0, kLinHmax)) * (rz * kQ31) : 0.f;
-#pragma unroll
-                                    for (int q = 0; q < P; ++q) {
-                                        gB[q] = aB[q] * (pb[q] * sb);
-                                        if (q + 1 < P) gY[q] = aY[q] * (py[q] * sq);
-                                    }
-                                    if (hasX1) gY[P - 1] = aY[P - 1] * (py[P - 1] * sy);
-                                }
-                            }
-                            float bsum = 0.f;
-#pragma unroll
-                            for (int q = 0; q < P; ++q) {
-                                bsum += gB[q];
-                                atomicAdd(ok[q] + r * ER, __float2uint_rn(gY[q]));
-                            }
-                            obl[r * ER] = bsum;
-                            stp += row_step;
-                            sto += row_step;
-                            end_step();
-                            if (P < 4 && (r + 1) % P == 0 && r + 1 < rows) renorm();
+                        for (int q = 0; q < P; ++q) {
+                            bsum += aB[q] * (pb[q] * sb);
+                            float gy = 0.f;
+                            if (q + 1 < P) gy = aY[q] * (py[q] * sq);
+                            else if (hasX1) gy = aY[q] * (py[q] * sy);
+                            atomicAdd(ocl + r * ER + lab[q], __float2uint_rn(gy));
                         }
                     }
-                    renorm();
-                    ring_part.advance();
-                    e_buf ^= 1;
+                    if (want_grad) obl[r * ER] = bsum;
                 }
-                ring_y.advance();
+                }
+                ring_part.advance();
+                a_buf ^= 1;
+                o_buf ^= 1;
             }
-            LPROF_END(k >= n1);
+            LPROF_END(it >= n1 + 2);
             __syncthreads();
-            if (it == n1) {  // phase break (see the helper branch)
+            if (it == n1) {
+                // Phase break: my REC warps have stored every row the partner will consume,
+                // and (after the cluster barrier) vice versa.
                 cluster_sync_all();
+                if (iss_part) {
+                    fence_proxy_async();
+                    for (int kk = n1; kk < n1 + 2; ++kk) {
+                        if (kk < nch && (want_grad || kk == n1)) issue_partner(kk, iss_p.slot);
+                        iss_p.advance();
+                    }
+                }
                 __syncthreads();
             }
         }
     } else {
         // =============================================================================
-        // HELP: staging producer, fused softmax, gradient rows
+        // SOFT / GRAD: logits staging + fused softmax; gradient rows
         // =============================================================================
-        // Helpers [0, nA) are "A": logits staging + softmax; helpers [nA, H) are "B": partner staging
-        // + gradient rows (H == 1: one warp does both).  A helper owns F = TC / n frames of every
-        // chunk and works on all of them AT ONCE, a group of G = 32 / F lanes per frame, so that one
-        // pass of short shuffle trees (log2 G levels) finishes the chunk.
-        const int nA = H >= 2 ? H / 2 : 1, nB = H >= 2 ? H - nA : 1;
-        const bool isA = H == 1 || hw < nA, isB = H == 1 || hw >= nA;
-        const int ha = hw, hb = H == 1 ? 0 : hw - nA;
+        // A helper owns F = TC / n frames of every chunk and works on all of them AT ONCE, a group
+        // of G = 32 / F lanes per frame, so that one pass of short shuffle trees finishes the chunk.
         const int FA = max(TC / nA, 1), FB = max(TC / nB, 1);
         auto group_sum = [&](float x, int G) {
             for (int o = G >> 1; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
@@ -569,9 +670,8 @@ ctc_lin_kernel(const PipeParams pp, int* __restrict__ flags) {
             return x;
         };
 
-        // ---- staging of one chunk ---------------------------------------------------------
-        //   logits rows of chunk ka: cp.async, 16 B per lane and copy; a lane's (row, column) of its
-        //   first two copies never change, so they are computed once
+        // ---- logits rows of a chunk: cp.async, 16 B per lane and copy; a lane's (row, column) of
+        //      its first two copies never change, so they are computed once
         const ptrdiff_t a_inc = (ptrdiff_t)tsign * (ptrdiff_t)frame_stride;
         const int n4 = TC * V4;
         int cp_dst[2], cp_row[2];
@@ -583,39 +683,27 @@ ctc_lin_kernel(const PipeParams pp, int* __restrict__ flags) {
             cp_dst[j] = r * Vs + 4 * c;
             cp_src[j] = r * a_inc + 4 * c;
         }
-        auto issue_chunk = [&](int ka, int slot_a, int kp, int slot_p) {
-            if (ka >= 0) {
-                int tt0, rows;
-                chunk_at(ka, tt0, rows);
-                float* dst = s_y + (size_t)slot_a * TC * Vs;
-                const float* src = acts_b + (ptrdiff_t)(tbase + tsign * tt0) * (ptrdiff_t)frame_stride;
+        auto issue_logits = [&](int ka, int slot_a) {
+            int tt0, rows;
+            chunk_at(ka, tt0, rows);
+            float* dst = s_y + (size_t)slot_a * TC * Vs;
+            const float* src = acts_b + (ptrdiff_t)(tbase + tsign * tt0) * (ptrdiff_t)frame_stride;
 #pragma unroll
-                for (int j = 0; j < 2; ++j)
-                    if (cp_row[j] < rows) cp_async16(dst + cp_dst[j], src + cp_src[j]);
-                if (n4 > 64) {
-                    int r = 64 / V4, c = 64 - r * V4 + lane;
+            for (int j = 0; j < 2; ++j)
+                if (cp_row[j] < rows) cp_async16(dst + cp_dst[j], src + cp_src[j]);
+            if (n4 > 64) {
+                int r = 64 / V4, c = 64 - r * V4 + lane;
+                while (c >= V4) { c -= V4; ++r; }
+                while (r < rows) {
+                    cp_async16(dst + r * Vs + 4 * c, src + r * a_inc + 4 * c);
+                    c += 32;
                     while (c >= V4) { c -= V4; ++r; }
-                    while (r < rows) {
-                        cp_async16(dst + r * Vs + 4 * c, src + r * a_inc + 4 * c);
-                        c += 32;
-                        while (c >= V4) { c -= V4; ++r; }
-                    }
                 }
-                cp_async_arrive(bar_acts + slot_a);
             }
-            if (kp >= 0 && lane == 0) {
-                int tt0, rows;
-                chunk_at(kp, tt0, rows);
-                uint64_t* bar = bar_part + slot_p;
-                const int t_lo = rev ? tbase - (tt0 + rows - 1) : tt0;
-                mbar_expect_tx(bar, (unsigned)(rows * RS) * 4u);
-                bulk_g2s(s_stage + (size_t)slot_p * TC * RS, lat_b + (ptrdiff_t)t_lo * RS,
-                         (unsigned)(rows * RS) * 4u, bar);
-            }
+            cp_async_arrive(bar_acts + slot_a);
         };
 
         // ---- fused softmax, in place, of my F frames of a chunk (a group of G lanes per frame) ----
-        const int V2 = V >> 1;
         auto softmax_chunk = [&](float* base, int rows) {
             const int G = 32 / FA, gl = lane & (G - 1), f = ha * FA + lane / G;
             const bool act = f < rows;
@@ -706,75 +794,54 @@ ctc_lin_kernel(const PipeParams pp, int* __restrict__ flags) {
         };
 
         // ---- the helper schedule -----------------------------------------------------------
-        // Iteration `it`:  issue { logits of chunk it+D+1 (A0), partner rows of chunk it+D (B0) };
-        //                  softmax of chunk it (A);  gradient rows of chunk it-2 (B).
-        // (REC runs chunk it-1.)  Partner rows of the first D+1 consume chunks cannot be requested
-        // before the partner CTA wrote them: they are issued at the phase break.
-        int wgh_i = want_grad ? 1 : 0;
-        asm volatile("" : "+r"(wgh_i));
-        const bool wgh = wgh_i != 0;
-        const bool iss_acts = isA && ha == 0, iss_part = isB && hb == 0;
-        const bool do_sm = isA && ha * FA < TC, do_gr = isB && hb * FB < TC;
-        Ring iss_a(NL), iss_p(NS), sm_a(NL), gr_a(NL);
-        int gr_e = 0;
+        // Iteration `it`:  SOFT 0 requests the logits of chunk it + kLinYDist + 1; SOFT: softmax of
+        // chunk it; GRAD: gradient rows of chunk it-3 (REC runs chunk it-1, COMB chunk it-2).
+        const bool iss_acts = isA && ha == 0;
+        const bool do_sm = isA && ha * FA < TC, do_gr = isB && hb * FB < TC && want_grad;
+        Ring iss_a(NL), sm_a(NL), gr_a(NL);
+        int gr_o = 0;
         if (iss_acts) {
-            for (int k = 0; k <= D; ++k) {            // prologue: logits of chunks 0..D
-                if (k < nch) issue_chunk(k, iss_a.slot, -1, 0);
+            for (int k = 0; k <= kLinYDist; ++k) {    // prologue: logits of chunks 0..kLinYDist
+                if (k < nch) issue_logits(k, iss_a.slot);
                 iss_a.advance();
             }
         }
-        for (int it = 0; it < nch + 2; ++it) {
+        for (int it = 0; it < n_it; ++it) {
             LPROF_BEGIN();
             {
-                const int ka = it + D + 1, kp = it + D;
-                const bool do_a = iss_acts && ka < nch;
-                const bool do_p = iss_part && wgh && it >= n1 + 1 && kp < nch;
-                if (do_a || do_p) issue_chunk(do_a ? ka : -1, iss_a.slot, do_p ? kp : -1, iss_p.slot);
+                const int ka = it + kLinYDist + 1;
+                if (iss_acts && ka < nch) issue_logits(ka, iss_a.slot);
                 iss_a.advance();
-                if (it >= n1 + 1) iss_p.advance();
             }
-            LPROF_SEC(8);
-            const int kg = it - 2;
+            const int kg = it - 3;
             if (kg >= 0) {
-                if (do_gr && wgh && kg >= n1 && kg < nch && s_flag[1] == 0) {   // gradient rows of chunk it-2
+                if (do_gr && kg >= n1 && kg < nch && s_flag[1] == 0) {   // gradient rows of chunk it-3
                     int tt0, rows;
                     chunk_at(kg, tt0, rows);
-                    grad_chunk(s_e + (size_t)gr_e * TC * ER, s_y + (size_t)gr_a.slot * TC * Vs, tt0, rows);
+                    grad_chunk(s_occ + (size_t)gr_o * TC * ER, s_y + (size_t)gr_a.slot * TC * Vs, tt0, rows);
                 }
-                if (kg >= n1) gr_e ^= 1;
+                if (kg >= n1) gr_o ^= 1;
                 gr_a.advance();
             }
-            LPROF_SEC(9);
             if (do_sm && it < nch) {                  // softmax of chunk `it`
                 int tt0, rows;
                 chunk_at(it, tt0, rows);
                 mbar_wait(bar_acts + sm_a.slot, sm_a.parity);
-                LPROF_SEC(10);
                 softmax_chunk(s_y + (size_t)sm_a.slot * TC * Vs, rows);
             }
-            LPROF_SEC(11);
             sm_a.advance();
             LPROF_END(it >= n1 + 1);
             __syncthreads();
             if (it == n1) {
-                // Phase break: my REC warps have stored every row the partner will consume,
-                // and (after the cluster barrier) vice versa.
                 cluster_sync_all();
-                if (iss_part) {
-                    fence_proxy_async();
-                    for (int k = n1; k <= n1 + D; ++k) {
-                        if (k < nch && (wgh || k == n1)) issue_chunk(-1, 0, k, iss_p.slot);
-                        iss_p.advance();
-                    }
-                }
                 __syncthreads();
             }
         }
     }
 #ifdef CTC_B200_PROFILE
     if (blockIdx.x == 0 && threadIdx.x == 0) {
-        prof[6] = (unsigned long long)(clock64() - prof_start);
-        prof[7] = (unsigned long long)(nch + 2);
+        prof[8] = (unsigned long long)(clock64() - prof_start);
+        prof[9] = (unsigned long long)n_it;
     }
 #endif
     // every CTA reports whether its half passed; the log-domain kernel redoes flagged utterances

@@ -13,8 +13,8 @@ for wl in sys.argv[1:] or ["C2"]:
     prob.ws[64:256].zero_()
     prob.run(reduce=False); torch.cuda.synchronize()
     c = prob.ws[64:64 + 8 * 12].cpu().view(torch.int64).tolist()
-    it = max(c[7], 1) / 2
+    it = max(c[9], 1) / 2
     print(wl, cabi.geometry(acts.shape[0], acts.shape[1], acts.shape[2], prob.S_max))
-    print(f"  CTA0 iterations={c[7]} wall={c[6]} cyc ({c[6] / max(c[7], 1):.0f}/iteration)")
-    print(f"  busy per iteration  phase1: REC {c[0]/it:.0f} H0 {c[2]/it:.0f} H1 {c[4]/it:.0f} | phase2: REC {c[1]/it:.0f} H0 {c[3]/it:.0f} H1 {c[5]/it:.0f}")
-    print(f"  helper0 sections per iteration (both phases): issue {c[8]/(2*it):.0f} grad {c[9]/(2*it):.0f} logits-wait {c[10]/(2*it):.0f} softmax {c[11]/(2*it):.0f}")
+    print(f"  CTA0 iterations={c[9]} wall={c[8]} cyc ({c[8] / max(c[9], 1):.0f}/iteration)")
+    print(f"  busy per iteration  phase1: REC {c[0]/it:.0f} COMB {c[2]/it:.0f} SOFT {c[4]/it:.0f} GRAD {c[6]/it:.0f}"
+          f" | phase2: REC {c[1]/it:.0f} COMB {c[3]/it:.0f} SOFT {c[5]/it:.0f} GRAD {c[7]/it:.0f}")
