@@ -136,10 +136,9 @@ bool pick_pipe(int T, int V, int pairs, int n_utt, Geometry* g) {
 // slots (alignment shift).
 bool pick_lin(int T, int V, int S_max, int n_utt, Geometry* g) {
     if (V % 4) return false;
+    // P = 8 always: one recursion warp covers 248 labels, and on B200 it is also the fastest choice for
+    // short targets (P < 8 is kept for experiments: it trips the posterior-mass check more often)
     int P = 8;
-    if (S_max + 1 <= 32) P = 1;
-    else if (S_max + 2 <= 64) P = 2;
-    else if (S_max + 4 <= 128) P = 4;
     const int q = env_int("CTC_B200_LIN_PAIRS", 0);
     if (q == 1 || q == 2 || q == 4 || q == 8) P = q;
     int R = (S_max + P + 32 * P - 1) / (32 * P);

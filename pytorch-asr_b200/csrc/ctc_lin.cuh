@@ -231,7 +231,7 @@ ctc_lin_kernel(const PipeParams pp, int* __restrict__ flags) {
     for (int i = threadIdx.x; i < 2 * (R + 1); i += NT) s_bnd[i] = make_float2(0.f, 0.f);
     for (int i = threadIdx.x; i < 2 * TC * ER; i += NT) s_occ[i] = 0.f;   // occupancy accumulators start at 0
     if (threadIdx.x == 0) {
-        s_flag[0] = 0; s_flag[1] = 0;
+        s_flag[0] = 0; s_flag[1] = 0; s_flag[2] = 0;
         for (int i = 0; i < NL; ++i) mbar_init(bar_acts + i, 32);   // 32 lanes' cp.async
         for (int i = 0; i < NS; ++i) mbar_init(bar_part + i, 1);    // one TMA producer
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -332,7 +332,11 @@ ctc_lin_kernel(const PipeParams pp, int* __restrict__ flags) {
                 m = fmaxf(m, c);
                 if (k >= P - PT) mt = fmaxf(mt, c);
             }
+#ifdef CTC_B200_EXP_NOKILL
+            const bool kill = false;
+#else
             const bool kill = u - (P - 1) > c_i + 1;           // even my last pair is dead
+#endif
             const int e_me = (m > 0.f && !kill) ? off + expo(m) : kLinFresh;
             const int e_top = (mt > 0.f && !kill) ? off + expo(mt) : kLinFresh;
             int e_in = __shfl_up_sync(0xffffffffu, e_top, 1);
@@ -346,7 +350,11 @@ ctc_lin_kernel(const PipeParams pp, int* __restrict__ flags) {
                 if (R > 1) named_bar_sync(1, nbar);
                 if (lane0) e_in = red[w];
             }
+#ifdef CTC_B200_EXP_NOIN
+            const int want = e_me - kLinTarget;
+#else
             const int want = max(e_me - kLinTarget, e_in + 7 - kLinInMax);
+#endif
             const int noff = want < kLinFresh / 2 ? kLinFresh : want;
             int sh = noff - off;                               // cells *= 2^-sh
             const bool reset = noff == kLinFresh || off == kLinFresh || sh > 126 || kill;
@@ -367,7 +375,9 @@ ctc_lin_kernel(const PipeParams pp, int* __restrict__ flags) {
             } else {
                 if (lane0) { const float2 bq = *bnd_rd; v = bq.x; o = __float_as_int(bq.y); }
             }
+#ifndef CTC_B200_EXP_NOKILL
             if (u > c_i) v = 0.f;        // the pair below me can no longer finish: cut the dead tail
+#endif
             const float am1 = v * pow2c(o - off);
 #pragma unroll
             for (int k = P - 1; k >= 0; --k) {
@@ -420,7 +430,11 @@ ctc_lin_kernel(const PipeParams pp, int* __restrict__ flags) {
                         if (warp_on(tt0 + r)) {
                             float xs[P], ins[P];
                             advance(yb_ptr, r * Vs, xs, ins);
+#ifdef CTC_B200_NOSTORE   // experiment: how fast is the first half without its HBM stores?
+                            if (r == last_r && (unsigned)(u + P) < win_store) {
+#else
                             if ((wg || r == last_r) && (unsigned)(u + P) < win_store) {
+#endif
                                 store_row<P>(row, xs, HS);
                                 store_row<P>(row + NP, ins, HS);
                                 *reinterpret_cast<int*>(row + offd) = off;
@@ -521,34 +535,38 @@ ctc_lin_kernel(const PipeParams pp, int* __restrict__ flags) {
                 float* orow = s_occ + (size_t)o_buf * TC * ER + wc * OW;
                 unsigned* ocl = reinterpret_cast<unsigned*>(orow);
                 float* obl = orow + VO + lane;
-                for (int r = r_begin; r < rows; r += r_inc) {
-                    const int u = tt0 + r - i0;
+                struct RowData { float aB[P], aY[P], pb[P], py[P]; int off, ob, oy; };
+                auto load_rd = [&](int r, RowData& d) {
                     // the chunk was staged in frame order: the reversed sweep walks it backwards
                     const float* str = st + (size_t)(rev ? rows - 1 - r : r) * RS;
                     const float* stp = str + (hasX ? X * PW : 0);        // partner thread's P blanks
                     const int* sto = reinterpret_cast<const int*>(str + 2 * NP) + (hasX ? X : 0);
-                    float aB[P], aY[P], pb[P], py[P];
-                    load_row<P>(arow + r * RS, aB, HS);
-                    load_row<P>(arow + r * RS + NP, aY, HS);
-                    const int off = *reinterpret_cast<const int*>(arow + r * RS + offd);
-                    int ob, oy;            // partner exponents: of thread X and of thread X-1
+                    load_row<P>(arow + r * RS, d.aB, HS);
+                    load_row<P>(arow + r * RS + NP, d.aY, HS);
+                    d.off = *reinterpret_cast<const int*>(arow + r * RS + offd);
                     {
                         float qb[P], qy[P];
                         load_row<P>(stp, qb, HS);
                         load_row<P>(stp + NP, qy, HS);
-                        ob = *sto;
+                        d.ob = *sto;
 #pragma unroll
-                        for (int q = 0; q < P; ++q) pb[q] = qb[P - 1 - q];
+                        for (int q = 0; q < P; ++q) d.pb[q] = qb[P - 1 - q];
 #pragma unroll
-                        for (int q = 0; q + 1 < P; ++q) py[q] = qy[P - 2 - q];
+                        for (int q = 0; q + 1 < P; ++q) d.py[q] = qy[P - 2 - q];
                         // my last label pairs with the LAST label of partner thread X-1 = the thread
                         // lane+1 of my warp talks to; lane 31 reads it itself
                         float yl = __shfl_down_sync(0xffffffffu, qy[P - 1], 1);
-                        int ol = __shfl_down_sync(0xffffffffu, ob, 1);
+                        int ol = __shfl_down_sync(0xffffffffu, d.ob, 1);
                         if (lane == 31 && hasX1) { yl = stp[NP + (P == 8 ? HS : 0) - 1]; ol = sto[-1]; }
-                        py[P - 1] = yl;
-                        oy = ol;
+                        d.py[P - 1] = yl;
+                        d.oy = ol;
                     }
+                };
+                auto combine_rd = [&](int r, const RowData& d) {
+                    const int u = tt0 + r - i0;
+                    const float (&aB)[P] = d.aB; const float (&aY)[P] = d.aY;
+                    const float (&pb)[P] = d.pb; const float (&py)[P] = d.py;
+                    const int off = d.off, ob = d.ob, oy = d.oy;
                     const bool in_win = (unsigned)u < win_cons;
                     float bsum = 0.f;
                     if (first && r == 0) {
@@ -632,6 +650,11 @@ ctc_lin_kernel(const PipeParams pp, int* __restrict__ flags) {
                         }
                     }
                     if (want_grad) obl[r * ER] = bsum;
+                };
+                for (int r = r_begin; r < rows; r += r_inc) {
+                    RowData d0;
+                    load_rd(r, d0);
+                    combine_rd(r, d0);
                 }
                 }
                 ring_part.advance();
@@ -660,7 +683,13 @@ ctc_lin_kernel(const PipeParams pp, int* __restrict__ flags) {
         // =============================================================================
         // A helper owns F = TC / n frames of every chunk and works on all of them AT ONCE, a group
         // of G = 32 / F lanes per frame, so that one pass of short shuffle trees finishes the chunk.
-        const int FA = max(TC / nA, 1), FB = max(TC / nB, 1);
+        // (all of it by shifts: the compiler does not hoist integer divisions out of the chunk loop)
+        const int lgTC = TC == 4 ? 2 : (TC == 2 ? 1 : 0);
+        const int lgA = max(lgTC - (nA >= 4 ? 2 : (nA >= 2 ? 1 : 0)), 0), lgB = max(lgTC - (nB >= 4 ? 2 : (nB >= 2 ? 1 : 0)), 0);
+        const int FA = 1 << lgA, FB = 1 << lgB;
+        const int GA = 32 >> lgA, glA = lane & (GA - 1), fA = ha * FA + (lane >> (5 - lgA));
+        const int GB = 32 >> lgB, glB = lane & (GB - 1), fB = hb * FB + (lane >> (5 - lgB));
+        const unsigned gmaskA = (GA == 32 ? 0xffffffffu : ((1u << GA) - 1u)) << (lane & ~(GA - 1));
         auto group_sum = [&](float x, int G) {
             for (int o = G >> 1; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
             return x;
@@ -703,12 +732,72 @@ ctc_lin_kernel(const PipeParams pp, int* __restrict__ flags) {
             cp_async_arrive(bar_acts + slot_a);
         };
 
+        // V = 48 with four frames per pass: the logits never touch shared memory.  Every lane keeps
+        // its 3 float2 of the chunks it+1 and it+2 in registers (plain read-only loads issued two
+        // iterations ahead), so the softmax pass is: exp, one redux, three shuffles, three stores.
+        // (measured slower than the cp.async ring on B200 -- the loads are not back after two
+        // iterations -- so the path is kept but switched off)
+        const bool fastV = false && GA == 8 && V2 == 24 && nA == 1;
+        float2 lg0[3], lg1[3], lg2[3];   // logits of chunk c live in set c % 3 (no register moves)
+        int lg_ph = 0;                   // it % 3
+        auto load_logits = [&](int kc, float2 (&dst)[3]) {
+            if (kc < nch) {
+                int tt0, rows;
+                chunk_at(kc, tt0, rows);
+                if (fA < rows) {
+                    const float2* src = reinterpret_cast<const float2*>(
+                        acts_b + (ptrdiff_t)(tbase + tsign * (tt0 + fA)) * (ptrdiff_t)frame_stride) + glA;
+#pragma unroll
+                    for (int j = 0; j < 3; ++j) dst[j] = __ldg(src + 8 * j);
+                }
+            }
+        };
+        auto softmax_fast = [&](float* base, int rows, const float2 (&lg)[3]) {
+            const bool act = fA < rows;
+            float* row = base + min(fA, rows - 1) * Vs;
+            float2* row2 = reinterpret_cast<float2*>(row);
+            float2 x[3];
+#pragma unroll
+            for (int j = 0; j < 3; ++j) x[j] = act ? lg[j] : make_float2(0.f, 0.f);
+            float m = fmaxf(fmaxf(fmaxf(x[0].x, x[0].y), fmaxf(x[1].x, x[1].y)), fmaxf(x[2].x, x[2].y));
+            asm volatile("redux.sync.max.f32 %0, %1, %2;" : "=f"(m) : "f"(m), "r"(gmaskA));
+            const float mb = m * kLog2e;
+            float z = 0.f;
+#pragma unroll
+            for (int j = 0; j < 3; ++j) {
+                x[j].x = ex2f(fmaf(x[j].x, kLog2e, -mb));
+                x[j].y = ex2f(fmaf(x[j].y, kLog2e, -mb));
+                z += x[j].x + x[j].y;
+            }
+            z += __shfl_xor_sync(0xffffffffu, z, 4);
+            z += __shfl_xor_sync(0xffffffffu, z, 2);
+            z += __shfl_xor_sync(0xffffffffu, z, 1);
+            float rs;
+            asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rs) : "f"(z));
+            rs = rs * (2.0f - z * rs);          // one Newton step: full fp32 accuracy
+            if (act) {
+#pragma unroll
+                for (int j = 0; j < 3; ++j) row2[glA + 8 * j] = make_float2(x[j].x * rs, x[j].y * rs);
+                if (glA == 0) row[V] = 0.f;     // what padding pairs gather
+            }
+        };
+
         // ---- fused softmax, in place, of my F frames of a chunk (a group of G lanes per frame) ----
+        // The maximum of a row comes from ONE redux.sync per group (no shuffle tree); the sum needs
+        // log2 G shuffle levels.
         auto softmax_chunk = [&](float* base, int rows) {
-            const int G = 32 / FA, gl = lane & (G - 1), f = ha * FA + lane / G;
+            const int G = GA, gl = glA, f = fA;
+            const unsigned gmask = gmaskA;
             const bool act = f < rows;
             float* row = base + min(f, rows - 1) * Vs;
             float2* row2 = reinterpret_cast<float2*>(row);
+            if (G == 8 && V2 == 24) {      // V = 48, four frames per pass: straight-line code, no guards
+                float2 lg[3];
+#pragma unroll
+                for (int j = 0; j < 3; ++j) lg[j] = row2[gl + 8 * j];
+                softmax_fast(base, rows, lg);
+                return;
+            }
             if (V2 <= 4 * G) {      // at most 4 float2 per lane: the row stays in registers
                 float2 x[4];
                 float m = -CUDART_INF_F;
@@ -718,12 +807,13 @@ ctc_lin_kernel(const PipeParams pp, int* __restrict__ flags) {
                     x[j] = c < V2 ? row2[c] : make_float2(-CUDART_INF_F, -CUDART_INF_F);
                     m = fmaxf(m, fmaxf(x[j].x, x[j].y));
                 }
-                m = group_max(m, G);
+                asm volatile("redux.sync.max.f32 %0, %1, %2;" : "=f"(m) : "f"(m), "r"(gmask));
+                const float mb = m * kLog2e;
                 float z = 0.f;
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
-                    x[j].x = ex2f((x[j].x - m) * kLog2e);
-                    x[j].y = ex2f((x[j].y - m) * kLog2e);
+                    x[j].x = ex2f(fmaf(x[j].x, kLog2e, -mb));
+                    x[j].y = ex2f(fmaf(x[j].y, kLog2e, -mb));
                     z += x[j].x + x[j].y;
                 }
                 const float rs = 1.0f / group_sum(z, G);
@@ -740,7 +830,7 @@ ctc_lin_kernel(const PipeParams pp, int* __restrict__ flags) {
                     const float2 x = row2[c];
                     m = fmaxf(m, fmaxf(x.x, x.y));
                 }
-                m = group_max(m, G);
+                asm volatile("redux.sync.max.f32 %0, %1, %2;" : "=f"(m) : "f"(m), "r"(gmask));
                 for (int c = gl; c < V2; c += G) {
                     float2 x = row2[c];
                     x.x = ex2f((x.x - m) * kLog2e);
@@ -762,15 +852,91 @@ ctc_lin_kernel(const PipeParams pp, int* __restrict__ flags) {
         //   occupancy row = per recursion warp [class sums, Q1.31: VO][blank partial sums, fp32: 32].
         //   The row is read, cleared for its next use, and turned into gscale * (softmax - occupancy).
         //   The sum of ALL occupancies of a frame must be 1: the posterior-mass check.
+        //   All loads are issued up front and the two reductions (blank sum, total) share their
+        //   shuffle levels, so that the pass is one short dependent chain.
         auto grad_chunk = [&](float* obase, const float* ybase, int tt0, int rows) {
-            const int G = 32 / FB, gl = lane & (G - 1), f = hb * FB + lane / G;
+            const int G = GB, gl = glB, f = fB;
             const bool act = f < rows;
             const int fr = min(f, rows - 1);
             float* orow = obase + fr * ER;
             const float2* y2 = reinterpret_cast<const float2*>(ybase + fr * Vs);
             float2* g2 = reinterpret_cast<float2*>(grad_b + (size_t)(tbase + tsign * (tt0 + fr)) * frame_stride);
+            if (RC == 1 && G == 8 && V2 == 24) {   // V = 48, four frames per pass: straight-line code
+                const float4 bp = *reinterpret_cast<const float4*>(orow + VO + 4 * gl);
+                uint2 x[3];
+                float2 y[3];
+#pragma unroll
+                for (int j = 0; j < 3; ++j) {
+                    uint2* p2 = reinterpret_cast<uint2*>(orow) + gl + 8 * j;
+                    x[j] = *p2;
+                    y[j] = y2[gl + 8 * j];
+                    if (act) *p2 = make_uint2(0u, 0u);
+                }
+                float bs = (bp.x + bp.y) + (bp.z + bp.w), tot = 0.f;
+                float2 o[3];
+#pragma unroll
+                for (int j = 0; j < 3; ++j) {
+                    o[j].x = __uint2float_rn(x[j].x) * (1.0f / kQ31);
+                    o[j].y = __uint2float_rn(x[j].y) * (1.0f / kQ31);
+                    tot += o[j].x + o[j].y;
+                }
+#pragma unroll
+                for (int sft = 4; sft > 0; sft >>= 1) {
+                    bs += __shfl_xor_sync(0xffffffffu, bs, sft);
+                    tot += __shfl_xor_sync(0xffffffffu, tot, sft);
+                }
+                // the blank class sits in column (blank >> 1) of lane (blank >> 1) & 7, slot (blank >> 1) >> 3
+                const int cb = blank >> 1;
+                const float addx = (blank & 1) ? 0.f : bs, addy = (blank & 1) ? bs : 0.f;
+#pragma unroll
+                for (int j = 0; j < 3; ++j) {
+                    const bool mine = cb == gl + 8 * j;
+                    const float ox = o[j].x + (mine ? addx : 0.f), oy = o[j].y + (mine ? addy : 0.f);
+                    if (act) g2[gl + 8 * j] = make_float2(gscale * (y[j].x - ox), gscale * (y[j].y - oy));
+                }
+                if (act && !(fabsf(tot + bs - 1.0f) <= kMassTol)) s_flag[0] = 1;   // NaN-safe
+#ifdef CTC_B200_MASSDEV
+                if (act) atomicMax(&s_flag[2], __float_as_int(fabsf(tot + bs - 1.0f)));
+#endif
+                return;
+            }
             float bs = 0.f;
             for (int i = gl; i < 32 * R; i += G) bs += orow[(i >> 5) * OW + VO + (i & 31)];
+            if (R == 1 && V2 <= 4 * G) {     // at most 4 float2 per lane: everything stays in registers
+                float2 o[4], y[4];
+                float tot = 0.f;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int c = gl + j * G;
+                    o[j] = make_float2(0.f, 0.f);
+                    y[j] = make_float2(0.f, 0.f);
+                    if (c < V2) {
+                        uint2* p2 = reinterpret_cast<uint2*>(orow) + c;
+                        const uint2 x = *p2;
+                        y[j] = y2[c];
+                        if (act) *p2 = make_uint2(0u, 0u);
+                        o[j].x = __uint2float_rn(x.x) * (1.0f / kQ31);
+                        o[j].y = __uint2float_rn(x.y) * (1.0f / kQ31);
+                        tot += o[j].x + o[j].y;
+                    }
+                }
+                for (int sft = G >> 1; sft > 0; sft >>= 1) {
+                    bs += __shfl_xor_sync(0xffffffffu, bs, sft);
+                    tot += __shfl_xor_sync(0xffffffffu, tot, sft);
+                }
+                if (act) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const int c = gl + j * G;
+                        if (c < V2) {
+                            if ((blank >> 1) == c) { if (blank & 1) o[j].y += bs; else o[j].x += bs; }
+                            g2[c] = make_float2(gscale * (y[j].x - o[j].x), gscale * (y[j].y - o[j].y));
+                        }
+                    }
+                    if (!(fabsf(tot + bs - 1.0f) <= kMassTol)) s_flag[0] = 1;   // NaN-safe
+                }
+                return;
+            }
             bs = group_sum(bs, G);
             float tot = 0.f;
             for (int c = gl; c < V2; c += G) {
@@ -791,12 +957,15 @@ ctc_lin_kernel(const PipeParams pp, int* __restrict__ flags) {
             }
             tot = group_sum(tot, G) + bs;
             if (act && !(fabsf(tot - 1.0f) <= kMassTol)) s_flag[0] = 1;   // NaN-safe
+#ifdef CTC_B200_MASSDEV
+            if (act) atomicMax(&s_flag[2], __float_as_int(fabsf(tot - 1.0f)));
+#endif
         };
 
         // ---- the helper schedule -----------------------------------------------------------
         // Iteration `it`:  SOFT 0 requests the logits of chunk it + kLinYDist + 1; SOFT: softmax of
         // chunk it; GRAD: gradient rows of chunk it-3 (REC runs chunk it-1, COMB chunk it-2).
-        const bool iss_acts = isA && ha == 0;
+        const bool iss_acts = isA && ha == 0 && !fastV;
         const bool do_sm = isA && ha * FA < TC, do_gr = isB && hb * FB < TC && want_grad;
         Ring iss_a(NL), sm_a(NL), gr_a(NL);
         int gr_o = 0;
@@ -806,6 +975,7 @@ ctc_lin_kernel(const PipeParams pp, int* __restrict__ flags) {
                 iss_a.advance();
             }
         }
+        if (fastV && do_sm) { load_logits(0, lg0); load_logits(1, lg1); }
         for (int it = 0; it < n_it; ++it) {
             LPROF_BEGIN();
             {
@@ -826,10 +996,20 @@ ctc_lin_kernel(const PipeParams pp, int* __restrict__ flags) {
             if (do_sm && it < nch) {                  // softmax of chunk `it`
                 int tt0, rows;
                 chunk_at(it, tt0, rows);
-                mbar_wait(bar_acts + sm_a.slot, sm_a.parity);
-                softmax_chunk(s_y + (size_t)sm_a.slot * TC * Vs, rows);
+                if (fastV) {
+                    // chunk it+2 is requested now (two iterations of flight time) into the set that
+                    // chunk it-1 has just left
+                    float* ybase = s_y + (size_t)sm_a.slot * TC * Vs;
+                    if (lg_ph == 0) { load_logits(it + 2, lg2); softmax_fast(ybase, rows, lg0); }
+                    else if (lg_ph == 1) { load_logits(it + 2, lg0); softmax_fast(ybase, rows, lg1); }
+                    else { load_logits(it + 2, lg1); softmax_fast(ybase, rows, lg2); }
+                } else {
+                    mbar_wait(bar_acts + sm_a.slot, sm_a.parity);
+                    softmax_chunk(s_y + (size_t)sm_a.slot * TC * Vs, rows);
+                }
             }
             sm_a.advance();
+            lg_ph = lg_ph == 2 ? 0 : lg_ph + 1;
             LPROF_END(it >= n1 + 1);
             __syncthreads();
             if (it == n1) {
@@ -846,7 +1026,11 @@ ctc_lin_kernel(const PipeParams pp, int* __restrict__ flags) {
 #endif
     // every CTA reports whether its half passed; the log-domain kernel redoes flagged utterances
     __syncthreads();
+#ifdef CTC_B200_MASSDEV   // developer build: report the largest posterior-mass deviation instead of the flag
+    if (threadIdx.x == 0) flags[2 * b + (rev ? 1 : 0)] = s_flag[1] ? 0x7f800000 : s_flag[2];
+#else
     if (threadIdx.x == 0) flags[2 * b + (rev ? 1 : 0)] = s_flag[0];
+#endif
 }
 
 }  // namespace ctcb200

@@ -159,7 +159,9 @@ def test_forward_only_matches():
     acts, tg, il, tl = synth.make_batch(5, 90, 48, 18, seed=5, repeat_frac=0.2)
     nll_g, _, _ = run_engine(acts, tg, il, tl)
     nll_f, _, loss = run_engine(acts, tg, il, tl, want_grad=False)
-    np.testing.assert_array_equal(nll_g, nll_f)
+    # same arithmetic in both modes; an utterance whose posterior-mass check (gradient mode only)
+    # hands it to the log-domain fallback may differ in the last bits
+    np.testing.assert_allclose(nll_g, nll_f, rtol=1e-6)
 
 
 def test_long_target_multiple_pairs_per_thread():
