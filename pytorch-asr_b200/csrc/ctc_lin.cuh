@@ -266,12 +266,14 @@ ctc_lin_kernel(const PipeParams pp, int* __restrict__ flags) {
     unsigned long long* prof = reinterpret_cast<unsigned long long*>(reinterpret_cast<char*>(p.status) + 64);
     const int prof_role = w == 0 ? 0 : (w == R ? 2 : (hw == 0 ? 4 : (hw == nA ? 6 : -1)));
     const bool prof_on = blockIdx.x == 0 && lane == 0 && prof_role >= 0;
-    long long prof_t0 = clock64();
+    long long prof_t0 = clock64(), prof_t1 = prof_t0;
     const long long prof_start = prof_t0;
-#define LPROF_BEGIN() do { prof_t0 = clock64(); } while (0)
+#define LPROF_SEC(slot) do { if (prof_on && prof_role == 4) { const long long t_ = clock64(); atomicAdd(prof + (slot), (unsigned long long)(t_ - prof_t1)); prof_t1 = t_; } } while (0)
+#define LPROF_BEGIN() do { prof_t0 = clock64(); prof_t1 = prof_t0; } while (0)
 #define LPROF_END(phase2) do { if (prof_on) atomicAdd(prof + prof_role + ((phase2) ? 1 : 0), (unsigned long long)(clock64() - prof_t0)); } while (0)
 #else
 #define LPROF_BEGIN() do {} while (0)
+#define LPROF_SEC(slot) do {} while (0)
 #define LPROF_END(phase2) do {} while (0)
 #endif
 
@@ -729,7 +731,10 @@ ctc_lin_kernel(const PipeParams pp, int* __restrict__ flags) {
                     while (c >= V4) { c -= V4; ++r; }
                 }
             }
-            cp_async_arrive(bar_acts + slot_a);
+            // one softmax warp: it waits for its own copies with cp.async groups (the mbarrier arrive
+            // costs the issuing warp about a microsecond on B200); several: completion on the mbarrier
+            if (nA == 1) cp_async_commit();
+            else cp_async_arrive(bar_acts + slot_a);
         };
 
         // V = 48 with four frames per pass: the logits never touch shared memory.  Every lane keeps
@@ -972,6 +977,7 @@ ctc_lin_kernel(const PipeParams pp, int* __restrict__ flags) {
         if (iss_acts) {
             for (int k = 0; k <= kLinYDist; ++k) {    // prologue: logits of chunks 0..kLinYDist
                 if (k < nch) issue_logits(k, iss_a.slot);
+                else if (nA == 1) cp_async_commit();
                 iss_a.advance();
             }
         }
@@ -980,9 +986,13 @@ ctc_lin_kernel(const PipeParams pp, int* __restrict__ flags) {
             LPROF_BEGIN();
             {
                 const int ka = it + kLinYDist + 1;
-                if (iss_acts && ka < nch) issue_logits(ka, iss_a.slot);
+                if (iss_acts) {
+                    if (ka < nch) issue_logits(ka, iss_a.slot);
+                    else if (nA == 1) cp_async_commit();   // keep one group per iteration
+                }
                 iss_a.advance();
             }
+            LPROF_SEC(10);
             const int kg = it - 3;
             if (kg >= 0) {
                 if (do_gr && kg >= n1 && kg < nch && s_flag[1] == 0) {   // gradient rows of chunk it-3
@@ -993,6 +1003,7 @@ ctc_lin_kernel(const PipeParams pp, int* __restrict__ flags) {
                 if (kg >= n1) gr_o ^= 1;
                 gr_a.advance();
             }
+            LPROF_SEC(11);
             if (do_sm && it < nch) {                  // softmax of chunk `it`
                 int tt0, rows;
                 chunk_at(it, tt0, rows);
@@ -1004,10 +1015,13 @@ ctc_lin_kernel(const PipeParams pp, int* __restrict__ flags) {
                     else if (lg_ph == 1) { load_logits(it + 2, lg0); softmax_fast(ybase, rows, lg1); }
                     else { load_logits(it + 2, lg1); softmax_fast(ybase, rows, lg2); }
                 } else {
-                    mbar_wait(bar_acts + sm_a.slot, sm_a.parity);
+                    if (nA == 1) { cp_async_wait<kLinYDist + 1>(); __syncwarp(); }
+                    else mbar_wait(bar_acts + sm_a.slot, sm_a.parity);
+                    LPROF_SEC(12);
                     softmax_chunk(s_y + (size_t)sm_a.slot * TC * Vs, rows);
                 }
             }
+            LPROF_SEC(13);
             sm_a.advance();
             lg_ph = lg_ph == 2 ? 0 : lg_ph + 1;
             LPROF_END(it >= n1 + 1);
