@@ -50,6 +50,10 @@ struct Geometry {
 };
 
 inline size_t flag_bytes(int n_utt) { return ((size_t)std::max(n_utt, 1) * 8 + 255) / 256 * 256; }
+// softmax rows the linear kernel saves for the partner CTA's second half: [n_utt][T][V] fp32
+inline size_t ysave_bytes(int T, int V, int n_utt) {
+    return ((size_t)std::max(n_utt, 1) * (size_t)std::max(T, 1) * (size_t)V * 4 + 255) / 256 * 256;
+}
 
 int env_int(const char* name, int dflt) {
     const char* e = std::getenv(name);
@@ -144,7 +148,8 @@ bool pick_lin(int T, int V, int S_max, int n_utt, Geometry* g) {
     int R = (S_max + P + 32 * P - 1) / (32 * P);
     if (R > 1 && P != 8) { P = 8; R = (S_max + P + 32 * P - 1) / (32 * P); }   // several warps: P = 8 only
     int H = env_int("CTC_B200_HELPERS", 0);
-    if (!(H == 1 || H == 2 || H == 4 || H == 8)) H = V > 256 ? 4 : 2;
+    if (!(H == 1 || H == 2 || H == 4 || H == 8)) H = V > 256 ? 4 : 2;   // (H = 1: one helper warp; the softmax
+                                       // rows are then saved / re-staged through HBM, see ctc_lin.cuh -- measured no faster)
     int NC = env_int("CTC_B200_COMB", 0);          // combine groups (warps per recursion warp)
     if (NC < 1 || NC > 4) NC = R == 1 ? 2 : 1;
     const int NT = 32 * ((1 + NC) * R + H);
@@ -157,7 +162,7 @@ bool pick_lin(int T, int V, int S_max, int n_utt, Geometry* g) {
     for (int pass = 0; pass < 2; ++pass) {
         for (int ci = 0; ci < 3; ++ci) {
             int TC = cand[ci];
-            if (tc_env == 1 || tc_env == 2 || tc_env == 4) TC = tc_env;   // the kernel unrolls 4 rows
+            if (tc_env >= 1 && tc_env <= 4) TC = tc_env;   // the kernel unrolls 4 rows
             LinSmem lay(NP, R, V, TC, RS, YS);
             const int need = std::max(1, std::min(4, (2 * std::max(n_utt, 1) + kNumSmsHint - 1) / kNumSmsHint));
             const int limit = pass == 0 ? std::min(kMaxSmemBytes, 227 * 1024 / need - 1024) : kMaxSmemBytes;
@@ -286,8 +291,9 @@ int launch_fused(const float* acts, const int32_t* targets, const int32_t* tgt_o
     Geometry g;
     int rc = pick_geometry(T, V, S_max, N, &g);
     if (rc != CTC_B200_OK) return rc;
-    if (!lattice || lattice_bytes < g.lattice_floats_per_utt() * sizeof(float) * (size_t)utt_count)
-        return CTC_B200_WORKSPACE_TOO_SMALL;
+    const size_t lat_need = g.lattice_floats_per_utt() * sizeof(float) * (size_t)utt_count;
+    const size_t ys_need = 0;   // (saved softmax rows: tried, no faster; the kernel keeps the hook)
+    if (!lattice || lattice_bytes < lat_need + ys_need) return CTC_B200_WORKSPACE_TOO_SMALL;
     if (g.pipe == 2 && !flags) return CTC_B200_INVALID_ARGUMENT;
     if ((reinterpret_cast<uintptr_t>(lattice) & 15) || (reinterpret_cast<uintptr_t>(acts) & 15) ||
         (grad && (reinterpret_cast<uintptr_t>(grad) & 15)))
@@ -303,6 +309,7 @@ int launch_fused(const float* acts, const int32_t* targets, const int32_t* tgt_o
     prm.nll = nll;
     prm.grad = grad;
     prm.lattice = lattice;
+    prm.ysave = ys_need ? reinterpret_cast<float*>(reinterpret_cast<char*>(lattice) + (lat_need + 255) / 256 * 256) : nullptr;
     prm.status = status_word;
     prm.lat_utt_stride = (long long)g.lat_utt_stride;
     prm.T = T;
@@ -410,7 +417,8 @@ int ctc_b200_get_geometry(int T, int n_utt, int V, int S_max, ctc_b200_geometry*
     out->smem_bytes = lin ? g.lsmem : g.smem;
     // [256 B header: status word][redo flags: 2 ints per utterance][lattice]
     out->workspace_bytes = kHeaderBytes + flag_bytes(n_utt) +
-                           g.lattice_floats_per_utt() * sizeof(float) * (size_t)n_utt;
+                           (g.lattice_floats_per_utt() * sizeof(float) * (size_t)n_utt + 255) / 256 * 256 +
+                           0;
     return CTC_B200_OK;
 }
 
@@ -522,7 +530,10 @@ int ctc_b200_session_create(int T, int N, int V, int S_max, int max_targets, int
     int rc = pick_geometry(T, V, S_max, N, &s->geo);
     if (rc != CTC_B200_OK) { delete s; return rc; }
     const size_t nact = (size_t)T * N * V * sizeof(float);
-    s->lattice_bytes = s->geo.lattice_floats_per_utt() * sizeof(float) * (size_t)N;
+    // (slices run one after the other, so the saved-softmax region of a slice may overlap the lattice of
+    // later slices; the allocation only has to leave room behind the last slice)
+    s->lattice_bytes = s->geo.lattice_floats_per_utt() * sizeof(float) * (size_t)N +
+                       0;
     s->small_bytes = align_up((size_t)std::max(max_targets, 1) * 4, 16) + 4 * align_up((size_t)N * 4, 16);
     s->res_bytes = 16 + (size_t)N * 4;
     cudaError_t e = cudaSuccess;

@@ -59,6 +59,7 @@ struct FusedParams {
     float* __restrict__ nll;               // [N]
     float* __restrict__ grad;              // [T, N, V] or nullptr
     float* __restrict__ lattice;           // workspace: [n_utt][T][row_stride]
+    float* __restrict__ ysave;             // workspace: [n_utt][T][V] softmax rows (ctc_lin.cuh) or nullptr
     int* __restrict__ status;              // device status word (bit flags)
     long long lat_utt_stride;              // floats per utterance in `lattice`
     int T, N, V, blank, zero_infinity;

@@ -48,14 +48,27 @@
 
 namespace ctcb200 {
 
-constexpr int kLinTarget = 32;          // a thread's largest cell is renormalised to ~2^32
-constexpr int kLinInMax = 96;           // what the neighbour hands up stays below 2^96 in my scale
+#ifndef CTC_LIN_TGT
+#define CTC_LIN_TGT 32
+#endif
+#ifndef CTC_LIN_INMAX
+#define CTC_LIN_INMAX 96
+#endif
+constexpr int kLinTarget = CTC_LIN_TGT; // a thread's largest cell is renormalised to ~2^32
+constexpr int kLinInMax = CTC_LIN_INMAX; // what the neighbour hands up stays below 2^96 in my scale
 constexpr int kLinFresh = -(1 << 24);   // exponent of a thread that has not received anything yet
-constexpr int kLinHmax = 44;            // clamp of the combine exponent (no overflow of p * 2^h)
+constexpr int kLinHmax = 127 - (kLinInMax + 7) - 4;   // largest exponent applied to the partner cell alone (p * 2^h finite)
 constexpr float kMassTol = 3.0e-5f;     // |sum of occupancies - 1| per frame
 constexpr int kLinNone = -(1 << 28);    // exponent of a term that is exactly zero
 constexpr float kQ31 = 2147483648.0f;   // label occupancies are accumulated as Q1.31 fixed point
-constexpr int kLinYDist = 1;            // logits are requested kLinYDist + 1 chunks before their softmax
+#ifndef CTC_LIN_YD
+#define CTC_LIN_YD 1
+#endif
+#ifndef CTC_LIN_PD
+#define CTC_LIN_PD 2
+#endif
+constexpr int kLinYDist = CTC_LIN_YD;   // logits are requested kLinYDist + 1 chunks before their softmax
+constexpr int kLinPDist = CTC_LIN_PD;   // partner rows are requested kLinPDist chunks before COMB needs them
 
 __device__ __forceinline__ int clamp_exp(int e) { return max(min(e, 127), -127); }
 // 2^e for e in [-126, 127]; 0 for e <= -127 (flush); 2^127 above
@@ -121,7 +134,7 @@ struct LinSmem {
         OW = VO + 32;            // + 32 blank partial sums
         ER = R * OW;
         NL = kLinYDist + 5;      // requested kLinYDist+1 chunks early .. gradient 3 chunks later
-        NS = 3;                  // requested 2 chunks before COMB needs them
+        NS = kLinPDist + 1;      // requested kLinPDist chunks before COMB needs them
         int o = 0;
         lab = o;    o += up(NP * 4, 16);
         y = o;      o += up(NL * TC * Vs * 4, 16);
@@ -513,23 +526,28 @@ ctc_lin_kernel(const PipeParams pp, int* __restrict__ flags) {
         };
         Ring ring_part(NS), iss_p(NS);
         int a_buf = 0, o_buf = 0;
+        // loop-invariant kernel parameters live in registers (each re-read from the constant bank
+        // would be an exposed latency in front of a branch)
+        int wgc_i = want_grad ? 1 : 0, nc_i = NC, n1_i = n1, nch_i = nch;
+        asm volatile("" : "+r"(wgc_i), "+r"(nc_i), "+r"(n1_i), "+r"(nch_i));
+        const bool wgc = wgc_i != 0;
         for (int it = 0; it < n_it; ++it) {
             LPROF_BEGIN();
             // partner rows of chunk `it` (consumed in iteration it+2); the first two consume chunks
             // are requested at the phase break
-            if (it >= n1 + 2 && it < nch && want_grad) {
-                if (iss_part) issue_partner(it, iss_p.slot);
+            if (it >= n1_i + 2 && it + kLinPDist - 2 < nch_i && wgc) {
+                if (iss_part) issue_partner(it + kLinPDist - 2, iss_p.slot);
                 iss_p.advance();
             }
             const int k = it - 2;
-            if (k >= n1 && k < nch) {
+            if (k >= n1_i && k < nch_i) {
                 int tt0, rows;
                 chunk_at(k, tt0, rows);
                 // the chunk with the first combined row is done by group 0 alone (it yields E0 and
                 // 1/z, which the other groups pick up from shared memory one barrier later)
-                const bool first = k == n1;
-                if (k == n1 + 1 && cg > 0) { E0 = s_red[100]; rz = __int_as_float(s_red[101]); }
-                const int r_begin = first ? 0 : cg, r_inc = first ? 1 : NC;
+                const bool first = k == n1_i;
+                if (k == n1_i + 1 && cg > 0) { E0 = s_red[100]; rz = __int_as_float(s_red[101]); }
+                const int r_begin = first ? 0 : cg, r_inc = first ? 1 : nc_i;
                 if (!first || cg == 0) {
                 mbar_wait(bar_part + ring_part.slot, ring_part.parity);   // TMA data landed
                 const float* st = s_stage + (size_t)ring_part.slot * TC * RS;
@@ -543,14 +561,14 @@ ctc_lin_kernel(const PipeParams pp, int* __restrict__ flags) {
                     const float* str = st + (size_t)(rev ? rows - 1 - r : r) * RS;
                     const float* stp = str + (hasX ? X * PW : 0);        // partner thread's P blanks
                     const int* sto = reinterpret_cast<const int*>(str + 2 * NP) + (hasX ? X : 0);
-                    load_row<P>(arow + r * RS, d.aB, HS);
-                    load_row<P>(arow + r * RS + NP, d.aY, HS);
-                    d.off = *reinterpret_cast<const int*>(arow + r * RS + offd);
                     {
                         float qb[P], qy[P];
-                        load_row<P>(stp, qb, HS);
-                        load_row<P>(stp + NP, qy, HS);
+                        load_row<P>(stp + NP, qy, HS);     // first: the shuffles below wait for these
                         d.ob = *sto;
+                        load_row<P>(stp, qb, HS);
+                        load_row<P>(arow + r * RS, d.aB, HS);
+                        load_row<P>(arow + r * RS + NP, d.aY, HS);
+                        d.off = *reinterpret_cast<const int*>(arow + r * RS + offd);
 #pragma unroll
                         for (int q = 0; q < P; ++q) d.pb[q] = qb[P - 1 - q];
 #pragma unroll
@@ -564,13 +582,15 @@ ctc_lin_kernel(const PipeParams pp, int* __restrict__ flags) {
                         d.oy = ol;
                     }
                 };
-                auto combine_rd = [&](int r, const RowData& d) {
+                // returns true when `gq` (label occupancies, Q1.31) still has to be added to the class slots
+                auto combine_rd = [&](int r, const RowData& d, unsigned (&gq)[P], float& bsum_out) -> bool {
                     const int u = tt0 + r - i0;
                     const float (&aB)[P] = d.aB; const float (&aY)[P] = d.aY;
                     const float (&pb)[P] = d.pb; const float (&py)[P] = d.py;
                     const int off = d.off, ob = d.ob, oy = d.oy;
                     const bool in_win = (unsigned)u < win_cons;
                     float bsum = 0.f;
+                    bool pending = false;
                     if (first && r == 0) {
                         // first combined row: also yields the likelihood P = sum_s a * p~.
                         // Exponent/mantissa form: E0 = max exponent of any term, z = sum of the
@@ -628,7 +648,7 @@ ctc_lin_kernel(const PipeParams pp, int* __restrict__ flags) {
                             if (bad) { s_flag[0] = 1; s_flag[1] = 1; }
                             if (!rev) p.nll[b] = bad ? 0.f : (float)(-((double)E0 + (double)log2f(z)) * kLn2);
                         }
-                        if (want_grad) {
+                        if (wgc) {
 #pragma unroll
                             for (int q = 0; q < P; ++q) {
                                 bsum += tB[q] * rz;
@@ -639,24 +659,39 @@ ctc_lin_kernel(const PipeParams pp, int* __restrict__ flags) {
                         // occupancy = a * p~ * 2^(off + o - E0) / z   (exact exponents); cells outside
                         // [0, S] are exact zeros on REC's side, partner vectors are finite
                         // (label cells directly in Q1.31 units)
-                        const float sb = pow2c(min(off + ob - E0, kLinHmax)) * rz;
+                        // The exponent h = off + o - E0 goes onto the partner cell up to kLinHmax (so that
+                        // p * 2^h cannot overflow); a larger h -- cells far below their thread's maximum on
+                        // both sides, steep lattices -- puts the rest onto the product (a factor of 1 otherwise).
+                        const int hb = off + ob - E0, hy = off + oy - E0;
+                        const int hbc = min(hb, kLinHmax), hyc = min(hy, kLinHmax);
+                        const float sb = pow2c(hbc) * rz;
                         const float sq = sb * kQ31;
-                        const float sy = hasX1 ? pow2c(min(off + oy - E0, kLinHmax)) * (rz * kQ31) : 0.f;
+                        const float sy = hasX1 ? pow2c(hyc) * (rz * kQ31) : 0.f;
+                        const float rb = pow2c(hb - hbc), ry = pow2c(hy - hyc);   // 1 unless h > kLinHmax
 #pragma unroll
                         for (int q = 0; q < P; ++q) {
-                            bsum += aB[q] * (pb[q] * sb);
+                            bsum += (aB[q] * (pb[q] * sb)) * rb;
                             float gy = 0.f;
-                            if (q + 1 < P) gy = aY[q] * (py[q] * sq);
-                            else if (hasX1) gy = aY[q] * (py[q] * sy);
-                            atomicAdd(ocl + r * ER + lab[q], __float2uint_rn(gy));
+                            if (q + 1 < P) gy = (aY[q] * (py[q] * sq)) * rb;
+                            else if (hasX1) gy = (aY[q] * (py[q] * sy)) * ry;
+                            gq[q] = __float2uint_rn(gy);
                         }
+                        pending = true;
                     }
-                    if (want_grad) obl[r * ER] = bsum;
+                    bsum_out = bsum;
+                    return pending;
                 };
-                for (int r = r_begin; r < rows; r += r_inc) {
+                int r = r_begin;
+                for (; r < rows; r += r_inc) {
                     RowData d0;
+                    unsigned gq[P];
+                    float bsum;
                     load_rd(r, d0);
-                    combine_rd(r, d0);
+                    if (combine_rd(r, d0, gq, bsum)) {
+#pragma unroll
+                        for (int q = 0; q < P; ++q) atomicAdd(ocl + r * ER + lab[q], gq[q]);
+                    }
+                    if (wgc) obl[r * ER] = bsum;
                 }
                 }
                 ring_part.advance();
@@ -671,7 +706,7 @@ ctc_lin_kernel(const PipeParams pp, int* __restrict__ flags) {
                 cluster_sync_all();
                 if (iss_part) {
                     fence_proxy_async();
-                    for (int kk = n1; kk < n1 + 2; ++kk) {
+                    for (int kk = n1; kk < n1 + kLinPDist; ++kk) {
                         if (kk < nch && (want_grad || kk == n1)) issue_partner(kk, iss_p.slot);
                         iss_p.advance();
                     }
@@ -686,7 +721,7 @@ ctc_lin_kernel(const PipeParams pp, int* __restrict__ flags) {
         // A helper owns F = TC / n frames of every chunk and works on all of them AT ONCE, a group
         // of G = 32 / F lanes per frame, so that one pass of short shuffle trees finishes the chunk.
         // (all of it by shifts: the compiler does not hoist integer divisions out of the chunk loop)
-        const int lgTC = TC == 4 ? 2 : (TC == 2 ? 1 : 0);
+        const int lgTC = TC >= 3 ? 2 : (TC == 2 ? 1 : 0);   // TC = 3: four frame slots, the last one idle
         const int lgA = max(lgTC - (nA >= 4 ? 2 : (nA >= 2 ? 1 : 0)), 0), lgB = max(lgTC - (nB >= 4 ? 2 : (nB >= 2 ? 1 : 0)), 0);
         const int FA = 1 << lgA, FB = 1 << lgB;
         const int GA = 32 >> lgA, glA = lane & (GA - 1), fA = ha * FA + (lane >> (5 - lgA));
@@ -757,7 +792,7 @@ ctc_lin_kernel(const PipeParams pp, int* __restrict__ flags) {
                 }
             }
         };
-        auto softmax_fast = [&](float* base, int rows, const float2 (&lg)[3]) {
+        auto softmax_fast = [&](float* base, int rows, const float2 (&lg)[3], float* ysv) {
             const bool act = fA < rows;
             float* row = base + min(fA, rows - 1) * Vs;
             float2* row2 = reinterpret_cast<float2*>(row);
@@ -765,7 +800,9 @@ ctc_lin_kernel(const PipeParams pp, int* __restrict__ flags) {
 #pragma unroll
             for (int j = 0; j < 3; ++j) x[j] = act ? lg[j] : make_float2(0.f, 0.f);
             float m = fmaxf(fmaxf(fmaxf(x[0].x, x[0].y), fmaxf(x[1].x, x[1].y)), fmaxf(x[2].x, x[2].y));
-            asm volatile("redux.sync.max.f32 %0, %1, %2;" : "=f"(m) : "f"(m), "r"(gmaskA));
+            m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 4));
+            m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 2));
+            m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 1));
             const float mb = m * kLog2e;
             float z = 0.f;
 #pragma unroll
@@ -774,6 +811,7 @@ ctc_lin_kernel(const PipeParams pp, int* __restrict__ flags) {
                 x[j].y = ex2f(fmaf(x[j].y, kLog2e, -mb));
                 z += x[j].x + x[j].y;
             }
+            // (redux.sync was measured SLOWER than three shuffle levels here, for the sum and the max)
             z += __shfl_xor_sync(0xffffffffu, z, 4);
             z += __shfl_xor_sync(0xffffffffu, z, 2);
             z += __shfl_xor_sync(0xffffffffu, z, 1);
@@ -782,7 +820,11 @@ ctc_lin_kernel(const PipeParams pp, int* __restrict__ flags) {
             rs = rs * (2.0f - z * rs);          // one Newton step: full fp32 accuracy
             if (act) {
 #pragma unroll
-                for (int j = 0; j < 3; ++j) row2[glA + 8 * j] = make_float2(x[j].x * rs, x[j].y * rs);
+                for (int j = 0; j < 3; ++j) {
+                    const float2 yv = make_float2(x[j].x * rs, x[j].y * rs);
+                    row2[glA + 8 * j] = yv;
+                    if (ysv) reinterpret_cast<float2*>(ysv)[glA + 8 * j] = yv;   // for the partner's second half
+                }
                 if (glA == 0) row[V] = 0.f;     // what padding pairs gather
             }
         };
@@ -790,7 +832,7 @@ ctc_lin_kernel(const PipeParams pp, int* __restrict__ flags) {
         // ---- fused softmax, in place, of my F frames of a chunk (a group of G lanes per frame) ----
         // The maximum of a row comes from ONE redux.sync per group (no shuffle tree); the sum needs
         // log2 G shuffle levels.
-        auto softmax_chunk = [&](float* base, int rows) {
+        auto softmax_chunk = [&](float* base, int rows, float* ysv) {
             const int G = GA, gl = glA, f = fA;
             const unsigned gmask = gmaskA;
             const bool act = f < rows;
@@ -800,7 +842,7 @@ ctc_lin_kernel(const PipeParams pp, int* __restrict__ flags) {
                 float2 lg[3];
 #pragma unroll
                 for (int j = 0; j < 3; ++j) lg[j] = row2[gl + 8 * j];
-                softmax_fast(base, rows, lg);
+                softmax_fast(base, rows, lg, ysv);
                 return;
             }
             if (V2 <= 4 * G) {      // at most 4 float2 per lane: the row stays in registers
@@ -974,6 +1016,8 @@ ctc_lin_kernel(const PipeParams pp, int* __restrict__ flags) {
         const bool do_sm = isA && ha * FA < TC, do_gr = isB && hb * FB < TC && want_grad;
         Ring iss_a(NL), sm_a(NL), gr_a(NL);
         int gr_o = 0;
+        int n1h_i = n1, nchh_i = nch;
+        asm volatile("" : "+r"(n1h_i), "+r"(nchh_i));
         if (iss_acts) {
             for (int k = 0; k <= kLinYDist; ++k) {    // prologue: logits of chunks 0..kLinYDist
                 if (k < nch) issue_logits(k, iss_a.slot);
@@ -995,30 +1039,30 @@ ctc_lin_kernel(const PipeParams pp, int* __restrict__ flags) {
             LPROF_SEC(10);
             const int kg = it - 3;
             if (kg >= 0) {
-                if (do_gr && kg >= n1 && kg < nch && s_flag[1] == 0) {   // gradient rows of chunk it-3
+                if (do_gr && kg >= n1h_i && kg < nchh_i && s_flag[1] == 0) {   // gradient rows of chunk it-3
                     int tt0, rows;
                     chunk_at(kg, tt0, rows);
                     grad_chunk(s_occ + (size_t)gr_o * TC * ER, s_y + (size_t)gr_a.slot * TC * Vs, tt0, rows);
                 }
-                if (kg >= n1) gr_o ^= 1;
+                if (kg >= n1h_i) gr_o ^= 1;
                 gr_a.advance();
             }
             LPROF_SEC(11);
-            if (do_sm && it < nch) {                  // softmax of chunk `it`
+            if (do_sm && it < nchh_i) {               // softmax of chunk `it`
                 int tt0, rows;
                 chunk_at(it, tt0, rows);
                 if (fastV) {
                     // chunk it+2 is requested now (two iterations of flight time) into the set that
                     // chunk it-1 has just left
                     float* ybase = s_y + (size_t)sm_a.slot * TC * Vs;
-                    if (lg_ph == 0) { load_logits(it + 2, lg2); softmax_fast(ybase, rows, lg0); }
-                    else if (lg_ph == 1) { load_logits(it + 2, lg0); softmax_fast(ybase, rows, lg1); }
-                    else { load_logits(it + 2, lg1); softmax_fast(ybase, rows, lg2); }
+                    if (lg_ph == 0) { load_logits(it + 2, lg2); softmax_fast(ybase, rows, lg0, nullptr); }
+                    else if (lg_ph == 1) { load_logits(it + 2, lg0); softmax_fast(ybase, rows, lg1, nullptr); }
+                    else { load_logits(it + 2, lg1); softmax_fast(ybase, rows, lg2, nullptr); }
                 } else {
                     if (nA == 1) { cp_async_wait<kLinYDist + 1>(); __syncwarp(); }
                     else mbar_wait(bar_acts + sm_a.slot, sm_a.parity);
                     LPROF_SEC(12);
-                    softmax_chunk(s_y + (size_t)sm_a.slot * TC * Vs, rows);
+                    softmax_chunk(s_y + (size_t)sm_a.slot * TC * Vs, rows, nullptr);
                 }
             }
             LPROF_SEC(13);
