@@ -155,6 +155,46 @@ def test_edge_cases():
             assert not grad[int(il[b]):, b].any()
 
 
+def test_fallback_on_saturated_logits():
+    """Hardtanh-saturated logits (every entry +-50, network.py:370): emissions of 2^-144 underflow the
+    probability-domain kernel, its posterior-mass check must flag the utterances and the log-domain
+    fallback must still produce the reference's numbers."""
+    g = torch.Generator().manual_seed(11)
+    B, T, V, S = 6, 60, 48, 12
+    acts = torch.where(torch.rand(T, B, V, generator=g) < 0.5, 50.0, -50.0)
+    _, tg, il, tl = synth.make_batch(B, T, V, S, seed=3)
+    prob = cabi.DeviceProblem(acts, tg, il, tl, reduction="sum")
+    prob.grad.fill_(float("nan"))
+    prob.run()
+    torch.cuda.synchronize()
+    prob.check_status()
+    if cabi.geometry(T, B, V, prob.S_max)["kernel"] == 2:
+        flags = prob.ws[256:256 + 8 * B].view(torch.int32).view(-1, 2).cpu()
+        assert int((flags.sum(1) > 0).sum()) >= 1          # the safety net was exercised
+    orc = oracle.ctc_oracle_f64(acts.numpy(), tg.numpy(), il.numpy(), tl.numpy())
+    assert_parity(prob.nll.cpu().numpy(), prob.grad.cpu().numpy(), orc["nll"], orc["grad"],
+                  what="saturated logits via the fallback")
+
+
+def test_peaky_full_size_no_fallback_needed():
+    """C2 with blank-dominated, Hardtanh-ranged logits: parity on a slice, and the linear kernel's own
+    posterior-mass check passes for every utterance (steep lattices are handled exactly)."""
+    acts, tg, il, tl = synth.make_config("C2", batch=32, peaky=True)
+    prob = cabi.DeviceProblem(acts, tg, il, tl, reduction="sum")
+    prob.run()
+    torch.cuda.synchronize()
+    if cabi.geometry(acts.shape[0], 32, acts.shape[2], prob.S_max)["kernel"] == 2:
+        flags = prob.ws[256:256 + 8 * 32].view(torch.int32).cpu()
+        assert int(flags.sum()) == 0
+    sel = [0, 9, 31]
+    offs = torch.cat([torch.zeros(1, dtype=torch.int64), tl.long().cumsum(0)])
+    sub_t = torch.cat([tg[offs[b]:offs[b + 1]] for b in sel])
+    sub = (acts[:, sel].contiguous(), sub_t, il[sel].contiguous(), tl[sel].contiguous())
+    orc = oracle.ctc_oracle_f64(sub[0].numpy(), sub[1].numpy(), sub[2].numpy(), sub[3].numpy())
+    assert_parity(prob.nll.cpu().numpy()[sel], prob.grad.cpu().numpy()[:, sel], orc["nll"], orc["grad"],
+                  grad_atol=grad_atol_fp64(1000), what="C2 peaky slice vs fp64")
+
+
 def test_forward_only_matches():
     acts, tg, il, tl = synth.make_batch(5, 90, 48, 18, seed=5, repeat_frac=0.2)
     nll_g, _, _ = run_engine(acts, tg, il, tl)
