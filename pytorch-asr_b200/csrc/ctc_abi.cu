@@ -148,8 +148,9 @@ bool pick_lin(int T, int V, int S_max, int n_utt, Geometry* g) {
     int R = (S_max + P + 32 * P - 1) / (32 * P);
     if (R > 1 && P != 8) { P = 8; R = (S_max + P + 32 * P - 1) / (32 * P); }   // several warps: P = 8 only
     int H = env_int("CTC_B200_HELPERS", 0);
-    if (!(H == 1 || H == 2 || H == 4 || H == 8)) H = V > 256 ? 4 : 2;   // (H = 1: one helper warp; the softmax
-                                       // rows are then saved / re-staged through HBM, see ctc_lin.cuh -- measured no faster)
+    // one helper warp (softmax, then gradient rows) when one recursion warp suffices: 4 warps per CTA
+    // leave 128 registers per thread, which the two-rows-in-flight combine pass needs
+    if (!(H == 1 || H == 2 || H == 4 || H == 8)) H = V > 256 ? 4 : (R == 1 ? 1 : 2);
     int NC = env_int("CTC_B200_COMB", 0);          // combine groups (warps per recursion warp)
     if (NC < 1 || NC > 4) NC = R == 1 ? 2 : 1;
     const int NT = 32 * ((1 + NC) * R + H);

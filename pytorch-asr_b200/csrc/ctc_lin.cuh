@@ -681,7 +681,83 @@ ctc_lin_kernel(const PipeParams pp, int* __restrict__ flags) {
                     bsum_out = bsum;
                     return pending;
                 };
+                // Steady state with registers to spare (4-warp CTAs): TWO rows per pass, staged so that
+                // at most ~48 cell registers are live: label planes of both rows -> Q1.31 occupancies;
+                // blank planes of both rows -> blank sums; then all atomics.  Two independent dependency
+                // chains per warp instead of one.
+                auto combine2 = [&](int rA, int rB) {
+                    const float* strA = st + (size_t)(rev ? rows - 1 - rA : rA) * RS;
+                    const float* strB = st + (size_t)(rev ? rows - 1 - rB : rB) * RS;
+                    const float* stpA = strA + (hasX ? X * PW : 0);
+                    const float* stpB = strB + (hasX ? X * PW : 0);
+                    const int* stoA = reinterpret_cast<const int*>(strA + 2 * NP) + (hasX ? X : 0);
+                    const int* stoB = reinterpret_cast<const int*>(strB + 2 * NP) + (hasX ? X : 0);
+                    const float* arA = arow + rA * RS;
+                    const float* arB = arow + rB * RS;
+                    float qyA[P], qyB[P], aYA[P], aYB[P];
+                    load_row<P>(stpA + NP, qyA, HS);
+                    load_row<P>(stpB + NP, qyB, HS);
+                    const int obA = *stoA, obB = *stoB;
+                    const int offA = *reinterpret_cast<const int*>(arA + offd);
+                    const int offB = *reinterpret_cast<const int*>(arB + offd);
+                    load_row<P>(arA + NP, aYA, HS);
+                    load_row<P>(arB + NP, aYB, HS);
+                    float ylA = __shfl_down_sync(0xffffffffu, qyA[P - 1], 1);
+                    float ylB = __shfl_down_sync(0xffffffffu, qyB[P - 1], 1);
+                    int olA = __shfl_down_sync(0xffffffffu, obA, 1);
+                    int olB = __shfl_down_sync(0xffffffffu, obB, 1);
+                    if (lane == 31 && hasX1) {
+                        ylA = stpA[NP + (P == 8 ? HS : 0) - 1]; olA = stoA[-1];
+                        ylB = stpB[NP + (P == 8 ? HS : 0) - 1]; olB = stoB[-1];
+                    }
+                    const bool winA = (unsigned)(tt0 + rA - i0) < win_cons;
+                    const bool winB = (unsigned)(tt0 + rB - i0) < win_cons;
+                    // occupancy = a * p~ * 2^(off + o - E0) / z (see combine_rd for the exponent split)
+                    const int hbA = offA + obA - E0, hyA = offA + olA - E0;
+                    const int hbB = offB + obB - E0, hyB = offB + olB - E0;
+                    const int cbA = min(hbA, kLinHmax), cyA = min(hyA, kLinHmax);
+                    const int cbB = min(hbB, kLinHmax), cyB = min(hyB, kLinHmax);
+                    const float sbA = winA ? pow2c(cbA) * rz : 0.f, sbB = winB ? pow2c(cbB) * rz : 0.f;
+                    const float syA = (winA && hasX1) ? pow2c(cyA) * (rz * kQ31) : 0.f;
+                    const float syB = (winB && hasX1) ? pow2c(cyB) * (rz * kQ31) : 0.f;
+                    const float rbA = pow2c(hbA - cbA), ryA = pow2c(hyA - cyA);
+                    const float rbB = pow2c(hbB - cbB), ryB = pow2c(hyB - cyB);
+                    const float sqA = sbA * kQ31, sqB = sbB * kQ31;
+                    unsigned gA[P], gB[P];
+#pragma unroll
+                    for (int q = 0; q + 1 < P; ++q) {
+                        gA[q] = __float2uint_rn((aYA[q] * (qyA[P - 2 - q] * sqA)) * rbA);
+                        gB[q] = __float2uint_rn((aYB[q] * (qyB[P - 2 - q] * sqB)) * rbB);
+                    }
+                    gA[P - 1] = __float2uint_rn((aYA[P - 1] * (ylA * syA)) * ryA);
+                    gB[P - 1] = __float2uint_rn((aYB[P - 1] * (ylB * syB)) * ryB);
+                    float bsA = 0.f, bsB = 0.f;
+                    {
+                        float qbA[P], qbB[P], aBA[P], aBB[P];
+                        load_row<P>(stpA, qbA, HS);
+                        load_row<P>(stpB, qbB, HS);
+                        load_row<P>(arA, aBA, HS);
+                        load_row<P>(arB, aBB, HS);
+#pragma unroll
+                        for (int q = 0; q < P; ++q) {
+                            bsA += (aBA[q] * (qbA[P - 1 - q] * sbA)) * rbA;
+                            bsB += (aBB[q] * (qbB[P - 1 - q] * sbB)) * rbB;
+                        }
+                    }
+                    if (winA) {
+#pragma unroll
+                        for (int q = 0; q < P; ++q) atomicAdd(ocl + rA * ER + lab[q], gA[q]);
+                    }
+                    if (winB) {
+#pragma unroll
+                        for (int q = 0; q < P; ++q) atomicAdd(ocl + rB * ER + lab[q], gB[q]);
+                    }
+                    obl[rA * ER] = bsA;
+                    obl[rB * ER] = bsB;
+                };
                 int r = r_begin;
+                if (!first && wgc && NT <= 128)
+                    for (; r + r_inc < rows; r += 2 * r_inc) combine2(r, r + r_inc);
                 for (; r < rows; r += r_inc) {
                     RowData d0;
                     unsigned gq[P];
