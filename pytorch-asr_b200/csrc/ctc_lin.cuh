@@ -25,20 +25,23 @@
 // (ctc_pipe_kernel, launched right after with the same grid; clusters of unflagged utterances
 // exit at once).  The linear path is therefore exact to fp32 rounding or not used at all.
 //
-// Warp roles (R = recursion warps, 1 for targets up to 248 labels):
-//   [0, R)        REC   the lattice recursion and nothing else: one step = emission loads, one
-//                       shuffle pair, 5 FP32 per pair, one row out -- to HBM (first half of the
-//                       sweep, for the partner CTA) or to a shared-memory ring (second half)
-//   [R, 2R)       COMB  second half only: combines REC's rows with the partner's stored rows (TMA-staged)
-//                       into occupancies; NC groups of them share the rows of a chunk; label cells are ADDED to their class slot as Q1.31
-//                       fixed point with native shared-memory integer atomics (order-independent,
-//                       hence bit-reproducible); also the likelihood from the first combined row
-//   2R .. 2R+nA   SOFT  logits staging (cp.async + mbarrier) and the fused softmax, all frames of a
-//                       chunk at once (a group of lanes per frame)
-//   the rest      GRAD  gradient rows = gscale * (softmax - occupancy), posterior-mass check,
-//                       zero fill of rows t >= T_b
+// Warp roles (R = recursion warps, 1 for targets up to 248 labels; NC = combine groups):
+//   [0, R)          REC   the lattice recursion and nothing else: one step = emission loads, one
+//                         shuffle pair, 5 FP32 per pair, one row out -- to HBM (first half of the
+//                         sweep, for the partner CTA) or to a shared-memory ring (second half)
+//   [R, (1+NC)R)    COMB  second half only: combines REC's rows with the partner's stored rows (one
+//                         TMA bulk copy per chunk, 3-slot ring) into occupancies; group g takes the
+//                         rows r == g (mod NC) of a chunk, two rows in flight per pass when registers
+//                         allow; label cells are ADDED to their class slot as Q1.31 fixed point with
+//                         native shared-memory integer atomics (order-independent, hence
+//                         bit-reproducible); also the likelihood from the first combined row
+//   then nA warps   SOFT  logits staging (cp.async groups) and the fused softmax, all frames of a chunk
+//                         at once (a group of lanes per frame)
+//   then nB warps   GRAD  gradient rows = gscale * (softmax - occupancy), posterior-mass check,
+//                         zero fill of rows t >= T_b   (H = 1: ONE helper warp is SOFT and GRAD)
 // One CTA barrier per chunk of TC frames hands the rings over: in iteration `it` SOFT works on
-// chunk it, REC on chunk it-1, COMB on chunk it-2, GRAD on chunk it-3.
+// chunk it, REC on chunk it-1, COMB on chunk it-2, GRAD on chunk it-3.  C2 (B=256, T=1000, V=48):
+// 4 warps per CTA (REC, 2 x COMB, helper), 4 CTAs per SM, 125 registers.
 //
 // Alignment trick: the alpha CTA shifts its lattice by delta = (P-1-S) mod P slots, so that the
 // P partner cells a thread needs are exactly ONE partner thread's P cells, reversed: 128-bit
