@@ -153,7 +153,9 @@ bool pick_lin(int T, int V, int S_max, int n_utt, Geometry* g) {
     if (!(H == 1 || H == 2 || H == 4 || H == 8)) H = V > 256 ? 4 : (R == 1 ? 1 : 2);
     int NC = env_int("CTC_B200_COMB", 0);          // combine groups (warps per recursion warp)
     if (NC < 1 || NC > 4) NC = R == 1 ? 2 : 1;
-    const int NT = 32 * ((1 + NC) * R + H);
+    int NT = 32 * ((1 + NC) * R + H);
+    if (R == 1)   // the single-recursion-warp kernels are built for at most 256 threads
+        while (NT > 256 && H > 1) { H >>= 1; NT = 32 * ((1 + NC) * R + H); }
     if (NT > 1024) return false;
     const int NP = 32 * P * R;
     const int RS = lin_row_stride(NP, P);

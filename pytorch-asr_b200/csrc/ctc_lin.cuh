@@ -72,6 +72,10 @@ constexpr float kQ31 = 2147483648.0f;   // label occupancies are accumulated as 
 #endif
 constexpr int kLinYDist = CTC_LIN_YD;   // logits are requested kLinYDist + 1 chunks before their softmax
 constexpr int kLinPDist = CTC_LIN_PD;   // partner rows are requested kLinPDist chunks before COMB needs them
+#ifndef CTC_LIN_L2D
+#define CTC_LIN_L2D 0
+#endif
+constexpr int kLinL2Dist = CTC_LIN_L2D; // L2 prefetch of partner rows / logits this many chunks ahead (0 = off: measured slower)
 
 __device__ __forceinline__ int clamp_exp(int e) { return max(min(e, 127), -127); }
 // 2^e for e in [-126, 127]; 0 for e <= -127 (flush); 2^127 above
@@ -284,7 +288,11 @@ ctc_lin_kernel(const PipeParams pp, int* __restrict__ flags) {
     const bool prof_on = blockIdx.x == 0 && lane == 0 && prof_role >= 0;
     long long prof_t0 = clock64(), prof_t1 = prof_t0;
     const long long prof_start = prof_t0;
+#ifdef CTC_B200_PROFILE_SECTIONS
 #define LPROF_SEC(slot) do { if (prof_on && prof_role == 4) { const long long t_ = clock64(); atomicAdd(prof + (slot), (unsigned long long)(t_ - prof_t1)); prof_t1 = t_; } } while (0)
+#else
+#define LPROF_SEC(slot) do {} while (0)
+#endif
 #define LPROF_BEGIN() do { prof_t0 = clock64(); prof_t1 = prof_t0; } while (0)
 #define LPROF_END(phase2) do { if (prof_on) atomicAdd(prof + prof_role + ((phase2) ? 1 : 0), (unsigned long long)(clock64() - prof_t0)); } while (0)
 #else
@@ -527,6 +535,16 @@ ctc_lin_kernel(const PipeParams pp, int* __restrict__ flags) {
                          (unsigned)(rows * RS) * 4u, bar);
             }
         };
+        // bulk L2 prefetch of a whole chunk of partner rows (no shared memory, no completion to wait for)
+        auto prefetch_partner = [&](int kp) {
+            if (lane == 0 && kp < nch) {
+                int tt0, rows;
+                chunk_at(kp, tt0, rows);
+                const int t_lo = rev ? tbase - (tt0 + rows - 1) : tt0;
+                asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;"
+                             ::"l"(lat_b + (ptrdiff_t)t_lo * RS), "r"((unsigned)(rows * RS) * 4u) : "memory");
+            }
+        };
         Ring ring_part(NS), iss_p(NS);
         int a_buf = 0, o_buf = 0;
         // loop-invariant kernel parameters live in registers (each re-read from the constant bank
@@ -542,6 +560,7 @@ ctc_lin_kernel(const PipeParams pp, int* __restrict__ flags) {
                 if (iss_part) issue_partner(it + kLinPDist - 2, iss_p.slot);
                 iss_p.advance();
             }
+            if (kLinL2Dist > 0 && iss_part && wgc && it >= n1_i + 1) prefetch_partner(it + kLinL2Dist);
             const int k = it - 2;
             if (k >= n1_i && k < nch_i) {
                 int tt0, rows;
@@ -789,6 +808,8 @@ ctc_lin_kernel(const PipeParams pp, int* __restrict__ flags) {
                         if (kk < nch && (want_grad || kk == n1)) issue_partner(kk, iss_p.slot);
                         iss_p.advance();
                     }
+                    if (kLinL2Dist > 0 && want_grad)
+                        for (int kk = n1 + kLinPDist; kk <= n1 + kLinL2Dist; ++kk) prefetch_partner(kk);
                 }
                 __syncthreads();
             }
@@ -828,6 +849,20 @@ ctc_lin_kernel(const PipeParams pp, int* __restrict__ flags) {
             cp_dst[j] = r * Vs + 4 * c;
             cp_src[j] = r * a_inc + 4 * c;
         }
+        // L2 prefetch of the logits rows of chunk kc: lane l takes 128-byte line (l % lines) of row (l / lines)
+        const int lg_lines = (V * 4 + 127) / 128;
+        auto prefetch_logits = [&](int kc) {
+            if (kc < nch) {
+                int tt0, rows;
+                chunk_at(kc, tt0, rows);
+                const int r = lane / lg_lines, ln = lane - r * lg_lines;
+                if (r < rows) {
+                    const char* q = reinterpret_cast<const char*>(
+                        acts_b + (ptrdiff_t)(tbase + tsign * (tt0 + r)) * (ptrdiff_t)frame_stride) + 128 * ln;
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(q));
+                }
+            }
+        };
         auto issue_logits = [&](int ka, int slot_a) {
             int tt0, rows;
             chunk_at(ka, tt0, rows);
@@ -1112,6 +1147,7 @@ ctc_lin_kernel(const PipeParams pp, int* __restrict__ flags) {
                 if (iss_acts) {
                     if (ka < nch) issue_logits(ka, iss_a.slot);
                     else if (nA == 1) cp_async_commit();   // keep one group per iteration
+                    if (kLinL2Dist > 0 && lg_lines * TC <= 32) prefetch_logits(ka + kLinL2Dist);
                 }
                 iss_a.advance();
             }
