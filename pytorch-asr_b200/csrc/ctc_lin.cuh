@@ -72,10 +72,6 @@ constexpr float kQ31 = 2147483648.0f;   // label occupancies are accumulated as 
 #endif
 constexpr int kLinYDist = CTC_LIN_YD;   // logits are requested kLinYDist + 1 chunks before their softmax
 constexpr int kLinPDist = CTC_LIN_PD;   // partner rows are requested kLinPDist chunks before COMB needs them
-#ifndef CTC_LIN_L2D
-#define CTC_LIN_L2D 0
-#endif
-constexpr int kLinL2Dist = CTC_LIN_L2D; // L2 prefetch of partner rows / logits this many chunks ahead (0 = off: measured slower)
 
 __device__ __forceinline__ int clamp_exp(int e) { return max(min(e, 127), -127); }
 // 2^e for e in [-126, 127]; 0 for e <= -127 (flush); 2^127 above
@@ -358,11 +354,7 @@ ctc_lin_kernel(const PipeParams pp, int* __restrict__ flags) {
                 m = fmaxf(m, c);
                 if (k >= P - PT) mt = fmaxf(mt, c);
             }
-#ifdef CTC_B200_EXP_NOKILL
-            const bool kill = false;
-#else
             const bool kill = u - (P - 1) > c_i + 1;           // even my last pair is dead
-#endif
             const int e_me = (m > 0.f && !kill) ? off + expo(m) : kLinFresh;
             const int e_top = (mt > 0.f && !kill) ? off + expo(mt) : kLinFresh;
             int e_in = __shfl_up_sync(0xffffffffu, e_top, 1);
@@ -376,11 +368,7 @@ ctc_lin_kernel(const PipeParams pp, int* __restrict__ flags) {
                 if (R > 1) named_bar_sync(1, nbar);
                 if (lane0) e_in = red[w];
             }
-#ifdef CTC_B200_EXP_NOIN
-            const int want = e_me - kLinTarget;
-#else
             const int want = max(e_me - kLinTarget, e_in + 7 - kLinInMax);
-#endif
             const int noff = want < kLinFresh / 2 ? kLinFresh : want;
             int sh = noff - off;                               // cells *= 2^-sh
             const bool reset = noff == kLinFresh || off == kLinFresh || sh > 126 || kill;
@@ -401,9 +389,7 @@ ctc_lin_kernel(const PipeParams pp, int* __restrict__ flags) {
             } else {
                 if (lane0) { const float2 bq = *bnd_rd; v = bq.x; o = __float_as_int(bq.y); }
             }
-#ifndef CTC_B200_EXP_NOKILL
             if (u > c_i) v = 0.f;        // the pair below me can no longer finish: cut the dead tail
-#endif
             const float am1 = v * pow2c(o - off);
 #pragma unroll
             for (int k = P - 1; k >= 0; --k) {
@@ -456,11 +442,7 @@ ctc_lin_kernel(const PipeParams pp, int* __restrict__ flags) {
                         if (warp_on(tt0 + r)) {
                             float xs[P], ins[P];
                             advance(yb_ptr, r * Vs, xs, ins);
-#ifdef CTC_B200_NOSTORE   // experiment: how fast is the first half without its HBM stores?
-                            if (r == last_r && (unsigned)(u + P) < win_store) {
-#else
                             if ((wg || r == last_r) && (unsigned)(u + P) < win_store) {
-#endif
                                 store_row<P>(row, xs, HS);
                                 store_row<P>(row + NP, ins, HS);
                                 *reinterpret_cast<int*>(row + offd) = off;
@@ -535,16 +517,6 @@ ctc_lin_kernel(const PipeParams pp, int* __restrict__ flags) {
                          (unsigned)(rows * RS) * 4u, bar);
             }
         };
-        // bulk L2 prefetch of a whole chunk of partner rows (no shared memory, no completion to wait for)
-        auto prefetch_partner = [&](int kp) {
-            if (lane == 0 && kp < nch) {
-                int tt0, rows;
-                chunk_at(kp, tt0, rows);
-                const int t_lo = rev ? tbase - (tt0 + rows - 1) : tt0;
-                asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;"
-                             ::"l"(lat_b + (ptrdiff_t)t_lo * RS), "r"((unsigned)(rows * RS) * 4u) : "memory");
-            }
-        };
         Ring ring_part(NS), iss_p(NS);
         int a_buf = 0, o_buf = 0;
         // loop-invariant kernel parameters live in registers (each re-read from the constant bank
@@ -560,7 +532,6 @@ ctc_lin_kernel(const PipeParams pp, int* __restrict__ flags) {
                 if (iss_part) issue_partner(it + kLinPDist - 2, iss_p.slot);
                 iss_p.advance();
             }
-            if (kLinL2Dist > 0 && iss_part && wgc && it >= n1_i + 1) prefetch_partner(it + kLinL2Dist);
             const int k = it - 2;
             if (k >= n1_i && k < nch_i) {
                 int tt0, rows;
@@ -808,8 +779,6 @@ ctc_lin_kernel(const PipeParams pp, int* __restrict__ flags) {
                         if (kk < nch && (want_grad || kk == n1)) issue_partner(kk, iss_p.slot);
                         iss_p.advance();
                     }
-                    if (kLinL2Dist > 0 && want_grad)
-                        for (int kk = n1 + kLinPDist; kk <= n1 + kLinL2Dist; ++kk) prefetch_partner(kk);
                 }
                 __syncthreads();
             }
@@ -849,20 +818,6 @@ ctc_lin_kernel(const PipeParams pp, int* __restrict__ flags) {
             cp_dst[j] = r * Vs + 4 * c;
             cp_src[j] = r * a_inc + 4 * c;
         }
-        // L2 prefetch of the logits rows of chunk kc: lane l takes 128-byte line (l % lines) of row (l / lines)
-        const int lg_lines = (V * 4 + 127) / 128;
-        auto prefetch_logits = [&](int kc) {
-            if (kc < nch) {
-                int tt0, rows;
-                chunk_at(kc, tt0, rows);
-                const int r = lane / lg_lines, ln = lane - r * lg_lines;
-                if (r < rows) {
-                    const char* q = reinterpret_cast<const char*>(
-                        acts_b + (ptrdiff_t)(tbase + tsign * (tt0 + r)) * (ptrdiff_t)frame_stride) + 128 * ln;
-                    asm volatile("prefetch.global.L2 [%0];" ::"l"(q));
-                }
-            }
-        };
         auto issue_logits = [&](int ka, int slot_a) {
             int tt0, rows;
             chunk_at(ka, tt0, rows);
@@ -886,27 +841,8 @@ ctc_lin_kernel(const PipeParams pp, int* __restrict__ flags) {
             else cp_async_arrive(bar_acts + slot_a);
         };
 
-        // V = 48 with four frames per pass: the logits never touch shared memory.  Every lane keeps
-        // its 3 float2 of the chunks it+1 and it+2 in registers (plain read-only loads issued two
-        // iterations ahead), so the softmax pass is: exp, one redux, three shuffles, three stores.
-        // (measured slower than the cp.async ring on B200 -- the loads are not back after two
-        // iterations -- so the path is kept but switched off)
-        const bool fastV = false && GA == 8 && V2 == 24 && nA == 1;
-        float2 lg0[3], lg1[3], lg2[3];   // logits of chunk c live in set c % 3 (no register moves)
-        int lg_ph = 0;                   // it % 3
-        auto load_logits = [&](int kc, float2 (&dst)[3]) {
-            if (kc < nch) {
-                int tt0, rows;
-                chunk_at(kc, tt0, rows);
-                if (fA < rows) {
-                    const float2* src = reinterpret_cast<const float2*>(
-                        acts_b + (ptrdiff_t)(tbase + tsign * (tt0 + fA)) * (ptrdiff_t)frame_stride) + glA;
-#pragma unroll
-                    for (int j = 0; j < 3; ++j) dst[j] = __ldg(src + 8 * j);
-                }
-            }
-        };
-        auto softmax_fast = [&](float* base, int rows, const float2 (&lg)[3], float* ysv) {
+        // V = 48 with four frames per pass: straight-line code, the row stays in registers
+        auto softmax_fast = [&](float* base, int rows, const float2 (&lg)[3]) {
             const bool act = fA < rows;
             float* row = base + min(fA, rows - 1) * Vs;
             float2* row2 = reinterpret_cast<float2*>(row);
@@ -935,9 +871,7 @@ ctc_lin_kernel(const PipeParams pp, int* __restrict__ flags) {
             if (act) {
 #pragma unroll
                 for (int j = 0; j < 3; ++j) {
-                    const float2 yv = make_float2(x[j].x * rs, x[j].y * rs);
-                    row2[glA + 8 * j] = yv;
-                    if (ysv) reinterpret_cast<float2*>(ysv)[glA + 8 * j] = yv;   // for the partner's second half
+                    row2[glA + 8 * j] = make_float2(x[j].x * rs, x[j].y * rs);
                 }
                 if (glA == 0) row[V] = 0.f;     // what padding pairs gather
             }
@@ -946,7 +880,7 @@ ctc_lin_kernel(const PipeParams pp, int* __restrict__ flags) {
         // ---- fused softmax, in place, of my F frames of a chunk (a group of G lanes per frame) ----
         // The maximum of a row comes from ONE redux.sync per group (no shuffle tree); the sum needs
         // log2 G shuffle levels.
-        auto softmax_chunk = [&](float* base, int rows, float* ysv) {
+        auto softmax_chunk = [&](float* base, int rows) {
             const int G = GA, gl = glA, f = fA;
             const unsigned gmask = gmaskA;
             const bool act = f < rows;
@@ -956,7 +890,7 @@ ctc_lin_kernel(const PipeParams pp, int* __restrict__ flags) {
                 float2 lg[3];
 #pragma unroll
                 for (int j = 0; j < 3; ++j) lg[j] = row2[gl + 8 * j];
-                softmax_fast(base, rows, lg, ysv);
+                softmax_fast(base, rows, lg);
                 return;
             }
             if (V2 <= 4 * G) {      // at most 4 float2 per lane: the row stays in registers
@@ -1126,7 +1060,7 @@ ctc_lin_kernel(const PipeParams pp, int* __restrict__ flags) {
         // ---- the helper schedule -----------------------------------------------------------
         // Iteration `it`:  SOFT 0 requests the logits of chunk it + kLinYDist + 1; SOFT: softmax of
         // chunk it; GRAD: gradient rows of chunk it-3 (REC runs chunk it-1, COMB chunk it-2).
-        const bool iss_acts = isA && ha == 0 && !fastV;
+        const bool iss_acts = isA && ha == 0;
         const bool do_sm = isA && ha * FA < TC, do_gr = isB && hb * FB < TC && want_grad;
         Ring iss_a(NL), sm_a(NL), gr_a(NL);
         int gr_o = 0;
@@ -1139,7 +1073,6 @@ ctc_lin_kernel(const PipeParams pp, int* __restrict__ flags) {
                 iss_a.advance();
             }
         }
-        if (fastV && do_sm) { load_logits(0, lg0); load_logits(1, lg1); }
         for (int it = 0; it < n_it; ++it) {
             LPROF_BEGIN();
             {
@@ -1147,7 +1080,6 @@ ctc_lin_kernel(const PipeParams pp, int* __restrict__ flags) {
                 if (iss_acts) {
                     if (ka < nch) issue_logits(ka, iss_a.slot);
                     else if (nA == 1) cp_async_commit();   // keep one group per iteration
-                    if (kLinL2Dist > 0 && lg_lines * TC <= 32) prefetch_logits(ka + kLinL2Dist);
                 }
                 iss_a.advance();
             }
@@ -1166,23 +1098,13 @@ ctc_lin_kernel(const PipeParams pp, int* __restrict__ flags) {
             if (do_sm && it < nchh_i) {               // softmax of chunk `it`
                 int tt0, rows;
                 chunk_at(it, tt0, rows);
-                if (fastV) {
-                    // chunk it+2 is requested now (two iterations of flight time) into the set that
-                    // chunk it-1 has just left
-                    float* ybase = s_y + (size_t)sm_a.slot * TC * Vs;
-                    if (lg_ph == 0) { load_logits(it + 2, lg2); softmax_fast(ybase, rows, lg0, nullptr); }
-                    else if (lg_ph == 1) { load_logits(it + 2, lg0); softmax_fast(ybase, rows, lg1, nullptr); }
-                    else { load_logits(it + 2, lg1); softmax_fast(ybase, rows, lg2, nullptr); }
-                } else {
-                    if (nA == 1) { cp_async_wait<kLinYDist + 1>(); __syncwarp(); }
-                    else mbar_wait(bar_acts + sm_a.slot, sm_a.parity);
-                    LPROF_SEC(12);
-                    softmax_chunk(s_y + (size_t)sm_a.slot * TC * Vs, rows, nullptr);
-                }
+                if (nA == 1) { cp_async_wait<kLinYDist + 1>(); __syncwarp(); }
+                else mbar_wait(bar_acts + sm_a.slot, sm_a.parity);
+                LPROF_SEC(12);
+                softmax_chunk(s_y + (size_t)sm_a.slot * TC * Vs, rows);
             }
             LPROF_SEC(13);
             sm_a.advance();
-            lg_ph = lg_ph == 2 ? 0 : lg_ph + 1;
             LPROF_END(it >= n1 + 1);
             __syncthreads();
             if (it == n1) {
