@@ -152,7 +152,7 @@ bool pick_lin(int T, int V, int S_max, int n_utt, Geometry* g) {
     // leave 128 registers per thread, which the two-rows-in-flight combine pass needs
     if (!(H == 1 || H == 2 || H == 4 || H == 8)) H = V > 256 ? 4 : (R == 1 ? 1 : 2);
     int NC = env_int("CTC_B200_COMB", 0);          // combine groups (warps per recursion warp)
-    if (NC < 1 || NC > 4) NC = R == 1 ? 2 : 1;
+    if (NC < 1 || NC > 4) NC = R <= 4 ? 2 : 1;   // two combine groups while the CTA stays within 512 threads
     int NT = 32 * ((1 + NC) * R + H);
     if (R == 1)   // the single-recursion-warp kernels are built for at most 256 threads
         while (NT > 256 && H > 1) { H >>= 1; NT = 32 * ((1 + NC) * R + H); }
@@ -273,8 +273,13 @@ int launch_lin_r1(const PipeParams& pp, int* flags, const Geometry& g, int n_utt
                         : launch_lin_pt<P, 1, 0, 256, 2>(pp, flags, g, n_utt, st);
 }
 
-// Several recursion warps (targets longer than 248 labels): P = 8, run-time strides.
+// Several recursion warps (targets longer than 248 labels): P = 8; compile-time strides for 2 and 4
+// recursion warps (up to 1016 labels) with the V <= 60 emission ring, run-time strides otherwise.
 int launch_lin_rn(const PipeParams& pp, int* flags, const Geometry& g, int n_utt, cudaStream_t st) {
+    if (g.lYS == 80 && g.lNT <= 512) {
+        if (g.lR == 2) return launch_lin_pt<8, 2, 80, 512, 1>(pp, flags, g, n_utt, st);
+        if (g.lR == 4) return launch_lin_pt<8, 4, 80, 512, 1>(pp, flags, g, n_utt, st);
+    }
     if (g.lNT <= 256) return launch_lin_pt<8, 0, 0, 256, 2>(pp, flags, g, n_utt, st);
     if (g.lNT <= 512) return launch_lin_pt<8, 0, 0, 512, 1>(pp, flags, g, n_utt, st);
     return launch_lin_pt<8, 0, 0, 1024, 1>(pp, flags, g, n_utt, st);
