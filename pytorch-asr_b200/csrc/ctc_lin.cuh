@@ -208,6 +208,8 @@ ctc_lin_kernel(const PipeParams pp, int* __restrict__ flags) {
     const int nA = H >= 2 ? H / 2 : 1, nB = H >= 2 ? H - nA : 1;
     const bool isA = hw >= 0 && (H == 1 || hw < nA), isB = hw >= 0 && (H == 1 || hw >= nA);
     const int ha = hw, hb = H == 1 ? 0 : hw - nA;
+    // wide vocabulary: logits rows come in by TMA bulk copies (one per row) instead of cp.async
+    const bool wide_rows = nA > 1 && V > 256;
 
     // ---- GRAD warps: mandatory zero fill of gradient rows t >= T_b (no compute) --------
     if (want_grad && isB) {
@@ -248,7 +250,7 @@ ctc_lin_kernel(const PipeParams pp, int* __restrict__ flags) {
     for (int i = threadIdx.x; i < 2 * TC * ER; i += NT) s_occ[i] = 0.f;   // occupancy accumulators start at 0
     if (threadIdx.x == 0) {
         s_flag[0] = 0; s_flag[1] = 0; s_flag[2] = 0;
-        for (int i = 0; i < NL; ++i) mbar_init(bar_acts + i, 32);   // 32 lanes' cp.async
+        for (int i = 0; i < NL; ++i) mbar_init(bar_acts + i, wide_rows ? 1 : 32);   // 32 lanes' cp.async, or one TMA producer
         for (int i = 0; i < NS; ++i) mbar_init(bar_part + i, 1);    // one TMA producer
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         fence_proxy_async();
@@ -823,6 +825,20 @@ ctc_lin_kernel(const PipeParams pp, int* __restrict__ flags) {
             chunk_at(ka, tt0, rows);
             float* dst = s_y + (size_t)slot_a * TC * Vs;
             const float* src = acts_b + (ptrdiff_t)(tbase + tsign * tt0) * (ptrdiff_t)frame_stride;
+            if (wide_rows) {
+                // wide vocabulary: ONE TMA bulk copy per logits row (V * 4 bytes, contiguous in HBM)
+                // instead of V / 128 cp.async per lane and row.  The ring slot was last written through
+                // the generic proxy NL - 1 CTA barriers ago (softmax of an earlier chunk) and last read
+                // at least one CTA barrier ago (gradient rows); as for the partner ring, no
+                // fence.proxy.async is issued per chunk: it was measured at ~1200 cycles of the issuing
+                // warp on B200 (ncu, 31 % of that warp's samples).
+                if (lane == 0) {    // the barrier expects ONE arrival in this mode
+                    mbar_expect_tx(bar_acts + slot_a, (unsigned)(rows * V) * 4u);
+                    for (int r = 0; r < rows; ++r)
+                        bulk_g2s(dst + r * Vs, src + r * a_inc, (unsigned)V * 4u, bar_acts + slot_a);
+                }
+                return;
+            }
 #pragma unroll
             for (int j = 0; j < 2; ++j)
                 if (cp_row[j] < rows) cp_async16(dst + cp_dst[j], src + cp_src[j]);
@@ -917,6 +933,39 @@ ctc_lin_kernel(const PipeParams pp, int* __restrict__ flags) {
                     for (int j = 0; j < 4; ++j) {
                         const int c = gl + j * G;
                         if (c < V2) row2[c] = make_float2(x[j].x * rs, x[j].y * rs);
+                    }
+                }
+            } else if (V4 <= 8 * G) {
+                // wide vocabulary (V = 1024 with a warp per frame): at most 8 float4 per lane, the row
+                // stays in registers and every load is issued before the first use (the looped path
+                // below pays the shared-memory latency once per element and pass)
+                float4* row4 = reinterpret_cast<float4*>(row);
+                float4 x[8];
+                float m = -CUDART_INF_F;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const int c = gl + j * G;
+                    x[j] = c < V4 ? row4[c] : make_float4(-CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F);
+                    m = fmaxf(m, fmaxf(fmaxf(x[j].x, x[j].y), fmaxf(x[j].z, x[j].w)));
+                }
+                m = group_max(m, G);
+                const float mb = m * kLog2e;
+                float z0 = 0.f, z1 = 0.f;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    x[j].x = ex2f(fmaf(x[j].x, kLog2e, -mb));
+                    x[j].y = ex2f(fmaf(x[j].y, kLog2e, -mb));
+                    x[j].z = ex2f(fmaf(x[j].z, kLog2e, -mb));
+                    x[j].w = ex2f(fmaf(x[j].w, kLog2e, -mb));
+                    z0 += x[j].x + x[j].y;
+                    z1 += x[j].z + x[j].w;
+                }
+                const float rs = 1.0f / group_sum(z0 + z1, G);
+                if (act) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const int c = gl + j * G;
+                        if (c < V4) row4[c] = make_float4(x[j].x * rs, x[j].y * rs, x[j].z * rs, x[j].w * rs);
                     }
                 }
             } else {
@@ -1029,6 +1078,61 @@ ctc_lin_kernel(const PipeParams pp, int* __restrict__ flags) {
                         }
                     }
                     if (!(fabsf(tot + bs - 1.0f) <= kMassTol)) s_flag[0] = 1;   // NaN-safe
+                }
+                return;
+            }
+            if (R == 1 && V4 <= 8 * G) {     // wide vocabulary: at most 8 x 128 bit per lane, all loads up front
+                uint4* o4 = reinterpret_cast<uint4*>(orow);
+                const float4* y4 = reinterpret_cast<const float4*>(y2);
+                float4* g4 = reinterpret_cast<float4*>(g2);
+                uint4 x[8];
+                float4 y[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const int c = gl + j * G;
+                    x[j] = make_uint4(0u, 0u, 0u, 0u);
+                    y[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (c < V4) {
+                        x[j] = o4[c];
+                        y[j] = y4[c];
+                        if (act) o4[c] = make_uint4(0u, 0u, 0u, 0u);
+                    }
+                }
+                float4 o[8];
+                float t0 = 0.f, t1 = 0.f;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    o[j].x = __uint2float_rn(x[j].x) * (1.0f / kQ31);
+                    o[j].y = __uint2float_rn(x[j].y) * (1.0f / kQ31);
+                    o[j].z = __uint2float_rn(x[j].z) * (1.0f / kQ31);
+                    o[j].w = __uint2float_rn(x[j].w) * (1.0f / kQ31);
+                    t0 += o[j].x + o[j].y;
+                    t1 += o[j].z + o[j].w;
+                }
+                float tot = t0 + t1;
+                for (int sft = G >> 1; sft > 0; sft >>= 1) {
+                    bs += __shfl_xor_sync(0xffffffffu, bs, sft);
+                    tot += __shfl_xor_sync(0xffffffffu, tot, sft);
+                }
+                if (act) {
+                    const int cb = blank >> 2, kb = blank & 3;
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const int c = gl + j * G;
+                        if (c < V4) {
+                            const bool mine = cb == c;
+                            o[j].x += (mine && kb == 0) ? bs : 0.f;
+                            o[j].y += (mine && kb == 1) ? bs : 0.f;
+                            o[j].z += (mine && kb == 2) ? bs : 0.f;
+                            o[j].w += (mine && kb == 3) ? bs : 0.f;
+                            g4[c] = make_float4(gscale * (y[j].x - o[j].x), gscale * (y[j].y - o[j].y),
+                                                gscale * (y[j].z - o[j].z), gscale * (y[j].w - o[j].w));
+                        }
+                    }
+                    if (!(fabsf(tot + bs - 1.0f) <= kMassTol)) s_flag[0] = 1;   // NaN-safe
+#ifdef CTC_B200_MASSDEV
+                    atomicMax(&s_flag[2], __float_as_int(fabsf(tot + bs - 1.0f)));
+#endif
                 }
                 return;
             }
