@@ -166,12 +166,13 @@ bool pick_lin(int T, int V, int S_max, int n_utt, Geometry* g) {
         for (int ci = 0; ci < 3; ++ci) {
             int TC = cand[ci];
             if (tc_env >= 1 && tc_env <= 4) TC = tc_env;   // the kernel unrolls 4 rows
-            LinSmem lay(NP, R, V, TC, RS, YS);
+            const int YSc = TC == 4 ? YS : 0;   // the fixed-stride variants are built for chunks of 4 frames
+            LinSmem lay(NP, R, V, TC, RS, YSc);
             const int need = std::max(1, std::min(4, (2 * std::max(n_utt, 1) + kNumSmsHint - 1) / kNumSmsHint));
             const int limit = pass == 0 ? std::min(kMaxSmemBytes, 227 * 1024 / need - 1024) : kMaxSmemBytes;
             if (lay.total > limit) continue;
             g->lP = P; g->lNT = NT; g->lNP = NP; g->lchunk = TC; g->lRS = RS; g->lsmem = lay.total;
-            g->lR = R; g->lH = H; g->lD = NC; g->lYS = YS;
+            g->lR = R; g->lH = H; g->lD = NC; g->lYS = YSc;
             g->l_lat_utt_stride = (size_t)std::max(T, 1) * (size_t)RS;
             return true;
         }

@@ -67,6 +67,16 @@ constexpr float kQ31 = 2147483648.0f;   // label occupancies are accumulated as 
 #ifndef CTC_LIN_YD
 #define CTC_LIN_YD 1
 #endif
+#ifndef CTC_LIN_TMA_Y
+#define CTC_LIN_TMA_Y 0   // 1: logits rows by TMA bulk copies for every vocabulary (measured slower for 192-byte rows:
+                          // C2 0.310 vs 0.280 ms); 0: cp.async, and TMA only for rows wider than 1 KB
+#endif
+#ifndef CTC_LIN_TC4
+#define CTC_LIN_TC4 1     // chunk length as a compile-time constant in the YS = 80 variants
+#endif
+#ifndef CTC_LIN_ISS_COMB
+#define CTC_LIN_ISS_COMB 0   // 1: the first combine warp (idle in the first half) requests the logits rows
+#endif
 #ifndef CTC_LIN_PD
 #define CTC_LIN_PD 2
 #endif
@@ -168,7 +178,8 @@ ctc_lin_kernel(const PipeParams pp, int* __restrict__ flags) {
     const int b = p.utt_begin + (blockIdx.x >> 1);
     const bool rev = (blockIdx.x & 1) != 0;
     const int T = p.T, N = p.N, V = p.V, blank = p.blank;
-    const int RS = RC > 0 ? lin_row_stride(32 * P * RC, P) : p.row_stride, TC = p.chunk;
+    // the V <= 60 emission-ring variants (YS = 80) are only launched with chunks of 4 frames
+    const int RS = RC > 0 ? lin_row_stride(32 * P * RC, P) : p.row_stride, TC = (YS == 80 && CTC_LIN_TC4) ? 4 : p.chunk;
     const int NC = pp.D;           // combine groups: group g takes the rows r == g (mod NC) of a chunk
     const bool is_rec = w < R, is_comb = w >= R && w < (1 + NC) * R;
     const int hw = w - (1 + NC) * R;   // helper index (>= 0 for SOFT / GRAD warps)
@@ -209,7 +220,7 @@ ctc_lin_kernel(const PipeParams pp, int* __restrict__ flags) {
     const bool isA = hw >= 0 && (H == 1 || hw < nA), isB = hw >= 0 && (H == 1 || hw >= nA);
     const int ha = hw, hb = H == 1 ? 0 : hw - nA;
     // wide vocabulary: logits rows come in by TMA bulk copies (one per row) instead of cp.async
-    const bool wide_rows = nA > 1 && V > 256;
+    const bool wide_rows = CTC_LIN_TMA_Y ? true : (YS == 0 && nA > 1 && V > 256);
 
     // ---- GRAD warps: mandatory zero fill of gradient rows t >= T_b (no compute) --------
     if (want_grad && isB) {
@@ -217,8 +228,19 @@ ctc_lin_kernel(const PipeParams pp, int* __restrict__ flags) {
         const int mine = (nrows + (rev ? 0 : 1)) >> 1;  // rows Tb+rev, Tb+rev+2, ...
         float* g = grad_b + (size_t)(Tb + (rev ? 1 : 0) + 2 * hb) * frame_stride;
         const size_t ginc = 2 * (size_t)nB * frame_stride;
-        for (int r = hb; r < mine; r += nB, g += ginc)
-            for (int c = lane; c < V4; c += 32) reinterpret_cast<float4*>(g)[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (YS == 80 || V4 < 32) {
+            // narrow rows: the 32 lanes of a store cover 32 / V4 rows (V = 48: 12 lanes per row otherwise)
+            int r = hb, c = lane;
+            while (c >= V4) { c -= V4; r += nB; g += ginc; }
+            while (r < mine) {
+                reinterpret_cast<float4*>(g)[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+                c += 32;
+                while (c >= V4) { c -= V4; r += nB; g += ginc; }
+            }
+        } else {
+            for (int r = hb; r < mine; r += nB, g += ginc)
+                for (int c = lane; c < V4; c += 32) reinterpret_cast<float4*>(g)[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
     }
     if (Tb == 0) {  // torch: empty input => 0 for an empty target, +inf otherwise
         if (threadIdx.x == 0) {
@@ -270,6 +292,22 @@ ctc_lin_kernel(const PipeParams pp, int* __restrict__ flags) {
     auto chunk_at = [&](int c, int& tt0, int& rows) {  // first sweep step / row count of chunk c
         if (c < n1) { tt0 = c * TC; rows = min(TC, n_store - tt0); }
         else { tt0 = n_store + (c - n1) * TC; rows = want_grad ? min(TC, Tb - tt0) : 1; }
+    };
+    // logits rows of chunk ka -> slot `slot` of the emission ring: ONE TMA bulk copy per row (V * 4 bytes,
+    // contiguous in HBM), completion on the slot's mbarrier (which expects ONE arrival).  Called by one lane.
+    // The ring slot was last written through the generic proxy NL - 1 CTA barriers ago (softmax of an
+    // earlier chunk) and last read at least one CTA barrier ago (gradient rows); as for the partner ring,
+    // no fence.proxy.async is issued per chunk: it was measured at ~1200 cycles of the issuing warp on
+    // B200 (ncu, 31 % of that warp's samples).
+    auto issue_logits_tma = [&](int ka, int slot) {
+        int tt0, rows;
+        chunk_at(ka, tt0, rows);
+        float* dst = s_y + (size_t)slot * TC * Vs;
+        const ptrdiff_t inc = (ptrdiff_t)tsign * (ptrdiff_t)frame_stride;
+        const float* src = acts_b + (ptrdiff_t)(tbase + tsign * tt0) * (ptrdiff_t)frame_stride;
+        mbar_expect_tx(bar_acts + slot, (unsigned)(rows * V) * 4u);
+        for (int r = 0; r < rows; ++r)
+            bulk_g2s(dst + r * Vs, src + r * inc, (unsigned)V * 4u, bar_acts + slot);
     };
     const int s0 = tid * P;          // my first slot (REC / COMB)
     const int PW = P == 8 ? 4 : P;   // floats per thread in one contiguous piece of a plane
@@ -520,6 +558,14 @@ ctc_lin_kernel(const PipeParams pp, int* __restrict__ flags) {
             }
         };
         Ring ring_part(NS), iss_p(NS);
+#if CTC_LIN_ISS_COMB
+        Ring iss_y(NL);
+        const bool iss_y_on = iss_part && wide_rows && lane == 0;
+        for (int k = 0; k <= kLinYDist; ++k) {    // prologue: logits of chunks 0..kLinYDist
+            if (iss_y_on && k < nch) issue_logits_tma(k, iss_y.slot);
+            iss_y.advance();
+        }
+#endif
         int a_buf = 0, o_buf = 0;
         // loop-invariant kernel parameters live in registers (each re-read from the constant bank
         // would be an exposed latency in front of a branch)
@@ -534,6 +580,10 @@ ctc_lin_kernel(const PipeParams pp, int* __restrict__ flags) {
                 if (iss_part) issue_partner(it + kLinPDist - 2, iss_p.slot);
                 iss_p.advance();
             }
+#if CTC_LIN_ISS_COMB
+            if (iss_y_on && it + kLinYDist + 1 < nch_i) issue_logits_tma(it + kLinYDist + 1, iss_y.slot);
+            iss_y.advance();
+#endif
             const int k = it - 2;
             if (k >= n1_i && k < nch_i) {
                 int tt0, rows;
@@ -811,6 +861,7 @@ ctc_lin_kernel(const PipeParams pp, int* __restrict__ flags) {
         //      its first two copies never change, so they are computed once
         const ptrdiff_t a_inc = (ptrdiff_t)tsign * (ptrdiff_t)frame_stride;
         const int n4 = TC * V4;
+        const bool cp_groups = nA == 1 && !wide_rows;   // one softmax warp waits for its own cp.async groups
         int cp_dst[2], cp_row[2];
         ptrdiff_t cp_src[2];
 #pragma unroll
@@ -826,17 +877,7 @@ ctc_lin_kernel(const PipeParams pp, int* __restrict__ flags) {
             float* dst = s_y + (size_t)slot_a * TC * Vs;
             const float* src = acts_b + (ptrdiff_t)(tbase + tsign * tt0) * (ptrdiff_t)frame_stride;
             if (wide_rows) {
-                // wide vocabulary: ONE TMA bulk copy per logits row (V * 4 bytes, contiguous in HBM)
-                // instead of V / 128 cp.async per lane and row.  The ring slot was last written through
-                // the generic proxy NL - 1 CTA barriers ago (softmax of an earlier chunk) and last read
-                // at least one CTA barrier ago (gradient rows); as for the partner ring, no
-                // fence.proxy.async is issued per chunk: it was measured at ~1200 cycles of the issuing
-                // warp on B200 (ncu, 31 % of that warp's samples).
-                if (lane == 0) {    // the barrier expects ONE arrival in this mode
-                    mbar_expect_tx(bar_acts + slot_a, (unsigned)(rows * V) * 4u);
-                    for (int r = 0; r < rows; ++r)
-                        bulk_g2s(dst + r * Vs, src + r * a_inc, (unsigned)V * 4u, bar_acts + slot_a);
-                }
+                if (lane == 0) issue_logits_tma(ka, slot_a);
                 return;
             }
 #pragma unroll
@@ -853,7 +894,7 @@ ctc_lin_kernel(const PipeParams pp, int* __restrict__ flags) {
             }
             // one softmax warp: it waits for its own copies with cp.async groups (the mbarrier arrive
             // costs the issuing warp about a microsecond on B200); several: completion on the mbarrier
-            if (nA == 1) cp_async_commit();
+            if (cp_groups) cp_async_commit();
             else cp_async_arrive(bar_acts + slot_a);
         };
 
@@ -935,7 +976,7 @@ ctc_lin_kernel(const PipeParams pp, int* __restrict__ flags) {
                         if (c < V2) row2[c] = make_float2(x[j].x * rs, x[j].y * rs);
                     }
                 }
-            } else if (V4 <= 8 * G) {
+            } else if (YS == 0 && V4 <= 8 * G) {
                 // wide vocabulary (V = 1024 with a warp per frame): at most 8 float4 per lane, the row
                 // stays in registers and every load is issued before the first use (the looped path
                 // below pays the shared-memory latency once per element and pass)
@@ -1081,7 +1122,7 @@ ctc_lin_kernel(const PipeParams pp, int* __restrict__ flags) {
                 }
                 return;
             }
-            if (R == 1 && V4 <= 8 * G) {     // wide vocabulary: at most 8 x 128 bit per lane, all loads up front
+            if (YS == 0 && R == 1 && V4 <= 8 * G) {     // wide vocabulary: at most 8 x 128 bit per lane, all loads up front
                 uint4* o4 = reinterpret_cast<uint4*>(orow);
                 const float4* y4 = reinterpret_cast<const float4*>(y2);
                 float4* g4 = reinterpret_cast<float4*>(g2);
@@ -1164,7 +1205,7 @@ ctc_lin_kernel(const PipeParams pp, int* __restrict__ flags) {
         // ---- the helper schedule -----------------------------------------------------------
         // Iteration `it`:  SOFT 0 requests the logits of chunk it + kLinYDist + 1; SOFT: softmax of
         // chunk it; GRAD: gradient rows of chunk it-3 (REC runs chunk it-1, COMB chunk it-2).
-        const bool iss_acts = isA && ha == 0;
+        const bool iss_acts = isA && ha == 0 && !(CTC_LIN_ISS_COMB && wide_rows);
         const bool do_sm = isA && ha * FA < TC, do_gr = isB && hb * FB < TC && want_grad;
         Ring iss_a(NL), sm_a(NL), gr_a(NL);
         int gr_o = 0;
@@ -1173,7 +1214,7 @@ ctc_lin_kernel(const PipeParams pp, int* __restrict__ flags) {
         if (iss_acts) {
             for (int k = 0; k <= kLinYDist; ++k) {    // prologue: logits of chunks 0..kLinYDist
                 if (k < nch) issue_logits(k, iss_a.slot);
-                else if (nA == 1) cp_async_commit();
+                else if (cp_groups) cp_async_commit();
                 iss_a.advance();
             }
         }
@@ -1183,7 +1224,7 @@ ctc_lin_kernel(const PipeParams pp, int* __restrict__ flags) {
                 const int ka = it + kLinYDist + 1;
                 if (iss_acts) {
                     if (ka < nch) issue_logits(ka, iss_a.slot);
-                    else if (nA == 1) cp_async_commit();   // keep one group per iteration
+                    else if (cp_groups) cp_async_commit();   // keep one group per iteration
                 }
                 iss_a.advance();
             }
@@ -1202,7 +1243,7 @@ ctc_lin_kernel(const PipeParams pp, int* __restrict__ flags) {
             if (do_sm && it < nchh_i) {               // softmax of chunk `it`
                 int tt0, rows;
                 chunk_at(it, tt0, rows);
-                if (nA == 1) { cp_async_wait<kLinYDist + 1>(); __syncwarp(); }
+                if (cp_groups) { cp_async_wait<kLinYDist + 1>(); __syncwarp(); }
                 else mbar_wait(bar_acts + sm_a.slot, sm_a.parity);
                 LPROF_SEC(12);
                 softmax_chunk(s_y + (size_t)sm_a.slot * TC * Vs, rows);

@@ -101,6 +101,23 @@ def test_against_reference_and_oracle(B, T, V, S, peaky, rep):
     assert np.abs(gmean - refm["grad"].numpy()).max() <= GRAD_ATOL
 
 
+@pytest.mark.parametrize("B,T,V,S,blank", [
+    (4, 203, 1024, 40, 0),       # C4's vocabulary: TMA row copies, register-resident softmax / gradient rows
+    (3, 90, 1024, 17, 513),      # blank in another 128-bit column / component
+    (3, 77, 300, 15, 2),         # V / 4 not a multiple of the lane group: guarded tails
+    (2, 60, 2048, 11, 0),        # wider than the register paths: looped softmax / gradient rows
+])
+def test_wide_vocabulary(B, T, V, S, blank):
+    acts, tg, il, tl = synth.make_batch(B, T, V, S, seed=21, repeat_frac=0.2)
+    if blank:                    # labels must avoid the blank index
+        tg = torch.where(tg == blank, torch.zeros_like(tg), tg)
+    nll, grad, _ = run_engine(acts, tg, il, tl, blank=blank, reduction="sum")
+    orc = oracle.ctc_oracle_f64(acts.numpy(), tg.numpy(), il.numpy(), tl.numpy(), blank=blank)
+    assert_parity(nll, grad, orc["nll"], orc["grad"], grad_atol=grad_atol_fp64(T), what="wide vocabulary")
+    for b in range(B):           # padding rows are exact zeros
+        assert not grad[int(il[b]):, b].any()
+
+
 def test_reference_call_convention_mean():
     """Exactly the reference's call: reduction='mean', int32 CPU targets/lengths."""
     acts, tg, il, tl = synth.make_config("C1")
