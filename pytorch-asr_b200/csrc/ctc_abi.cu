@@ -249,15 +249,15 @@ int launch_pipe_p(const PipeParams& pp, const Geometry& g, int n_utt, cudaStream
     return launch_pipe_pt<P, 1024, 1>(pp, g, n_utt, st);
 }
 
-template <int P, int RC, int YS, int MAXT, int MINB>
+template <int P, int RC, int YS, int MAXT, int MINB, bool FIX = false>
 int launch_lin_pt(const PipeParams& pp, int* flags, const Geometry& g, int n_utt, cudaStream_t st) {
     static int configured_smem = -1;
     if (g.lsmem > configured_smem) {
-        CTC_CUDA(cudaFuncSetAttribute(ctc_lin_kernel<P, RC, YS, MAXT, MINB>,
+        CTC_CUDA(cudaFuncSetAttribute(ctc_lin_kernel<P, RC, YS, MAXT, MINB, FIX>,
                                       cudaFuncAttributeMaxDynamicSharedMemorySize, g.lsmem));
         configured_smem = g.lsmem;
     }
-    ctc_lin_kernel<P, RC, YS, MAXT, MINB><<<dim3(2 * n_utt), dim3(g.lNT), g.lsmem, st>>>(pp, flags);
+    ctc_lin_kernel<P, RC, YS, MAXT, MINB, FIX><<<dim3(2 * n_utt), dim3(g.lNT), g.lsmem, st>>>(pp, flags);
     CTC_CUDA(cudaGetLastError());
     return CTC_B200_OK;
 }
@@ -266,6 +266,10 @@ int launch_lin_pt(const PipeParams& pp, int* flags, const Geometry& g, int n_utt
 template <int P>
 int launch_lin_r1(const PipeParams& pp, int* flags, const Geometry& g, int n_utt, cudaStream_t st) {
     if (g.lYS == 80) {
+        if constexpr (P == 8) {   // the headline shape class: V = 48, REC + 2 x COMB + one helper warp
+            if (g.lNT == 128 && g.lH == 1 && g.lD == 2 && pp.f.V == 48 && env_int("CTC_B200_NOFIX", 0) == 0)
+                return launch_lin_pt<P, 1, 80, 128, 4, true>(pp, flags, g, n_utt, st);
+        }
         if (g.lNT <= 128) return launch_lin_pt<P, 1, 80, 128, 4>(pp, flags, g, n_utt, st);
         if (g.lNT <= 160) return launch_lin_pt<P, 1, 80, 160, 4>(pp, flags, g, n_utt, st);
         return launch_lin_pt<P, 1, 80, 256, 2>(pp, flags, g, n_utt, st);

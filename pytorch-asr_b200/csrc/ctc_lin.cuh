@@ -165,22 +165,24 @@ struct LinSmem {
 // Template parameters: P pairs per thread; RC = number of recursion warps when it is known at
 // compile time (1: the common case S + P <= 32 * P, every stride becomes an immediate) or 0 for
 // "run time"; YS = floats per row of the emission ring (compile time) or 0 for "run time".
-template <int P, int RC, int YS, int MAXT, int MINB>
+// FIX: the headline shape class (V = 48, one helper warp, two combine groups, 128 threads) with all
+// of these as compile-time constants.
+template <int P, int RC, int YS, int MAXT, int MINB, bool FIX = false>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(MAXT, MINB)
 ctc_lin_kernel(const PipeParams pp, int* __restrict__ flags) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const FusedParams& p = pp.f;
-    const int NT = blockDim.x, NW = NT >> 5;
-    const int R = RC > 0 ? RC : pp.R, H = pp.H, NP = RC > 0 ? 32 * P * RC : pp.NP;
+    const int NT = FIX ? 128 : blockDim.x, NW = NT >> 5;
+    const int R = RC > 0 ? RC : pp.R, H = FIX ? 1 : pp.H, NP = RC > 0 ? 32 * P * RC : pp.NP;
     const int lane = threadIdx.x & 31;
     const int shift = pp.rotate > 0 ? (int)((blockIdx.x / pp.rotate) * R) % NW : 0;
     const int w = ((int)(threadIdx.x >> 5) + NW - shift) % NW;   // role (virtual) warp id
     const int b = p.utt_begin + (blockIdx.x >> 1);
     const bool rev = (blockIdx.x & 1) != 0;
-    const int T = p.T, N = p.N, V = p.V, blank = p.blank;
+    const int T = p.T, N = p.N, V = FIX ? 48 : p.V, blank = p.blank;
     // the V <= 60 emission-ring variants (YS = 80) are only launched with chunks of 4 frames
     const int RS = RC > 0 ? lin_row_stride(32 * P * RC, P) : p.row_stride, TC = (YS == 80 && CTC_LIN_TC4) ? 4 : p.chunk;
-    const int NC = pp.D;           // combine groups: group g takes the rows r == g (mod NC) of a chunk
+    const int NC = FIX ? 2 : pp.D;           // combine groups: group g takes the rows r == g (mod NC) of a chunk
     const bool is_rec = w < R, is_comb = w >= R && w < (1 + NC) * R;
     const int hw = w - (1 + NC) * R;   // helper index (>= 0 for SOFT / GRAD warps)
     const int cg = is_comb ? (w - R) / R : 0;
