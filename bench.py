@@ -165,7 +165,7 @@ def main():
     ap.add_argument("--ref-utts", type=int, default=64, help="utterances in the CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-flush", action="store_true")
-    ap.add_argument("--slices", type=int, default=4, help="batch slices of the host-buffer e2e path")
+    ap.add_argument("--slices", type=int, default=8, help="batch slices of the host-buffer e2e path")
     args = ap.parse_args()
     workload = args.workload
 

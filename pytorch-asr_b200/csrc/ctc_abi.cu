@@ -36,6 +36,27 @@ inline int cuda_fail(cudaError_t e) {
         if (e__ != cudaSuccess) return cuda_fail(e__);  \
     } while (0)
 
+// Programmatic dependent launch for the small kernels that follow the fused kernel (its fallback pass
+// and the loss reduction): the launch is set up while the previous kernel drains; the kernels
+// themselves wait for it with griddepcontrol.wait before their first global-memory read.
+thread_local bool t_allow_pdl = true;   // the host-buffer session launches without it (measured slower there)
+
+template <typename... KArgs, typename... Args>
+cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                       Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
+}
+
 struct Geometry {
     int pipe;       // 2: linear-domain kernel (ctc_lin.cuh) with the log-domain pipe kernel as its
                     //    per-utterance fallback, 1: log-domain pipe kernel (ctc_pipe.cuh),
@@ -235,7 +256,10 @@ int launch_pipe_pt(const PipeParams& pp, const Geometry& g, int n_utt, cudaStrea
                                       cudaFuncAttributeMaxDynamicSharedMemorySize, g.smem));
         configured_smem = g.smem;
     }
-    ctc_pipe_kernel<P, MAXT, MINB><<<dim3(2 * n_utt), dim3(g.NT), g.smem, st>>>(pp);
+    if (pp.redo != nullptr && t_allow_pdl && env_int("CTC_B200_PDL", 1))   // fallback pass right behind the linear kernel
+        CTC_CUDA(launch_pdl(ctc_pipe_kernel<P, MAXT, MINB>, dim3(2 * n_utt), dim3(g.NT), (size_t)g.smem, st, pp));
+    else
+        ctc_pipe_kernel<P, MAXT, MINB><<<dim3(2 * n_utt), dim3(g.NT), g.smem, st>>>(pp);
     CTC_CUDA(cudaGetLastError());
     return CTC_B200_OK;
 }
@@ -487,8 +511,12 @@ int ctc_b200_scale_grad_f32(float* grad, const float* scale, int per_utt, int T,
 int ctc_b200_reduce_loss_f32(const float* nll, const int32_t* tgt_lens, int N, int reduction,
                              float* out2, float* loss, void* stream) {
     if (!nll || !tgt_lens || !out2 || N < 0) return CTC_B200_INVALID_ARGUMENT;
-    ctc_reduce_loss_kernel<<<1, 256, 0, static_cast<cudaStream_t>(stream)>>>(
-        nll, tgt_lens, N, reduction == CTC_B200_REDUCE_MEAN ? 1 : 2, out2, loss);
+    if (t_allow_pdl && env_int("CTC_B200_PDL", 1))
+        CTC_CUDA(launch_pdl(ctc_reduce_loss_kernel, dim3(1), dim3(256), (size_t)0, static_cast<cudaStream_t>(stream),
+                            nll, tgt_lens, N, reduction == CTC_B200_REDUCE_MEAN ? 1 : 2, out2, loss));
+    else
+        ctc_reduce_loss_kernel<<<1, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+            nll, tgt_lens, N, reduction == CTC_B200_REDUCE_MEAN ? 1 : 2, out2, loss);
     CTC_CUDA(cudaGetLastError());
     return CTC_B200_OK;
 }
@@ -527,6 +555,10 @@ struct ctc_b200_session {
     size_t res_bytes = 0;
     cudaStream_t s_copy = nullptr, s_comp = nullptr;
     std::vector<cudaEvent_t> ev;
+    // one compute stream per slice: a slice's kernels start when ITS copy has landed, whether or not the
+    // previous slice's (latency-bound) kernel has finished; s_comp joins them for the loss reduction
+    std::vector<cudaStream_t> s_slice;
+    std::vector<cudaEvent_t> ev_done;
     int last_launches = 0;
 };
 
@@ -563,6 +595,10 @@ int ctc_b200_session_create(int T, int N, int V, int S_max, int max_targets, int
     ok(cudaStreamCreateWithFlags(&s->s_comp, cudaStreamNonBlocking));
     s->ev.resize(s->n_slices + 1, nullptr);
     for (auto& ev : s->ev) ok(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    s->s_slice.resize(s->n_slices, nullptr);
+    s->ev_done.resize(s->n_slices, nullptr);
+    for (auto& st : s->s_slice) ok(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    for (auto& ev : s->ev_done) ok(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
     if (e != cudaSuccess) {
         ctc_b200_session_destroy(s);
         return cuda_fail(e);
@@ -574,6 +610,8 @@ int ctc_b200_session_create(int T, int N, int V, int S_max, int max_targets, int
 int ctc_b200_session_destroy(ctc_b200_session* s) {
     if (!s) return CTC_B200_OK;
     for (auto ev : s->ev) if (ev) cudaEventDestroy(ev);
+    for (auto ev : s->ev_done) if (ev) cudaEventDestroy(ev);
+    for (auto st : s->s_slice) if (st) cudaStreamDestroy(st);
     if (s->s_copy) cudaStreamDestroy(s->s_copy);
     if (s->s_comp) cudaStreamDestroy(s->s_comp);
     cudaFree(s->d_acts); cudaFree(s->d_grad); cudaFree(s->d_lattice); cudaFree(s->d_flags);
@@ -644,13 +682,19 @@ int ctc_b200_session_run_host_f32(ctc_b200_session* s, const float* acts_host,
                                    pitch, (size_t)(b1 - b0) * V * sizeof(float), (size_t)T,
                                    cudaMemcpyHostToDevice, s->s_copy));
         CTC_CUDA(cudaEventRecord(s->ev[k], s->s_copy));
-        CTC_CUDA(cudaStreamWaitEvent(s->s_comp, s->ev[k], 0));
+        cudaStream_t sk = env_int("CTC_B200_SLICE_STREAMS", 1) ? s->s_slice[k] : s->s_comp;
+        CTC_CUDA(cudaStreamWaitEvent(sk, s->ev[s->n_slices], 0));   // targets / lengths / cleared status
+        CTC_CUDA(cudaStreamWaitEvent(sk, s->ev[k], 0));              // this slice's logits
+        t_allow_pdl = false;
         int rc = launch_fused(s->d_acts, d_tg, d_off, d_il, d_tl, T, N, V, s->S_max, blank,
                               zero_infinity, b0, b1 - b0, d_nll, want_grad ? s->d_grad : nullptr,
                               d_sc, s->d_lattice + (size_t)b0 * s->geo.lattice_floats_per_utt(),
                               s->lattice_bytes - (size_t)b0 * s->geo.lattice_floats_per_utt() * sizeof(float),
-                              d_status, s->d_flags + 2 * (size_t)b0, s->s_comp);
+                              d_status, s->d_flags + 2 * (size_t)b0, sk);
+        t_allow_pdl = true;
         if (rc != CTC_B200_OK) return rc;
+        CTC_CUDA(cudaEventRecord(s->ev_done[k], sk));
+        CTC_CUDA(cudaStreamWaitEvent(s->s_comp, s->ev_done[k], 0));
         launches += s->geo.pipe == 2 ? 2 : 1;
     }
     ctc_reduce_loss_kernel<<<1, 256, 0, s->s_comp>>>(

@@ -656,6 +656,8 @@ __global__ void ctc_reduce_loss_kernel(const float* __restrict__ nll,
                                        const int32_t* __restrict__ tgt_lens, int N, int mode,
                                        float* __restrict__ out, float* __restrict__ loss) {
     __shared__ double s_part[32];
+    // may be launched with programmatic stream serialization: the producer of `nll` must be complete
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     double acc = 0.0;
     for (int b = threadIdx.x; b < N; b += blockDim.x) {
         double v = (double)nll[b];

@@ -143,6 +143,8 @@ ctc_pipe_kernel(const PipeParams pp) {
     const int b = p.utt_begin + (blockIdx.x >> 1);
     const bool rev = (blockIdx.x & 1) != 0;
     // fallback mode: both CTAs of the cluster leave unless the linear kernel flagged the utterance
+    // (launched with programmatic stream serialization: wait for the linear kernel's flags)
+    if (pp.redo != nullptr) asm volatile("griddepcontrol.wait;" ::: "memory");
     if (pp.redo != nullptr && (pp.redo[2 * b] | pp.redo[2 * b + 1]) == 0) return;
     const int T = p.T, N = p.N, V = p.V, blank = p.blank;
     const int RS = p.row_stride, TC = p.chunk, D = pp.D;
