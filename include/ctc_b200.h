@@ -41,7 +41,8 @@ typedef enum ctc_b200_status {
     CTC_B200_UNSUPPORTED = 3,        /* target longer than 4095 labels, vocabulary too large for smem */
     CTC_B200_CUDA_ERROR = 4,         /* launch / runtime failure, see ctc_b200_last_cuda_error() */
     CTC_B200_BAD_LABEL = 5,          /* device-side check: a label outside [0,V) */
-    CTC_B200_BAD_LENGTH = 6          /* device-side check: input length > T or target length > S_max */
+    CTC_B200_BAD_LENGTH = 6,         /* device-side check: input length > T or target length > S_max */
+    CTC_B200_PEER_TIMEOUT = 7        /* fused loss all-reduce: a peer's pair did not arrive */
 } ctc_b200_status;
 
 typedef enum ctc_b200_reduction {
@@ -137,6 +138,33 @@ int ctc_b200_scale_grad_f32(float* grad, const float* scale, int per_utt, int T,
  */
 int ctc_b200_reduce_loss_f32(const float* nll, const int32_t* tgt_lens, int N, int reduction,
                              float* out2, float* loss, void* stream);
+
+/*
+ * The loss reduction FUSED with the data-parallel job's only collective (SURVEY.md
+ * section 8e; replaces ctc_b200_reduce_loss_f32 + an NCCL all-reduce of the
+ * (sum, count) pair).  ONE kernel, one CTA: it sums this rank's nll, stores the pair
+ * with a sequence number straight into every peer's exchange buffer (P2P stores over
+ * NVLink / NVSwitch), waits for the world_size pairs addressed to this rank and adds
+ * them in rank order, so that every rank obtains bit-identical results:
+ * out2 = (global sum, global utterance count), loss[0] = out2[0] / out2[1] for MEAN,
+ * out2[0] for SUM.
+ *   peer_bufs  host array of world_size DEVICE pointers: rank r's exchange buffer as
+ *              mapped in this process (peer_bufs[rank] is the local one).  Each buffer
+ *              is CTC_B200_EXCHANGE_BYTES long, symmetric-memory / IPC mapped by the
+ *              caller, and zero-filled before the first call.
+ *   seq        1, 2, 3, ... : the same value on every rank for the same step; steps
+ *              alternate between two slot sets, so a rank may run one step ahead.
+ *   status     workspace status word (the int at offset 0 of a workspace): a peer
+ *              that does not arrive within ~2 s sets CTC_B200_PEER_TIMEOUT there
+ *              instead of hanging the stream.
+ * world_size <= CTC_B200_MAX_PEERS.
+ */
+#define CTC_B200_MAX_PEERS 8
+#define CTC_B200_EXCHANGE_BYTES 256
+int ctc_b200_reduce_loss_allreduce_f32(const float* nll, const int32_t* tgt_lens, int N,
+                                       int reduction, void* const* peer_bufs, int rank,
+                                       int world_size, unsigned seq, float* out2, float* loss,
+                                       void* workspace, void* stream);
 
 /*
  * Device-side validation result of the launches that used `workspace` since it

@@ -12,7 +12,8 @@ import os
 _PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("CTC_B200_LIB") or os.path.join(_PKG, "torch_asr", "libctc_b200.so")
 
-OK, INVALID_ARGUMENT, WORKSPACE_TOO_SMALL, UNSUPPORTED, CUDA_ERROR, BAD_LABEL, BAD_LENGTH = range(7)
+OK, INVALID_ARGUMENT, WORKSPACE_TOO_SMALL, UNSUPPORTED, CUDA_ERROR, BAD_LABEL, BAD_LENGTH, PEER_TIMEOUT = range(8)
+MAX_PEERS, EXCHANGE_BYTES = 8, 256
 REDUCE_NONE, REDUCE_MEAN, REDUCE_SUM = 0, 1, 2
 
 # every symbol include/ctc_b200.h declares: name -> (restype, argtypes)
@@ -34,6 +35,7 @@ SYMBOLS = {
     "ctc_b200_fwd_bwd_range_f32": (_i, [_vp] * 5 + [_i] * 8 + [_vp] * 4 + [_sz, _vp]),
     "ctc_b200_scale_grad_f32": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
     "ctc_b200_reduce_loss_f32": (_i, [_vp, _vp, _i, _i, _vp, _vp, _vp]),
+    "ctc_b200_reduce_loss_allreduce_f32": (_i, [_vp, _vp, _i, _i, _vp, _i, _i, C.c_uint, _vp, _vp, _vp, _vp]),
     "ctc_b200_check_status": (_i, [_vp, _vp]),
     "ctc_b200_clear_status": (_i, [_vp, _vp]),
     "ctc_b200_session_create": (_i, [_i] * 6 + [C.POINTER(_vp)]),
@@ -204,3 +206,37 @@ class HostSession:
             self.close()
         except Exception:
             pass
+
+
+class PeerLossReducer:
+    """Loss reduction fused with the data-parallel job's only collective (include/ctc_b200.h:
+    ctc_b200_reduce_loss_allreduce_f32).  The 256-byte exchange buffer of every rank is allocated
+    as torch symmetric memory (P2P-mapped over NVLink / NVSwitch by the rendezvous); the kernel
+    stores this rank's (sum, count) pair into every peer's buffer and adds the pairs it receives.
+    Raises if the ranks cannot map each other's memory -- the caller then keeps the NCCL
+    all-reduce of the pair (`ctc/_ctc.py: global_loss`), which is the same collective."""
+
+    def __init__(self, group=None):
+        import torch
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm
+        self.lib = load()
+        group = group if group is not None else dist.group.WORLD
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        if self.world > MAX_PEERS:
+            raise RuntimeError(f"ctc_b200: fused loss all-reduce supports at most {MAX_PEERS} ranks")
+        self.buf = symm.empty(EXCHANGE_BYTES // 4, dtype=torch.float32, device=torch.device("cuda", torch.cuda.current_device()))
+        self.hdl = symm.rendezvous(self.buf, group=group)
+        self.buf.zero_()
+        torch.cuda.synchronize()
+        self.hdl.barrier()                       # every buffer is zeroed before anyone writes
+        ptrs = [int(p) for p in self.hdl.buffer_ptrs]
+        self.ptrs = (C.c_void_p * self.world)(*ptrs)
+        self.seq = 0
+
+    def __call__(self, nll, tgt_lens, N, reduction, out2, loss, workspace, stream):
+        self.seq += 1
+        _check(self.lib.ctc_b200_reduce_loss_allreduce_f32(
+            nll.data_ptr(), tgt_lens.data_ptr(), N, reduction, self.ptrs, self.rank, self.world,
+            self.seq, out2.data_ptr(), loss.data_ptr() if loss is not None else None,
+            workspace.data_ptr(), stream), "ctc_b200_reduce_loss_allreduce_f32")

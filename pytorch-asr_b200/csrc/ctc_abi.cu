@@ -414,6 +414,7 @@ int launch_fused(const float* acts, const int32_t* targets, const int32_t* tgt_o
 int status_from_bits(int bits) {
     if (bits & kStatusBadLabel) return CTC_B200_BAD_LABEL;
     if (bits & kStatusBadLength) return CTC_B200_BAD_LENGTH;
+    if (bits & kStatusPeerTimeout) return CTC_B200_PEER_TIMEOUT;
     return CTC_B200_OK;
 }
 
@@ -432,6 +433,7 @@ const char* ctc_b200_status_string(int status) {
         case CTC_B200_CUDA_ERROR: return "CUDA error";
         case CTC_B200_BAD_LABEL: return "target label outside [0, V)";
         case CTC_B200_BAD_LENGTH: return "input length > T or target length > S_max";
+        case CTC_B200_PEER_TIMEOUT: return "fused loss all-reduce: a peer did not arrive";
     }
     return "unknown status";
 }
@@ -517,6 +519,30 @@ int ctc_b200_reduce_loss_f32(const float* nll, const int32_t* tgt_lens, int N, i
     else
         ctc_reduce_loss_kernel<<<1, 256, 0, static_cast<cudaStream_t>(stream)>>>(
             nll, tgt_lens, N, reduction == CTC_B200_REDUCE_MEAN ? 1 : 2, out2, loss);
+    CTC_CUDA(cudaGetLastError());
+    return CTC_B200_OK;
+}
+
+int ctc_b200_reduce_loss_allreduce_f32(const float* nll, const int32_t* tgt_lens, int N, int reduction,
+                                       void* const* peer_bufs, int rank, int world_size, unsigned seq,
+                                       float* out2, float* loss, void* workspace, void* stream) {
+    if (!nll || !tgt_lens || !out2 || !peer_bufs || !workspace || N < 0 || world_size < 1 ||
+        world_size > CTC_B200_MAX_PEERS || rank < 0 || rank >= world_size || seq == 0)
+        return CTC_B200_INVALID_ARGUMENT;
+    PeerBufs pb;
+    for (int r = 0; r < CTC_B200_MAX_PEERS; ++r) {
+        void* q = r < world_size ? peer_bufs[r] : nullptr;
+        if (r < world_size && (!q || (reinterpret_cast<uintptr_t>(q) & 15))) return CTC_B200_INVALID_ARGUMENT;
+        pb.p[r] = static_cast<float4*>(q);
+    }
+    const int mode = reduction == CTC_B200_REDUCE_MEAN ? 1 : 2;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (t_allow_pdl && env_int("CTC_B200_PDL", 1))
+        CTC_CUDA(launch_pdl(ctc_reduce_loss_allreduce_kernel, dim3(1), dim3(256), (size_t)0, st, nll, tgt_lens,
+                            N, mode, pb, rank, world_size, seq, out2, loss, static_cast<int*>(workspace)));
+    else
+        ctc_reduce_loss_allreduce_kernel<<<1, 256, 0, st>>>(nll, tgt_lens, N, mode, pb, rank, world_size, seq,
+                                                            out2, loss, static_cast<int*>(workspace));
     CTC_CUDA(cudaGetLastError());
     return CTC_B200_OK;
 }

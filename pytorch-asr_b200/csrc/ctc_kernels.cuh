@@ -71,6 +71,7 @@ struct FusedParams {
 enum StatusBits : int {
     kStatusBadLabel = 1,     // a target label outside [0, V)
     kStatusBadLength = 2,    // input length outside [0, T] or target length < 0 / too long
+    kStatusPeerTimeout = 4,  // fused loss all-reduce: a peer's pair did not arrive in time
 };
 
 __device__ __forceinline__ float ex2f(float x) {
@@ -674,6 +675,76 @@ __global__ void ctc_reduce_loss_kernel(const float* __restrict__ nll,
         out[0] = (float)s;
         out[1] = (float)N;
         if (loss) loss[0] = (mode == 1) ? (float)(s / (double)max(N, 1)) : (float)s;
+    }
+}
+
+// ---------------------------------------------------------------------------
+// Loss reduction fused with the job's only collective: the (sum, count) pair goes straight into
+// every peer's exchange buffer (P2P stores over NVLink), the pairs addressed to this rank are
+// awaited and added in rank order.  Exchange buffer: slot[parity][rank] = {sum, seq, count, seq}.
+// ---------------------------------------------------------------------------
+struct PeerBufs { float4* p[8]; };
+
+__global__ void ctc_reduce_loss_allreduce_kernel(const float* __restrict__ nll,
+                                                 const int32_t* __restrict__ tgt_lens, int N, int mode,
+                                                 PeerBufs peers, int rank, int world, unsigned seq,
+                                                 float* __restrict__ out2, float* __restrict__ loss,
+                                                 int* __restrict__ status) {
+    __shared__ double s_part[32];
+    __shared__ float s_pair[2];
+    __shared__ float2 s_in[8];
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    double acc = 0.0;
+    for (int b = threadIdx.x; b < N; b += blockDim.x) {
+        double v = (double)nll[b];
+        if (mode == 1) v /= (double)max(tgt_lens[b], 1);
+        acc += v;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double s = 0.0;
+        for (int i = 0; i < (int)(blockDim.x >> 5); ++i) s += s_part[i];
+        s_pair[0] = (float)s;
+        s_pair[1] = (float)N;
+    }
+    __syncthreads();
+    const int par = (int)(seq & 1u);
+    if ((int)threadIdx.x < world) {
+        // one 16-byte store per peer, each 8-byte half carrying its own copy of the sequence number
+        // (8 bytes is the unit NVLink delivers atomically: the NCCL "LL" convention)
+        float4 v = make_float4(s_pair[0], __uint_as_float(seq), s_pair[1], __uint_as_float(seq));
+        float4* dst = peers.p[threadIdx.x] + par * 8 + rank;
+        asm volatile("st.volatile.global.v4.f32 [%0], {%1, %2, %3, %4};"
+                     ::"l"(dst), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+        __threadfence_system();
+        // the pair rank `threadIdx.x` addressed to me
+        const float4* src = peers.p[rank] + par * 8 + threadIdx.x;
+        float4 r;
+        unsigned spins = 0;
+        for (;;) {
+            asm volatile("ld.volatile.global.v4.f32 {%0, %1, %2, %3}, [%4];"
+                         : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(src) : "memory");
+            if (__float_as_uint(r.y) == seq && __float_as_uint(r.w) == seq) break;
+            if (++spins > (1u << 22)) {   // ~2 s: a missing peer must fail loudly, not hang the stream
+                atomicOr(status, kStatusPeerTimeout);
+                r.x = CUDART_NAN_F;
+                r.z = 0.f;
+                break;
+            }
+            __nanosleep(200);
+        }
+        s_in[threadIdx.x] = make_float2(r.x, r.z);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double s = 0.0, n = 0.0;
+        for (int r = 0; r < world; ++r) { s += (double)s_in[r].x; n += (double)s_in[r].y; }
+        out2[0] = (float)s;
+        out2[1] = (float)n;
+        if (loss) loss[0] = (mode == 1) ? (float)(s / fmax(n, 1.0)) : (float)s;
     }
 }
 
