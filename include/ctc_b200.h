@@ -167,6 +167,15 @@ int ctc_b200_reduce_loss_allreduce_f32(const float* nll, const int32_t* tgt_lens
                                        void* workspace, void* stream);
 
 /*
+ * Exchange-only form of the above for a pair that ctc_b200_reduce_loss_f32 already
+ * produced (the torch shim's forward): out2 (sum, count) is replaced in place by the
+ * global pair; `status_word` is a zero-initialised device int (or a workspace).
+ */
+int ctc_b200_allreduce_pair_f32(float* out2, int reduction, void* const* peer_bufs, int rank,
+                                int world_size, unsigned seq, float* loss, void* status_word,
+                                void* stream);
+
+/*
  * Device-side validation result of the launches that used `workspace` since it
  * was last cleared.  Synchronises `stream`.  Returns CTC_B200_OK,
  * CTC_B200_BAD_LABEL or CTC_B200_BAD_LENGTH.  ctc_b200_clear_status resets it

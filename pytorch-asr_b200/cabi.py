@@ -36,6 +36,7 @@ SYMBOLS = {
     "ctc_b200_scale_grad_f32": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
     "ctc_b200_reduce_loss_f32": (_i, [_vp, _vp, _i, _i, _vp, _vp, _vp]),
     "ctc_b200_reduce_loss_allreduce_f32": (_i, [_vp, _vp, _i, _i, _vp, _i, _i, C.c_uint, _vp, _vp, _vp, _vp]),
+    "ctc_b200_allreduce_pair_f32": (_i, [_vp, _i, _vp, _i, _i, C.c_uint, _vp, _vp, _vp]),
     "ctc_b200_check_status": (_i, [_vp, _vp]),
     "ctc_b200_clear_status": (_i, [_vp, _vp]),
     "ctc_b200_session_create": (_i, [_i] * 6 + [C.POINTER(_vp)]),
@@ -233,6 +234,19 @@ class PeerLossReducer:
         ptrs = [int(p) for p in self.hdl.buffer_ptrs]
         self.ptrs = (C.c_void_p * self.world)(*ptrs)
         self.seq = 0
+        self.status = torch.zeros(4, dtype=torch.int32, device=self.buf.device)
+
+    def exchange(self, out2, reduction, stream):
+        """In place: this rank's (sum, count) pair -> the global pair (exchange-only kernel)."""
+        self.seq += 1
+        _check(self.lib.ctc_b200_allreduce_pair_f32(
+            out2.data_ptr(), reduction, self.ptrs, self.rank, self.world, self.seq, None,
+            self.status.data_ptr(), stream), "ctc_b200_allreduce_pair_f32")
+
+    def check(self):
+        """Synchronises; raises if a peer did not arrive (CTC_B200_PEER_TIMEOUT)."""
+        if int(self.status[0].item()) & 4:
+            raise CtcB200Error(PEER_TIMEOUT, "fused loss all-reduce")
 
     def __call__(self, nll, tgt_lens, N, reduction, out2, loss, workspace, stream):
         self.seq += 1

@@ -523,10 +523,10 @@ int ctc_b200_reduce_loss_f32(const float* nll, const int32_t* tgt_lens, int N, i
     return CTC_B200_OK;
 }
 
-int ctc_b200_reduce_loss_allreduce_f32(const float* nll, const int32_t* tgt_lens, int N, int reduction,
-                                       void* const* peer_bufs, int rank, int world_size, unsigned seq,
-                                       float* out2, float* loss, void* workspace, void* stream) {
-    if (!nll || !tgt_lens || !out2 || !peer_bufs || !workspace || N < 0 || world_size < 1 ||
+static int launch_loss_allreduce(const float* nll, const int32_t* tgt_lens, int N, int reduction,
+                                 const float* pair_in, void* const* peer_bufs, int rank, int world_size,
+                                 unsigned seq, float* out2, float* loss, void* workspace, void* stream) {
+    if ((!pair_in && (!nll || !tgt_lens)) || !out2 || !peer_bufs || !workspace || N < 0 || world_size < 1 ||
         world_size > CTC_B200_MAX_PEERS || rank < 0 || rank >= world_size || seq == 0)
         return CTC_B200_INVALID_ARGUMENT;
     PeerBufs pb;
@@ -539,12 +539,25 @@ int ctc_b200_reduce_loss_allreduce_f32(const float* nll, const int32_t* tgt_lens
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (t_allow_pdl && env_int("CTC_B200_PDL", 1))
         CTC_CUDA(launch_pdl(ctc_reduce_loss_allreduce_kernel, dim3(1), dim3(256), (size_t)0, st, nll, tgt_lens,
-                            N, mode, pb, rank, world_size, seq, out2, loss, static_cast<int*>(workspace)));
+                            N, mode, pair_in, pb, rank, world_size, seq, out2, loss, static_cast<int*>(workspace)));
     else
-        ctc_reduce_loss_allreduce_kernel<<<1, 256, 0, st>>>(nll, tgt_lens, N, mode, pb, rank, world_size, seq,
-                                                            out2, loss, static_cast<int*>(workspace));
+        ctc_reduce_loss_allreduce_kernel<<<1, 256, 0, st>>>(nll, tgt_lens, N, mode, pair_in, pb, rank, world_size,
+                                                            seq, out2, loss, static_cast<int*>(workspace));
     CTC_CUDA(cudaGetLastError());
     return CTC_B200_OK;
+}
+
+int ctc_b200_reduce_loss_allreduce_f32(const float* nll, const int32_t* tgt_lens, int N, int reduction,
+                                       void* const* peer_bufs, int rank, int world_size, unsigned seq,
+                                       float* out2, float* loss, void* workspace, void* stream) {
+    return launch_loss_allreduce(nll, tgt_lens, N, reduction, nullptr, peer_bufs, rank, world_size, seq, out2,
+                                 loss, workspace, stream);
+}
+
+int ctc_b200_allreduce_pair_f32(float* out2, int reduction, void* const* peer_bufs, int rank, int world_size,
+                                unsigned seq, float* loss, void* status_word, void* stream) {
+    return launch_loss_allreduce(nullptr, nullptr, 0, reduction, out2, peer_bufs, rank, world_size, seq, out2,
+                                 loss, status_word, stream);
 }
 
 int ctc_b200_check_status(const void* workspace, void* stream) {

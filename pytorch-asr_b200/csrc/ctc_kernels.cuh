@@ -685,8 +685,10 @@ __global__ void ctc_reduce_loss_kernel(const float* __restrict__ nll,
 // ---------------------------------------------------------------------------
 struct PeerBufs { float4* p[8]; };
 
+// pair_in != nullptr: the local pair was already reduced (ctc_reduce_loss_kernel); exchange only.
 __global__ void ctc_reduce_loss_allreduce_kernel(const float* __restrict__ nll,
                                                  const int32_t* __restrict__ tgt_lens, int N, int mode,
+                                                 const float* pair_in,
                                                  PeerBufs peers, int rank, int world, unsigned seq,
                                                  float* __restrict__ out2, float* __restrict__ loss,
                                                  int* __restrict__ status) {
@@ -694,21 +696,25 @@ __global__ void ctc_reduce_loss_allreduce_kernel(const float* __restrict__ nll,
     __shared__ float s_pair[2];
     __shared__ float2 s_in[8];
     asm volatile("griddepcontrol.wait;" ::: "memory");
-    double acc = 0.0;
-    for (int b = threadIdx.x; b < N; b += blockDim.x) {
-        double v = (double)nll[b];
-        if (mode == 1) v /= (double)max(tgt_lens[b], 1);
-        acc += v;
-    }
+    if (pair_in != nullptr) {
+        if (threadIdx.x < 2) s_pair[threadIdx.x] = pair_in[threadIdx.x];
+    } else {
+        double acc = 0.0;
+        for (int b = threadIdx.x; b < N; b += blockDim.x) {
+            double v = (double)nll[b];
+            if (mode == 1) v /= (double)max(tgt_lens[b], 1);
+            acc += v;
+        }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-    if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = acc;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        double s = 0.0;
-        for (int i = 0; i < (int)(blockDim.x >> 5); ++i) s += s_part[i];
-        s_pair[0] = (float)s;
-        s_pair[1] = (float)N;
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = acc;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double s = 0.0;
+            for (int i = 0; i < (int)(blockDim.x >> 5); ++i) s += s_part[i];
+            s_pair[0] = (float)s;
+            s_pair[1] = (float)N;
+        }
     }
     __syncthreads();
     const int par = (int)(seq & 1u);

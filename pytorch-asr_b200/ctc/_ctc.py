@@ -55,6 +55,31 @@ def load_native():
     return mod
 
 
+_peer_reducers = {}   # process group -> cabi.PeerLossReducer, or None when peer memory is unavailable
+
+
+def _peer_reducer(group):
+    """The fused P2P exchange (cabi.PeerLossReducer) for an NCCL group on NVLink-connected GPUs; None
+    when it cannot be set up on every rank (then the same pair goes through the group's all-reduce).
+    CTC_B200_FUSED_COLLECTIVE=0 disables it."""
+    import torch.distributed as dist
+    if group in _peer_reducers:
+        return _peer_reducers[group]
+    red = None
+    if os.environ.get("CTC_B200_FUSED_COLLECTIVE", "1") != "0" and dist.get_backend(group) == "nccl":
+        try:
+            from .. import cabi
+            red = cabi.PeerLossReducer(group)
+        except Exception:  # noqa: BLE001  (no P2P mapping between the ranks' devices)
+            red = None
+        ok = torch.tensor([1 if red is not None else 0], device="cuda")
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)    # every rank takes the same path
+        if int(ok) == 0:
+            red = None
+    _peer_reducers[group] = red
+    return red
+
+
 def global_loss(out2, n_local, reduction, group):
     """Data-parallel reduction of the path: utterances are
     sharded over ranks with no data-path exchange; the only collective is ONE
@@ -64,7 +89,12 @@ def global_loss(out2, n_local, reduction, group):
     Returns (global loss, factor that turns the locally scaled gradient
     1/(N_local*S_b) into the global 1/(N_global*S_b); None for 'sum')."""
     import torch.distributed as dist
-    dist.all_reduce(out2, op=dist.ReduceOp.SUM, group=group)
+    red = _peer_reducer(group) if out2.is_cuda else None
+    if red is not None:
+        # ONE kernel: P2P stores of the pair into every peer's exchange buffer, rank-ordered sum
+        red.exchange(out2, reduction, torch.cuda.current_stream().cuda_stream)
+    else:
+        dist.all_reduce(out2, op=dist.ReduceOp.SUM, group=group)
     if reduction == 1:
         return out2[0] / out2[1], (n_local / out2[1]).reshape(())
     return out2[0].clone(), None

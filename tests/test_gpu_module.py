@@ -130,3 +130,55 @@ def test_no_grad_and_parts():
     ref = oracle.torch_reference(acts, tg, il, tl, reduction="mean")
     np.testing.assert_allclose(nll.cpu().numpy(), ref["nll"].numpy(), rtol=1e-5)
     assert abs(float(loss) - float(ref["loss"])) < 1e-5 * abs(float(ref["loss"]))
+
+
+def _dp_rank(rank, world, port, out):
+    import os
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        from pytorch_asr_b200.ctc import _ctc
+        acts, tg, il, tl = synth.make_batch(6 + 2 * rank, 90, 48, 18, seed=40 + rank)   # unequal shards
+        res = {}
+        for fused in ("1", "0"):
+            os.environ["CTC_B200_FUSED_COLLECTIVE"] = fused
+            _ctc._peer_reducers.clear()
+            x = acts.cuda().requires_grad_(True)
+            crit = CTCLoss(blank=0, reduction="mean", group=dist.group.WORLD)
+            for _ in range(3):                      # several steps: the exchange slots alternate
+                x.grad = None
+                loss = crit(x, tg, il, tl)
+                loss.backward()
+            red = _ctc._peer_reducers.get(dist.group.WORLD)
+            if red is not None:
+                red.check()
+            res[fused] = (float(loss), x.grad.cpu(), red is not None)
+        out[rank] = res
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs (gpurun --gpus 2)")
+def test_fused_collective_matches_nccl_world2():
+    """The loss reduction fused with the P2P exchange of the (sum, count) pair gives, on every rank,
+    the loss and gradient of the NCCL all-reduce path, and the global mean of one big batch."""
+    import torch.multiprocessing as mp
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_dp_rank, args=(2, 29533, out), nprocs=2, join=True)
+    (l0f, g0f, used0), (l0n, g0n, _) = out[0]["1"], out[0]["0"]
+    (l1f, g1f, used1), (l1n, g1n, _) = out[1]["1"], out[1]["0"]
+    assert used0 and used1                                  # peer memory was mapped: the fused kernel ran
+    assert l0f == l1f                                       # bit-identical on every rank
+    assert abs(l0f - l0n) <= 1e-6 * abs(l0n) and abs(l1f - l1n) <= 1e-6 * abs(l1n)
+    assert torch.allclose(g0f, g0n, rtol=1e-6, atol=1e-9) and torch.allclose(g1f, g1n, rtol=1e-6, atol=1e-9)
+    # one big batch on the CPU reference
+    parts = [synth.make_batch(6 + 2 * r, 90, 48, 18, seed=40 + r) for r in range(2)]
+    acts = torch.cat([p[0] for p in parts], 1)
+    tg = torch.cat([p[1] for p in parts]); il = torch.cat([p[2] for p in parts]); tl = torch.cat([p[3] for p in parts])
+    ref = oracle.torch_reference(acts, tg, il, tl, reduction="mean")
+    assert abs(l0f - float(ref["loss"])) <= 1e-5 * abs(float(ref["loss"]))
+    g_ref = ref["grad"]
+    assert (torch.cat([g0f, g1f], 1) - g_ref).abs().max() <= 1e-4
