@@ -373,6 +373,7 @@ int launch_fused(const float* acts, const int32_t* targets, const int32_t* tgt_o
         // consecutive CTAs already start on different SM sub-partitions)
         lp.rotate = (env_int("CTC_B200_ROTATE", 1) && (g.lNT / 32) % 4 == 0) ? num_sms() : 0;
         lp.redo = nullptr;
+        lp.utt_rot = std::max(0, std::min(env_int("CTC_B200_UTT_ROT", 0), utt_count - 1));
         int* fl = flags - 2 * (ptrdiff_t)utt_begin;   // kernels index flags by absolute utterance
         if (g.lR == 1) {
             switch (g.lP) {
@@ -391,6 +392,7 @@ int launch_fused(const float* acts, const int32_t* targets, const int32_t* tgt_o
         PipeParams pp;
         pp.f = prm;
         pp.redo = g.pipe == 2 ? flags - 2 * (ptrdiff_t)utt_begin : nullptr;
+        pp.utt_rot = 0;
         pp.R = g.R;
         pp.H = g.G;
         pp.NP = g.NP;

@@ -177,7 +177,11 @@ ctc_lin_kernel(const PipeParams pp, int* __restrict__ flags) {
     const int lane = threadIdx.x & 31;
     const int shift = pp.rotate > 0 ? (int)((blockIdx.x / pp.rotate) * R) % NW : 0;
     const int w = ((int)(threadIdx.x >> 5) + NW - shift) % NW;   // role (virtual) warp id
-    const int b = p.utt_begin + (blockIdx.x >> 1);
+    // which utterance this cluster works on: the batch is sorted by length (dataloader.py:53); utt_rot
+    // moves the longest utterances to the clusters whose SMs end up with the fewest co-resident CTAs
+    int b_local = (int)(blockIdx.x >> 1) + pp.utt_rot;
+    if (b_local >= (int)(gridDim.x >> 1)) b_local -= (int)(gridDim.x >> 1);
+    const int b = p.utt_begin + b_local;
     const bool rev = (blockIdx.x & 1) != 0;
     const int T = p.T, N = p.N, V = FIX ? 48 : p.V, blank = p.blank;
     // the V <= 60 emission-ring variants (YS = 80) are only launched with chunks of 4 frames

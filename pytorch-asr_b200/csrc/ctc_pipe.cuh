@@ -34,6 +34,7 @@ struct PipeParams {
     int D;         // fetch distance in chunks
     int rotate;    // CTAs per launch "layer" (= #SMs): co-resident CTAs rotate their warp roles
     const int* redo;  // [2 * N] or nullptr: run only utterances the linear kernel flagged (ctc_lin.cuh)
+    int utt_rot;      // linear kernel: cluster c works on utterance (c + utt_rot) mod n_utt (CTA placement)
 };
 
 // class-sorted label cell k lives at float index ypad(k) of the eY row: one float4 of

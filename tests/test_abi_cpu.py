@@ -33,8 +33,8 @@ def test_library_exports_every_declared_symbol():
 def test_version_and_status_strings():
     lib = cabi.load()
     assert lib.ctc_b200_version() >= 1000
-    seen = {lib.ctc_b200_status_string(i).decode() for i in range(7)}
-    assert len(seen) == 7 and "ok" in seen
+    seen = {lib.ctc_b200_status_string(i).decode() for i in range(8)}
+    assert len(seen) == 8 and "ok" in seen
     assert lib.ctc_b200_status_string(99).decode() == "unknown status"
 
 
@@ -69,6 +69,15 @@ def test_argument_validation_needs_no_device():
     assert lib.ctc_b200_scale_grad_f32(None, None, 0, 1, 1, 1, None) == cabi.INVALID_ARGUMENT
     assert lib.ctc_b200_reduce_loss_f32(None, None, 1, 1, None, None, None) == cabi.INVALID_ARGUMENT
     assert lib.ctc_b200_check_status(None, None) == cabi.INVALID_ARGUMENT
+    # fused loss all-reduce: null buffers, rank outside the world, more than 8 peers, sequence number 0
+    ptrs = (C.c_void_p * 2)(16, 32)
+    one = C.c_void_p(16)
+    f = lib.ctc_b200_reduce_loss_allreduce_f32
+    assert f(None, None, 1, 1, ptrs, 0, 2, 1, one, None, one, None) == cabi.INVALID_ARGUMENT
+    assert f(one, one, 1, 1, ptrs, 2, 2, 1, one, None, one, None) == cabi.INVALID_ARGUMENT
+    assert f(one, one, 1, 1, ptrs, 0, cabi.MAX_PEERS + 1, 1, one, None, one, None) == cabi.INVALID_ARGUMENT
+    assert f(one, one, 1, 1, ptrs, 0, 2, 0, one, None, one, None) == cabi.INVALID_ARGUMENT
+    assert lib.ctc_b200_allreduce_pair_f32(None, 1, ptrs, 0, 2, 1, None, one, None) == cabi.INVALID_ARGUMENT
 
 
 def test_module_fails_loudly_without_cuda():
