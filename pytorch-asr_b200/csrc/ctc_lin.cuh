@@ -61,6 +61,10 @@ constexpr int kLinTarget = CTC_LIN_TGT; // a thread's largest cell is renormalis
 constexpr int kLinInMax = CTC_LIN_INMAX; // what the neighbour hands up stays below 2^96 in my scale
 constexpr int kLinFresh = -(1 << 24);   // exponent of a thread that has not received anything yet
 constexpr int kLinHmax = 127 - (kLinInMax + 7) - 4;   // largest exponent applied to the partner cell alone (p * 2^h finite)
+// smallest exponent applied to the partner cell alone; a more negative h (both sides far ABOVE 1 in their
+// threads' scales: a thread that has just received its first value sits near 2^kLinInMax until its next
+// renormalisation) puts the rest onto the product as well instead of flushing 2^h to zero
+constexpr int kLinHmin = -100;
 constexpr float kMassTol = 3.0e-5f;     // |sum of occupancies - 1| per frame
 constexpr int kLinNone = -(1 << 28);    // exponent of a term that is exactly zero
 constexpr float kQ31 = 2147483648.0f;   // label occupancies are accumulated as Q1.31 fixed point
@@ -714,11 +718,11 @@ ctc_lin_kernel(const PipeParams pp, int* __restrict__ flags) {
                         // p * 2^h cannot overflow); a larger h -- cells far below their thread's maximum on
                         // both sides, steep lattices -- puts the rest onto the product (a factor of 1 otherwise).
                         const int hb = off + ob - E0, hy = off + oy - E0;
-                        const int hbc = min(hb, kLinHmax), hyc = min(hy, kLinHmax);
+                        const int hbc = max(min(hb, kLinHmax), kLinHmin), hyc = max(min(hy, kLinHmax), kLinHmin);
                         const float sb = pow2c(hbc) * rz;
                         const float sq = sb * kQ31;
                         const float sy = hasX1 ? pow2c(hyc) * (rz * kQ31) : 0.f;
-                        const float rb = pow2c(hb - hbc), ry = pow2c(hy - hyc);   // 1 unless h > kLinHmax
+                        const float rb = pow2c(hb - hbc), ry = pow2c(hy - hyc);   // 1 unless h is outside [kLinHmin, kLinHmax]
 #pragma unroll
                         for (int q = 0; q < P; ++q) {
                             bsum += (aB[q] * (pb[q] * sb)) * rb;
@@ -766,8 +770,8 @@ ctc_lin_kernel(const PipeParams pp, int* __restrict__ flags) {
                     // occupancy = a * p~ * 2^(off + o - E0) / z (see combine_rd for the exponent split)
                     const int hbA = offA + obA - E0, hyA = offA + olA - E0;
                     const int hbB = offB + obB - E0, hyB = offB + olB - E0;
-                    const int cbA = min(hbA, kLinHmax), cyA = min(hyA, kLinHmax);
-                    const int cbB = min(hbB, kLinHmax), cyB = min(hyB, kLinHmax);
+                    const int cbA = max(min(hbA, kLinHmax), kLinHmin), cyA = max(min(hyA, kLinHmax), kLinHmin);
+                    const int cbB = max(min(hbB, kLinHmax), kLinHmin), cyB = max(min(hyB, kLinHmax), kLinHmin);
                     const float sbA = winA ? pow2c(cbA) * rz : 0.f, sbB = winB ? pow2c(cbB) * rz : 0.f;
                     const float syA = (winA && hasX1) ? pow2c(cyA) * (rz * kQ31) : 0.f;
                     const float syB = (winB && hasX1) ? pow2c(cyB) * (rz * kQ31) : 0.f;
