@@ -212,6 +212,30 @@ def test_peaky_full_size_no_fallback_needed():
                   grad_atol=grad_atol_fp64(1000), what="C2 peaky slice vs fp64")
 
 
+@pytest.mark.parametrize("seed,utt", [(1, 216), (17, 13)])
+def test_band_edge_cell_after_first_value_regression(seed, utt):
+    """Regression (r01 v11): the leading-edge cell of the partner's sweep, in the first row after the
+    renormalisation that seeds a thread (t = 4, or 8 frames from the end), was flushed to zero by the
+    combine pass when the joint exponent fell below -126; the posterior-mass check then sent the
+    utterance to the log-domain fallback.  These two random C2-shaped batches each held one such
+    utterance: no utterance may be flagged now, and the frame in question must match the fp64 oracle."""
+    acts, tg, il, tl = synth.make_batch(256, 1000, 48, 200, seed=seed)
+    prob = cabi.DeviceProblem(acts, tg, il, tl, reduction="sum")
+    prob.run()
+    torch.cuda.synchronize()
+    prob.check_status()
+    assert cabi.geometry(1000, 256, 48, prob.S_max)["kernel"] == 2
+    flags = prob.ws[256:256 + 8 * 256].view(torch.int32).cpu()
+    assert int(flags.abs().sum()) == 0
+    offs = torch.cat([torch.zeros(1, dtype=torch.int64), tl.long().cumsum(0)])
+    sub = (acts[:, utt:utt + 1].contiguous(), tg[offs[utt]:offs[utt + 1]].contiguous(),
+           il[utt:utt + 1].contiguous(), tl[utt:utt + 1].contiguous())
+    orc = oracle.ctc_oracle_f64(sub[0].numpy(), sub[1].numpy(), sub[2].numpy(), sub[3].numpy())
+    g = prob.grad[:, utt:utt + 1].cpu().numpy()
+    assert np.abs(g - orc["grad"]).max() <= 1e-5          # was 3.9e-5 / 8.4e-5 in one frame
+    assert np.abs(g.sum(-1)).max() <= 1e-5                # posterior mass of every frame
+
+
 def test_forward_only_matches():
     acts, tg, il, tl = synth.make_batch(5, 90, 48, 18, seed=5, repeat_frac=0.2)
     nll_g, _, _ = run_engine(acts, tg, il, tl)
