@@ -78,9 +78,6 @@ constexpr float kQ31 = 2147483648.0f;   // label occupancies are accumulated as 
 #ifndef CTC_LIN_TC4
 #define CTC_LIN_TC4 1     // chunk length as a compile-time constant in the YS = 80 variants
 #endif
-#ifndef CTC_LIN_ISS_COMB
-#define CTC_LIN_ISS_COMB 0   // 1: the first combine warp (idle in the first half) requests the logits rows
-#endif
 #ifndef CTC_LIN_PD
 #define CTC_LIN_PD 2
 #endif
@@ -568,14 +565,6 @@ ctc_lin_kernel(const PipeParams pp, int* __restrict__ flags) {
             }
         };
         Ring ring_part(NS), iss_p(NS);
-#if CTC_LIN_ISS_COMB
-        Ring iss_y(NL);
-        const bool iss_y_on = iss_part && wide_rows && lane == 0;
-        for (int k = 0; k <= kLinYDist; ++k) {    // prologue: logits of chunks 0..kLinYDist
-            if (iss_y_on && k < nch) issue_logits_tma(k, iss_y.slot);
-            iss_y.advance();
-        }
-#endif
         int a_buf = 0, o_buf = 0;
         // loop-invariant kernel parameters live in registers (each re-read from the constant bank
         // would be an exposed latency in front of a branch)
@@ -590,10 +579,6 @@ ctc_lin_kernel(const PipeParams pp, int* __restrict__ flags) {
                 if (iss_part) issue_partner(it + kLinPDist - 2, iss_p.slot);
                 iss_p.advance();
             }
-#if CTC_LIN_ISS_COMB
-            if (iss_y_on && it + kLinYDist + 1 < nch_i) issue_logits_tma(it + kLinYDist + 1, iss_y.slot);
-            iss_y.advance();
-#endif
             const int k = it - 2;
             if (k >= n1_i && k < nch_i) {
                 int tt0, rows;
@@ -1215,7 +1200,7 @@ ctc_lin_kernel(const PipeParams pp, int* __restrict__ flags) {
         // ---- the helper schedule -----------------------------------------------------------
         // Iteration `it`:  SOFT 0 requests the logits of chunk it + kLinYDist + 1; SOFT: softmax of
         // chunk it; GRAD: gradient rows of chunk it-3 (REC runs chunk it-1, COMB chunk it-2).
-        const bool iss_acts = isA && ha == 0 && !(CTC_LIN_ISS_COMB && wide_rows);
+        const bool iss_acts = isA && ha == 0;
         const bool do_sm = isA && ha * FA < TC, do_gr = isB && hb * FB < TC && want_grad;
         Ring iss_a(NL), sm_a(NL), gr_a(NL);
         int gr_o = 0;
