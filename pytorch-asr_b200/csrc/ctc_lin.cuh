@@ -41,7 +41,14 @@
 //                         zero fill of rows t >= T_b   (H = 1: ONE helper warp is SOFT and GRAD)
 // One CTA barrier per chunk of TC frames hands the rings over: in iteration `it` SOFT works on
 // chunk it, REC on chunk it-1, COMB on chunk it-2, GRAD on chunk it-3.  C2 (B=256, T=1000, V=48):
-// 4 warps per CTA (REC, 2 x COMB, helper), 4 CTAs per SM, 125 registers.
+// 4 warps per CTA (REC, 2 x COMB, helper), 4 CTAs per SM, 128 registers; this shape class (V = 48, one
+// helper, two combine groups, chunks of 4 frames) has its own instantiation with all of these as
+// compile-time constants (FIX).  Wide vocabularies (V > 256): two SOFT and two GRAD warps, a warp per
+// frame, logits rows by ONE TMA bulk copy per row, softmax / gradient rows held in registers.
+//
+// Which utterance a cluster works on: (blockIdx.x / 2 + utt_rot) mod n_utt.  The host rotates the
+// (length-sorted) batch by whole launch layers so that the longest utterances land on the SM pairs that
+// end up with the fewest co-resident CTAs (ctc_abi.cu).
 //
 // Alignment trick: the alpha CTA shifts its lattice by delta = (P-1-S) mod P slots, so that the
 // P partner cells a thread needs are exactly ONE partner thread's P cells, reversed: 128-bit
