@@ -45,6 +45,22 @@ typedef enum ctc_b200_status {
     CTC_B200_PEER_TIMEOUT = 7        /* fused loss all-reduce: a peer's pair did not arrive */
 } ctc_b200_status;
 
+/* Memory layout of `acts` and `grad` (both always use the same one). */
+typedef enum ctc_b200_layout {
+    CTC_B200_LAYOUT_TNV = 0,         /* [T,N,V] time-major: what trainer.py:418 hands to the loss */
+    CTC_B200_LAYOUT_NTV = 1          /* [N,T,V] batch-major: what the network emits (network.py:380,393-396);
+                                        folds trainer.py:418's transpose(0,1).contiguous() and its backward */
+} ctc_b200_layout;
+
+/* Options of the extended calls; NULL means all defaults (time-major, no clamp). */
+typedef struct ctc_b200_options {
+    int layout;                      /* ctc_b200_layout */
+    int use_clamp;                   /* != 0: fused Hardtanh(clamp_min, clamp_max) in front of the log_softmax
+                                        (network.py:370 nn.Hardtanh(-50, 50)); the gradient is then with respect to
+                                        the RAW (un-clamped) logits: 0 where a logit is outside (clamp_min, clamp_max) */
+    float clamp_min, clamp_max;
+} ctc_b200_options;
+
 typedef enum ctc_b200_reduction {
     CTC_B200_REDUCE_NONE = 0,
     CTC_B200_REDUCE_MEAN = 1,        /* mean_b( nll_b / max(S_b,1) )  -- trainer.py:153 */
@@ -65,7 +81,9 @@ const char* ctc_b200_last_cuda_error(void);
  * DESIGN.md); also what ctc_b200_workspace_bytes is derived from.
  */
 typedef struct ctc_b200_geometry {
-    int kernel;                /* 1: warp-specialised kernel, 0: generic kernel */
+    int kernel;                /* 2: linear-domain warp-specialised kernel (ctc_lin_kernel) with a log-domain
+                                  per-utterance fallback pass, 1: log-domain warp-specialised kernel
+                                  (ctc_pipe_kernel), 0: generic log-domain kernel (ctc_fused_kernel) */
     int rec_warps;             /* warps per CTA running the lattice recursion */
     int grad_warps;            /* helper warps per CTA: TMA producer, softmax, gradient rows (0: generic kernel) */
     int pairs_per_thread;      /* lattice (blank,label) cell pairs per thread */
@@ -74,9 +92,16 @@ typedef struct ctc_b200_geometry {
     int row_stride;            /* floats per stored lattice row */
     int smem_bytes;            /* dynamic shared memory per CTA */
     size_t workspace_bytes;    /* for n_utt utterances */
+    int variant;               /* which template instantiation of `kernel` is launched (ctc_b200_variant_name) */
+    int fallback_kernel;       /* kernel == 2: the log-domain kernel that redoes flagged utterances (1 or 0); else -1 */
+    int comb_groups;           /* kernel == 2: combine warps per recursion warp */
+    int persistent;            /* kernel == 2: 1 when n_utt exceeds the co-resident clusters and the launch pulls
+                                  utterances from a device-side queue (needs a CUDA device to decide; 0 without one) */
 } ctc_b200_geometry;
 
 int ctc_b200_get_geometry(int T, int n_utt, int V, int S_max, ctc_b200_geometry* out);
+/* "ctc_lin_kernel<8,1,80,128,4,FIX>" ...; static string, "?" for an unknown id. */
+const char* ctc_b200_variant_name(int kernel, int variant);
 
 /* Bytes of device workspace ctc_b200_fwd_bwd_f32 needs for (T, N, V, S_max). */
 int ctc_b200_workspace_bytes(int T, int N, int V, int S_max, size_t* bytes);
@@ -122,12 +147,26 @@ int ctc_b200_fwd_bwd_range_f32(const float* acts, const int32_t* targets,
                                void* workspace, size_t workspace_bytes, void* stream);
 
 /*
+ * The same with options: batch-major [N,T,V] logits / gradient (folds the
+ * transpose + copy of trainer.py:418 and of its backward) and the fused Hardtanh of the FC head
+ * (section 8(f)2, network.py:367-375).  opt == NULL: ctc_b200_fwd_bwd_range_f32.
+ */
+int ctc_b200_fwd_bwd_ex_f32(const float* acts, const int32_t* targets, const int32_t* tgt_offsets,
+                            const int32_t* in_lens, const int32_t* tgt_lens, int T, int N, int V,
+                            int S_max, int blank, int zero_infinity, int utt_begin, int utt_count,
+                            float* nll, float* grad, const float* grad_scale, void* workspace,
+                            size_t workspace_bytes, const ctc_b200_options* opt, void* stream);
+
+/*
  * grad[t,b,:] *= scale[per_utt ? b : 0].  Applies autograd's grad_output
  * (trainer.py:429 loss.mul_(0); AMP loss scale, trainer.py:435-436).  Factors
  * equal to 1 are detected on the device and cost no memory traffic.
  */
 int ctc_b200_scale_grad_f32(float* grad, const float* scale, int per_utt, int T, int N, int V,
                             void* stream);
+/* the same for a gradient in `layout` (ctc_b200_layout) */
+int ctc_b200_scale_grad_ex_f32(float* grad, const float* scale, int per_utt, int T, int N, int V,
+                               int layout, void* stream);
 
 /*
  * out2[0] = sum_b nll_b / max(S_b,1) (MEAN) or sum_b nll_b (SUM); out2[1] = N.
@@ -138,6 +177,27 @@ int ctc_b200_scale_grad_f32(float* grad, const float* scale, int per_utt, int T,
  */
 int ctc_b200_reduce_loss_f32(const float* nll, const int32_t* tgt_lens, int N, int reduction,
                              float* out2, float* loss, void* stream);
+
+/*
+ * Loss reduction PLUS the trainer's post-loss host checks (SURVEY.md section 8(f)3,
+ * trainer.py:423-430) in one launch, so that the three device->host syncs of an iteration
+ * (isnan, .item() == +-inf, frame_lens < 2 * label_lens) become ONE 16-byte read of `result`:
+ *   result[0]  the reduced loss (as ctc_b200_reduce_loss_f32 writes to `loss`); 0 when
+ *              zero_on_short applies
+ *   result[1]  flags: the sum of the CTC_B200_FLAG_* bits that apply, as a float VALUE (0 ... 7)
+ *   result[2]  the factor the reference applies to the loss before backward: 0 if zero_on_short and
+ *              some T_b < 2 * S_b (trainer.py:427-429 loss.mul_(0)), else 1.  Feed it to
+ *              ctc_b200_scale_grad_f32 as the scale: no host round trip.
+ *   result[3]  number of utterances with T_b < 2 * S_b
+ * in_lens may be NULL (then CTC_B200_FLAG_SHORT is never set).  out2 as in ctc_b200_reduce_loss_f32;
+ * `loss` (may be NULL) receives a second copy of result[0].
+ */
+#define CTC_B200_FLAG_NAN 1        /* the reduced loss is NaN               (trainer.py:423 torch.isnan) */
+#define CTC_B200_FLAG_INF 2        /* the reduced loss is +-inf             (trainer.py:423 loss.item() == inf) */
+#define CTC_B200_FLAG_SHORT 4      /* some utterance has T_b < 2 * S_b      (trainer.py:427) */
+int ctc_b200_reduce_loss_status_f32(const float* nll, const int32_t* in_lens, const int32_t* tgt_lens,
+                                    int N, int reduction, int zero_on_short, float* out2,
+                                    float* loss, float* result4, void* stream);
 
 /*
  * The loss reduction FUSED with the data-parallel job's only collective (SURVEY.md
@@ -155,8 +215,10 @@ int ctc_b200_reduce_loss_f32(const float* nll, const int32_t* tgt_lens, int N, i
  *   seq        1, 2, 3, ... : the same value on every rank for the same step; steps
  *              alternate between two slot sets, so a rank may run one step ahead.
  *   status     workspace status word (the int at offset 0 of a workspace): a peer
- *              that does not arrive within ~2 s sets CTC_B200_PEER_TIMEOUT there
- *              instead of hanging the stream.
+ *              that does not arrive within the timeout sets CTC_B200_PEER_TIMEOUT there
+ *              (and the result is NaN) instead of hanging the stream.  The timeout is
+ *              ctc_b200_set_peer_timeout_ms (default 600 000 ms, the order of a process
+ *              group's own timeout; 0 = wait for ever).
  * world_size <= CTC_B200_MAX_PEERS.
  */
 #define CTC_B200_MAX_PEERS 8
@@ -174,6 +236,31 @@ int ctc_b200_reduce_loss_allreduce_f32(const float* nll, const int32_t* tgt_lens
 int ctc_b200_allreduce_pair_f32(float* out2, int reduction, void* const* peer_bufs, int rank,
                                 int world_size, unsigned seq, float* loss, void* status_word,
                                 void* stream);
+/* Process-wide timeout of the two calls above, in milliseconds (0: no timeout).  Returns the old value. */
+long long ctc_b200_set_peer_timeout_ms(long long ms);
+
+/* ------------------------------------------------------------------------
+ * Greedy CTC decode + label-error count for `validate`:
+ * replaces the per-utterance Python loops of trainer.py:450-463 (unit_validate:
+ * onehot2int = arg-max, misc.py:44-51; remove_duplicates(blank=0), misc.py:78-84) and
+ * trainer.py:336-343 (edit_distance, Levenshtein with unit costs).
+ *
+ *  acts       device fp32 logits or log-probs in `layout` (unit_validate uses the network's
+ *             own [N,T,V] output: CTC_B200_LAYOUT_NTV); arg-max takes the LOWEST index on ties
+ *  in_lens    device int32 [N]; frames t >= in_lens[b] are not read
+ *  targets / tgt_offsets / tgt_lens   device int32, as in ctc_b200_fwd_bwd_f32
+ *  hyp        device int32 [N,T] out: row b holds the hyp_len[b] decoded labels
+ *  hyp_len    device int32 [N] out
+ *  dist       device int32 [N] out: edit distance(hyp_b, target_b)
+ *  totals     device int64 [2] out: {sum_b dist[b], sum_b tgt_lens[b]}; LER % = 100 * [0] / [1]
+ *             (trainer.py:301-304)
+ * Needs no workspace (hyp doubles as the arg-max buffer).  targets == NULL: decode only.
+ * ------------------------------------------------------------------------ */
+int ctc_b200_greedy_decode_ler_i32(const float* acts, int T, int N, int V, int layout,
+                                   const int32_t* in_lens, const int32_t* targets,
+                                   const int32_t* tgt_offsets, const int32_t* tgt_lens, int blank,
+                                   int32_t* hyp, int32_t* hyp_len, int32_t* dist,
+                                   long long* totals, void* stream);
 
 /*
  * Device-side validation result of the launches that used `workspace` since it

@@ -10,7 +10,8 @@ the same Python surface:
 
 Layout: `csrc/` kernels + C ABI + torch shim, `torch_asr/` the built native
 modules (`torch_asr._ctc_lib`, named like the reference's `torch_asr._latgen_lib`),
-`ctc/` the nn.Module / autograd surface, `cabi.py` a ctypes view of the C ABI,
+`ctc/` the nn.Module / autograd surface, `decode.py` greedy decode + LER for `validate`,
+`cabi.py` a ctypes view of the C ABI,
 `synth.py` the synthetic workloads BASELINE.json names.
 
 There is no CPU fallback: using the engine without its CUDA extension, or on a
@@ -19,3 +20,4 @@ non-CUDA tensor, raises.
 from .ctc import CTCLoss, ctc_loss, ctc_loss_parts  # noqa: F401
 
 __all__ = ["CTCLoss", "ctc_loss", "ctc_loss_parts"]
+# `pytorch_asr_b200.decode`: greedy decode + label error rate for `validate` (imported on demand)

@@ -1,12 +1,10 @@
 // ctc_abi.cu -- the extern "C" boundary declared in include/ctc_b200.h.
 //
-// Host-side launch logic for the kernels in ctc_kernels.cuh plus the
-// host-buffer session.  No torch types here: this file builds into
-// libctc_b200.so with nvcc alone and is what a non-Python caller links.
-#include "ctc_kernels.cuh"
-#include "ctc_pipe.cuh"
-#include "ctc_lin.cuh"
-#include "../../include/ctc_b200.h"
+// Host-side geometry choice and launch logic, the small kernels (ctc_small.cuh) and the
+// host-buffer session.  No torch types here: libctc_b200.so is built with nvcc alone
+// (ctc_abi.cu + ctc_launch_lin.cu + ctc_launch_log.cu + ctc_decode.cu) and is what a non-Python caller links.
+#include "ctc_launch.h"
+#include "ctc_small.cuh"
 
 #include <algorithm>
 #include <cstdio>
@@ -17,17 +15,65 @@
 
 using namespace ctcb200;
 
+namespace ctcb200 {
+
+thread_local cudaError_t g_last_cuda = cudaSuccess;
+
+cudaError_t last_cuda_error_set(cudaError_t e) {
+    if (e != cudaSuccess) g_last_cuda = e;
+    return e;
+}
+
+const Env& env() {
+    static const Env e;   // thread-safe one-time initialisation
+    return e;
+}
+
+int current_device() {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) { cudaGetLastError(); dev = 0; }
+    return dev;
+}
+
+int num_sms() {
+    static std::atomic<int> n[kMaxDevices];
+    const int dev = current_device();
+    if (dev < 0 || dev >= kMaxDevices) return 148;
+    int v = n[dev].load(std::memory_order_relaxed);
+    if (v <= 0) {
+        if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) {
+            cudaGetLastError();
+            return 148;   // B200 (no device to ask: the geometry query still answers)
+        }
+        n[dev].store(v, std::memory_order_relaxed);
+    }
+    return v;
+}
+
+cudaError_t ensure_smem(const void* func, SmemMark& mark, int bytes) {
+    const int dev = current_device();
+    if (dev >= 0 && dev < kMaxDevices && mark.v[dev].load(std::memory_order_acquire) >= bytes) return cudaSuccess;
+    cudaError_t e = cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e != cudaSuccess) return last_cuda_error_set(e);
+    if (dev >= 0 && dev < kMaxDevices) {
+        int old = mark.v[dev].load(std::memory_order_relaxed);
+        while (old < bytes && !mark.v[dev].compare_exchange_weak(old, bytes, std::memory_order_release)) {}
+    }
+    return cudaSuccess;
+}
+
+}  // namespace ctcb200
+
 namespace {
 
-constexpr int kHeaderBytes = 256;          // workspace header: device status word
+constexpr int kHeaderBytes = 256;          // workspace header: [0] status word, [16] utterance queue (2 ints)
+constexpr int kQueueOffset = 16;
 constexpr int kMaxSmemBytes = 200 * 1024;  // leave room under the 227 KB per-CTA limit
 constexpr int kMinThreads = 32;
 constexpr int kNumSmsHint = 148;           // B200; only shapes the shared-memory budget heuristic
 
-thread_local cudaError_t g_last_cuda = cudaSuccess;
-
 inline int cuda_fail(cudaError_t e) {
-    g_last_cuda = e;
+    last_cuda_error_set(e);
     return CTC_B200_CUDA_ERROR;
 }
 #define CTC_CUDA(call)                                  \
@@ -36,59 +82,18 @@ inline int cuda_fail(cudaError_t e) {
         if (e__ != cudaSuccess) return cuda_fail(e__);  \
     } while (0)
 
-// Programmatic dependent launch for the small kernels that follow the fused kernel (its fallback pass
-// and the loss reduction): the launch is set up while the previous kernel drains; the kernels
-// themselves wait for it with griddepcontrol.wait before their first global-memory read.
 thread_local bool t_allow_pdl = true;   // the host-buffer session launches without it (measured slower there)
 
-template <typename... KArgs, typename... Args>
-cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
-                       Args... args) {
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = grid;
-    cfg.blockDim = block;
-    cfg.dynamicSmemBytes = smem;
-    cfg.stream = st;
-    cudaLaunchAttribute at[1];
-    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    at[0].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = at;
-    cfg.numAttrs = 1;
-    return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
-}
-
-struct Geometry {
-    int pipe;       // 2: linear-domain kernel (ctc_lin.cuh) with the log-domain pipe kernel as its
-                    //    per-utterance fallback, 1: log-domain pipe kernel (ctc_pipe.cuh),
-                    // 0: generic kernel (ctc_kernels.cuh)
-    int P, NT, W, NP, chunk, RS, smem;
-    int R, G, D;    // pipe only: recursion / gradient warps, fetch distance in chunks
-    size_t lat_utt_stride;  // floats
-    // pipe == 2: geometry of the linear kernel (the fields above describe the fallback)
-    int lP, lNT, lNP, lchunk, lRS, lsmem, lR, lH, lD, lYS;
-    size_t l_lat_utt_stride;
-    size_t lattice_floats_per_utt() const { return pipe == 2 ? std::max(lat_utt_stride, l_lat_utt_stride) : lat_utt_stride; }
-};
-
 inline size_t flag_bytes(int n_utt) { return ((size_t)std::max(n_utt, 1) * 8 + 255) / 256 * 256; }
-// softmax rows the linear kernel saves for the partner CTA's second half: [n_utt][T][V] fp32
-inline size_t ysave_bytes(int T, int V, int n_utt) {
-    return ((size_t)std::max(n_utt, 1) * (size_t)std::max(T, 1) * (size_t)V * 4 + 255) / 256 * 256;
-}
-
-int env_int(const char* name, int dflt) {
-    const char* e = std::getenv(name);
-    return e ? std::atoi(e) : dflt;
-}
 
 // Generic kernel: every warp does recursion + its share of softmax / gradient rows.
 int pick_generic(int T, int V, int pairs, Geometry* g) {
     int P = pairs > 1024 ? (pairs > 2048 ? 4 : 2) : 1;
-    const int q = env_int("CTC_B200_PAIRS", 0);  // tuning override (1, 2 or 4)
+    const int q = env().pairs;  // tuning override (1, 2 or 4)
     if ((q == 1 || q == 2 || q == 4) && (pairs + q - 1) / q <= 1024) P = q;
     int NT = ((pairs + P - 1) / P + 31) / 32 * 32;
     NT = std::max(NT, P == 1 ? 128 : kMinThreads);
-    g->pipe = 0;
+    g->base = 0;
     g->P = P;
     g->NT = NT;
     g->W = NT / 32;
@@ -112,21 +117,21 @@ int pick_generic(int T, int V, int pairs, Geometry* g) {
     return CTC_B200_OK;
 }
 
-// Warp-specialised kernel: R recursion warps (P pairs per thread) + 1 load warp + G gradient warps.
+// Warp-specialised log-domain kernel: R recursion warps (P pairs per thread) + H helper warps.
 bool pick_pipe(int T, int V, int pairs, int n_utt, Geometry* g) {
     if (V % 4) return false;   // TMA row copies need 16-byte aligned logit rows
     int P = pairs > 64 ? 4 : (pairs > 32 ? 2 : 1);
-    const int q = env_int("CTC_B200_PAIRS", 0);
+    const int q = env().pairs;
     if (q == 1 || q == 2 || q == 4) P = q;
     const int R = (pairs + 32 * P - 1) / (32 * P);
-    int H = env_int("CTC_B200_HELPERS", 0);
+    int H = env().helpers;
     if (H < 1 || H > 8) H = pairs > 700 ? 4 : 2;
     const int NT = 32 * (R + H);
     if (NT > 1024) return false;
     // (chunk, fetch distance) candidates.  All CTAs should be co-resident (one wave: the
     // kernel is as long as its longest utterance), so the shared-memory budget per CTA is
     // an SM's 227 KB divided by the CTAs per SM the launch needs (at most 4).
-    const int tc_env = env_int("CTC_B200_CHUNK", 0), d_env = env_int("CTC_B200_DIST", 0);
+    const int tc_env = env().chunk, d_env = env().dist;
     const int cand[4][2] = {{4, 1}, {2, 2}, {2, 1}, {1, 1}};
     const int RS = 2 * 32 * P * R + (R + 3) / 4 * 4;
     for (int pass = 0; pass < 2; ++pass) {
@@ -138,7 +143,7 @@ bool pick_pipe(int T, int V, int pairs, int n_utt, Geometry* g) {
             const int need = std::max(1, std::min(4, (2 * std::max(n_utt, 1) + kNumSmsHint - 1) / kNumSmsHint));
             const int limit = pass == 0 ? std::min(kMaxSmemBytes, 227 * 1024 / need - 2048) : kMaxSmemBytes;
             if (lay.total > limit) continue;
-            g->pipe = 1;
+            g->base = 1;
             g->P = P;
             g->NT = NT;
             g->W = NT / 32;
@@ -156,186 +161,93 @@ bool pick_pipe(int T, int V, int pairs, int n_utt, Geometry* g) {
     return false;
 }
 
-// Linear-domain kernel: R recursion warps with P pairs per thread in registers (P = 8 covers 256
-// lattice slots per warp), R combine warps, H softmax / gradient warps.  Needs S_max + P <= 32 * P * R
-// slots (alignment shift).
+// Linear-domain kernel: R recursion warps with 8 pairs per thread in registers (256 lattice slots per
+// warp), 2 (or 1) combine warps per recursion warp, H softmax / gradient warps.  Needs S_max + 8 <=
+// 256 * R slots (alignment shift).  Rows that are not 16-byte aligned (V % 4 != 0: the reference's V = 177,
+// params.py:27) use the run-time-stride variants with 4-byte copies.
 bool pick_lin(int T, int V, int S_max, int n_utt, Geometry* g) {
-    if (V % 4) return false;
-    // P = 8 always: one recursion warp covers 248 labels, and on B200 it is also the fastest choice for
-    // short targets (P < 8 is kept for experiments: it trips the posterior-mass check more often)
-    int P = 8;
-    const int q = env_int("CTC_B200_LIN_PAIRS", 0);
-    if (q == 1 || q == 2 || q == 4 || q == 8) P = q;
-    int R = (S_max + P + 32 * P - 1) / (32 * P);
-    if (R > 1 && P != 8) { P = 8; R = (S_max + P + 32 * P - 1) / (32 * P); }   // several warps: P = 8 only
-    int H = env_int("CTC_B200_HELPERS", 0);
+    const int P = 8;   // one recursion warp covers 248 labels; also the fastest choice for short targets
+    const int R = (S_max + P + 32 * P - 1) / (32 * P);
+    const bool al = V % 4 == 0;
     // one helper warp (softmax, then gradient rows) when one recursion warp suffices: 4 warps per CTA
     // leave 128 registers per thread, which the two-rows-in-flight combine pass needs
-    if (!(H == 1 || H == 2 || H == 4 || H == 8)) H = V > 256 ? 4 : (R == 1 ? 1 : 2);
-    int NC = env_int("CTC_B200_COMB", 0);          // combine groups (warps per recursion warp)
-    if (NC < 1 || NC > 4) NC = R <= 4 ? 2 : 1;   // two combine groups while the CTA stays within 512 threads
-    int NT = 32 * ((1 + NC) * R + H);
-    if (R == 1)   // the single-recursion-warp kernels are built for at most 256 threads
-        while (NT > 256 && H > 1) { H >>= 1; NT = 32 * ((1 + NC) * R + H); }
+    const int H = V > 256 ? 4 : (R == 1 ? 1 : 2);
+    const int NC = R <= 4 ? 2 : 1;   // two combine groups while the CTA stays within 512 threads
+    const int NT = 32 * ((1 + NC) * R + H);
     if (NT > 1024) return false;
     const int NP = 32 * P * R;
-    const int RS = lin_row_stride(NP, P);
-    const int YS = V <= 60 ? 80 : 0;   // fixed emission-ring row stride (an immediate in the kernel)
-    const int tc_env = env_int("CTC_B200_CHUNK", 0);
+    const int RS = lin_row_stride_host(NP, P);
+    // fixed emission-ring row stride (an immediate in the kernel): instantiated for 1, 2 and 4 recursion warps
+    const int YS = (al && V <= 60 && (R == 1 || R == 2 || R == 4)) ? 80 : 0;
+    const int tc_env = env().chunk;
     const int cand[3] = {4, 2, 1};
     for (int pass = 0; pass < 2; ++pass) {
         for (int ci = 0; ci < 3; ++ci) {
             int TC = cand[ci];
             if (tc_env >= 1 && tc_env <= 4) TC = tc_env;   // the kernel unrolls 4 rows
-            const int YSc = TC == 4 ? YS : 0;   // the fixed-stride variants are built for chunks of 4 frames
-            LinSmem lay(NP, R, V, TC, RS, YSc);
+            if (YS == 80 && TC != 4) continue;   // the fixed-stride variants are built for chunks of 4 frames
+            const int total = lin_smem_size(NP, R, V, TC, RS, YS);
             const int need = std::max(1, std::min(4, (2 * std::max(n_utt, 1) + kNumSmsHint - 1) / kNumSmsHint));
             const int limit = pass == 0 ? std::min(kMaxSmemBytes, 227 * 1024 / need - 1024) : kMaxSmemBytes;
-            if (lay.total > limit) continue;
-            g->lP = P; g->lNT = NT; g->lNP = NP; g->lchunk = TC; g->lRS = RS; g->lsmem = lay.total;
-            g->lR = R; g->lH = H; g->lD = NC; g->lYS = YSc;
+            if (total > limit) continue;
+            g->lP = P; g->lNT = NT; g->lNP = NP; g->lchunk = TC; g->lRS = RS; g->lsmem = total;
+            g->lR = R; g->lH = H; g->lD = NC; g->lYS = YS;
             g->l_lat_utt_stride = (size_t)std::max(T, 1) * (size_t)RS;
-            return true;
+            return lin_variant(*g, V) >= 0;
         }
     }
     return false;
-}
-
-int num_sms() {
-    static int n = -1;
-    if (n < 0) {
-        int dev = 0, v = 0;
-        if (cudaGetDevice(&dev) == cudaSuccess &&
-            cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && v > 0)
-            n = v;
-        else
-            n = 148;
-    }
-    return n;
 }
 
 int pick_geometry(int T, int V, int S_max, int n_utt, Geometry* g) {
     if (T < 0 || V < 1 || S_max < 0) return CTC_B200_INVALID_ARGUMENT;
     const int pairs = S_max + 1;
     if (pairs > 4096) return CTC_B200_UNSUPPORTED;  // targets longer than 4095 labels
-    const char* force = std::getenv("CTC_B200_KERNEL");   // g: generic, p: log-domain pipe, default: linear
-    const bool want_generic = force && force[0] == 'g';
-    const bool want_pipe = force && force[0] == 'p';
-    if (!want_generic && pick_pipe(T, V, pairs, n_utt, g)) {
-        if (!want_pipe && pick_lin(T, V, S_max, n_utt, g)) g->pipe = 2;
-        return CTC_B200_OK;
+    const char force = env().kernel;   // g: generic, p: log-domain pipe, default: linear
+    std::memset(g, 0, sizeof(*g));
+    // the log-domain kernel: warp-specialised when the logit rows are 16-byte aligned, else generic
+    if (force == 'g' || !pick_pipe(T, V, pairs, n_utt, g)) {
+        const int rc = pick_generic(T, V, pairs, g);
+        if (rc != CTC_B200_OK) return rc;
     }
-    return pick_generic(T, V, pairs, g);
-}
-
-template <int P, int MAXT>
-int launch_fused_pt(const FusedParams& prm, const Geometry& g, int n_utt, cudaStream_t st) {
-    static int configured_smem = -1;  // per-process, per-instantiation high-water mark
-    if (g.smem > configured_smem) {
-        CTC_CUDA(cudaFuncSetAttribute(ctc_fused_kernel<P, MAXT>,
-                                      cudaFuncAttributeMaxDynamicSharedMemorySize, g.smem));
-        configured_smem = g.smem;
-    }
-    ctc_fused_kernel<P, MAXT><<<dim3(2 * n_utt), dim3(g.NT), g.smem, st>>>(prm);
-    CTC_CUDA(cudaGetLastError());
+    g->pipe = g->base;
+    if (force != 'g' && force != 'p' && pick_lin(T, V, S_max, n_utt, g)) g->pipe = 2;
     return CTC_B200_OK;
 }
 
-template <int P>
-int launch_fused_p(const FusedParams& prm, const Geometry& g, int n_utt, cudaStream_t st) {
-    // small CTAs get the full register file, large ones the 64-register cap
-    return g.NT <= 256 ? launch_fused_pt<P, 256>(prm, g, n_utt, st)
-                       : launch_fused_pt<P, 1024>(prm, g, n_utt, st);
-}
-
-template <int P, int MAXT, int MINB>
-int launch_pipe_pt(const PipeParams& pp, const Geometry& g, int n_utt, cudaStream_t st) {
-    static int configured_smem = -1;
-    if (g.smem > configured_smem) {
-        CTC_CUDA(cudaFuncSetAttribute(ctc_pipe_kernel<P, MAXT, MINB>,
-                                      cudaFuncAttributeMaxDynamicSharedMemorySize, g.smem));
-        configured_smem = g.smem;
-    }
-    if (pp.redo != nullptr && t_allow_pdl && env_int("CTC_B200_PDL", 1))   // fallback pass right behind the linear kernel
-        CTC_CUDA(launch_pdl(ctc_pipe_kernel<P, MAXT, MINB>, dim3(2 * n_utt), dim3(g.NT), (size_t)g.smem, st, pp));
-    else
-        ctc_pipe_kernel<P, MAXT, MINB><<<dim3(2 * n_utt), dim3(g.NT), g.smem, st>>>(pp);
-    CTC_CUDA(cudaGetLastError());
-    return CTC_B200_OK;
-}
-
-template <int P>
-int launch_pipe_p(const PipeParams& pp, const Geometry& g, int n_utt, cudaStream_t st) {
-    if (g.NT <= 128) return launch_pipe_pt<P, 128, 4>(pp, g, n_utt, st);
-    if (g.NT <= 160) return launch_pipe_pt<P, 160, 4>(pp, g, n_utt, st);
-    if (g.NT <= 256) return launch_pipe_pt<P, 256, 2>(pp, g, n_utt, st);
-    if (g.NT <= 512) return launch_pipe_pt<P, 512, 1>(pp, g, n_utt, st);
-    return launch_pipe_pt<P, 1024, 1>(pp, g, n_utt, st);
-}
-
-template <int P, int RC, int YS, int MAXT, int MINB, bool FIX = false>
-int launch_lin_pt(const PipeParams& pp, int* flags, const Geometry& g, int n_utt, cudaStream_t st) {
-    static int configured_smem = -1;
-    if (g.lsmem > configured_smem) {
-        CTC_CUDA(cudaFuncSetAttribute(ctc_lin_kernel<P, RC, YS, MAXT, MINB, FIX>,
-                                      cudaFuncAttributeMaxDynamicSharedMemorySize, g.lsmem));
-        configured_smem = g.lsmem;
-    }
-    ctc_lin_kernel<P, RC, YS, MAXT, MINB, FIX><<<dim3(2 * n_utt), dim3(g.lNT), g.lsmem, st>>>(pp, flags);
-    CTC_CUDA(cudaGetLastError());
-    return CTC_B200_OK;
-}
-
-// One recursion warp (the common case): every stride of the kernel is a compile-time constant.
-template <int P>
-int launch_lin_r1(const PipeParams& pp, int* flags, const Geometry& g, int n_utt, cudaStream_t st) {
-    if (g.lYS == 80) {
-        if constexpr (P == 8) {   // the headline shape class: V = 48, REC + 2 x COMB + one helper warp
-            if (g.lNT == 128 && g.lH == 1 && g.lD == 2 && pp.f.V == 48 && env_int("CTC_B200_NOFIX", 0) == 0)
-                return launch_lin_pt<P, 1, 80, 128, 4, true>(pp, flags, g, n_utt, st);
-        }
-        if (g.lNT <= 128) return launch_lin_pt<P, 1, 80, 128, 4>(pp, flags, g, n_utt, st);
-        if (g.lNT <= 160) return launch_lin_pt<P, 1, 80, 160, 4>(pp, flags, g, n_utt, st);
-        return launch_lin_pt<P, 1, 80, 256, 2>(pp, flags, g, n_utt, st);
-    }
-    return g.lNT <= 128 ? launch_lin_pt<P, 1, 0, 128, 4>(pp, flags, g, n_utt, st)
-                        : launch_lin_pt<P, 1, 0, 256, 2>(pp, flags, g, n_utt, st);
-}
-
-// Several recursion warps (targets longer than 248 labels): P = 8; compile-time strides for 2 and 4
-// recursion warps (up to 1016 labels) with the V <= 60 emission ring, run-time strides otherwise.
-int launch_lin_rn(const PipeParams& pp, int* flags, const Geometry& g, int n_utt, cudaStream_t st) {
-    if (g.lYS == 80 && g.lNT <= 512) {
-        if (g.lR == 2) return launch_lin_pt<8, 2, 80, 512, 1>(pp, flags, g, n_utt, st);
-        if (g.lR == 4) return launch_lin_pt<8, 4, 80, 512, 1>(pp, flags, g, n_utt, st);
-    }
-    if (g.lNT <= 256) return launch_lin_pt<8, 0, 0, 256, 2>(pp, flags, g, n_utt, st);
-    if (g.lNT <= 512) return launch_lin_pt<8, 0, 0, 512, 1>(pp, flags, g, n_utt, st);
-    return launch_lin_pt<8, 0, 0, 1024, 1>(pp, flags, g, n_utt, st);
+struct Layout { long long frame_stride, utt_stride; };
+inline Layout make_layout(int layout, int T, int N, int V) {
+    if (layout == CTC_B200_LAYOUT_NTV) return {(long long)V, (long long)T * V};
+    return {(long long)N * V, (long long)V};
 }
 
 int launch_fused(const float* acts, const int32_t* targets, const int32_t* tgt_offsets,
                  const int32_t* in_lens, const int32_t* tgt_lens, int T, int N, int V, int S_max,
                  int blank, int zero_infinity, int utt_begin, int utt_count, float* nll,
                  float* grad, const float* grad_scale, float* lattice, size_t lattice_bytes,
-                 int* status_word, int* flags, cudaStream_t st) {
+                 int* status_word, int* flags, int* queue, const ctc_b200_options* opt, cudaStream_t st) {
     if (!acts || !targets || !tgt_offsets || !in_lens || !tgt_lens || !nll || !status_word)
         return CTC_B200_INVALID_ARGUMENT;
     if (T < 0 || N < 0 || V < 1 || blank < 0 || blank >= V || utt_begin < 0 || utt_count < 0 ||
         utt_begin + utt_count > N)
         return CTC_B200_INVALID_ARGUMENT;
+    const int layout = opt ? opt->layout : CTC_B200_LAYOUT_TNV;
+    if (layout != CTC_B200_LAYOUT_TNV && layout != CTC_B200_LAYOUT_NTV) return CTC_B200_INVALID_ARGUMENT;
+    if (opt && opt->use_clamp && !(opt->clamp_min < opt->clamp_max)) return CTC_B200_INVALID_ARGUMENT;
     if (utt_count == 0) return CTC_B200_OK;
     Geometry g;
     int rc = pick_geometry(T, V, S_max, N, &g);
     if (rc != CTC_B200_OK) return rc;
     const size_t lat_need = g.lattice_floats_per_utt() * sizeof(float) * (size_t)utt_count;
-    const size_t ys_need = 0;   // (saved softmax rows: tried, no faster; the kernel keeps the hook)
-    if (!lattice || lattice_bytes < lat_need + ys_need) return CTC_B200_WORKSPACE_TOO_SMALL;
+    if (!lattice || lattice_bytes < lat_need) return CTC_B200_WORKSPACE_TOO_SMALL;
     if (g.pipe == 2 && !flags) return CTC_B200_INVALID_ARGUMENT;
-    if ((reinterpret_cast<uintptr_t>(lattice) & 15) || (reinterpret_cast<uintptr_t>(acts) & 15) ||
-        (grad && (reinterpret_cast<uintptr_t>(grad) & 15)))
+    // the lattice always, acts / grad whenever the vocabulary allows 128-bit row accesses
+    if ((reinterpret_cast<uintptr_t>(lattice) & 15) ||
+        (V % 4 == 0 && ((reinterpret_cast<uintptr_t>(acts) & 15) || (grad && (reinterpret_cast<uintptr_t>(grad) & 15)))) ||
+        (reinterpret_cast<uintptr_t>(acts) & 3) || (grad && (reinterpret_cast<uintptr_t>(grad) & 3)))
         return CTC_B200_INVALID_ARGUMENT;
 
+    const Layout lay = make_layout(layout, T, N, V);
     FusedParams prm;
     prm.acts = acts;
     prm.targets = targets;
@@ -346,7 +258,7 @@ int launch_fused(const float* acts, const int32_t* targets, const int32_t* tgt_o
     prm.nll = nll;
     prm.grad = grad;
     prm.lattice = lattice;
-    prm.ysave = ys_need ? reinterpret_cast<float*>(reinterpret_cast<char*>(lattice) + (lat_need + 255) / 256 * 256) : nullptr;
+    prm.ysave = nullptr;   // (saved softmax rows: tried, no faster; the kernel keeps the hook)
     prm.status = status_word;
     prm.lat_utt_stride = (long long)g.lat_utt_stride;
     prm.T = T;
@@ -357,7 +269,18 @@ int launch_fused(const float* acts, const int32_t* targets, const int32_t* tgt_o
     prm.utt_begin = utt_begin;
     prm.row_stride = g.RS;
     prm.chunk = g.chunk;
-    if (g.pipe == 2) {
+    prm.frame_stride = lay.frame_stride;
+    prm.utt_stride = lay.utt_stride;
+    prm.use_clamp = (opt && opt->use_clamp) ? 1 : 0;
+    prm.clamp_lo = prm.use_clamp ? opt->clamp_min : 0.f;
+    prm.clamp_hi = prm.use_clamp ? opt->clamp_max : 0.f;
+    prm.redo = nullptr;
+    int* fl = flags ? flags - 2 * (ptrdiff_t)utt_begin : nullptr;   // kernels index flags by absolute utterance
+    // Forward-only calls (no gradient: torch.no_grad(), validation loss) go straight to the log-domain
+    // kernel: the linear kernel's safety net is the per-frame posterior-mass check of its GRADIENT pass,
+    // so without a gradient a partial loss of mass (flushed cells under saturated logits) would go unseen.
+    const bool use_lin = g.pipe == 2 && grad != nullptr;
+    if (use_lin) {
         // linear-domain kernel; `flags` ([2 * utt_count], indexed from utt_begin) marks the utterances
         // whose posterior-mass check failed, which the log-domain kernel below then recomputes
         PipeParams lp;
@@ -371,61 +294,54 @@ int launch_fused(const float* acts, const int32_t* targets, const int32_t* tgt_o
         lp.D = g.lD;
         // co-resident CTAs rotate their warp roles only when the CTA has a multiple of 4 warps (else
         // consecutive CTAs already start on different SM sub-partitions)
-        lp.rotate = (env_int("CTC_B200_ROTATE", 1) && (g.lNT / 32) % 4 == 0) ? num_sms() : 0;
+        lp.rotate = (env().rotate && (g.lNT / 32) % 4 == 0) ? num_sms() : 0;
         lp.redo = nullptr;
-        // CTA placement for a launch that fits one wave with an incomplete last "layer" (C2: 256 clusters on
-        // 74 SM pairs = 3 full layers + 34 clusters): the batch is sorted by length (dataloader.py:53), so with
-        // the identity mapping the LONGEST utterances share their SMs with a fourth CTA.  Rotating the
-        // utterances by whole layers moves them to the SM pairs that host only three (measured on B200, C2:
-        // 0.263 ms -> 0.248 ms with a rotation of two layers; rotations that are not whole layers: 0.27 ms).
-        {
+        lp.queue = nullptr;
+        lp.n_utt = utt_count;
+        lp.utt_rot = 0;
+        int n_clusters = utt_count;
+        // More utterances than co-resident clusters (C5: 512 per GPU and more): persistent clusters that pull
+        // utterances from a device-side queue, longest first, instead of a second, mostly idle wave.
+        const int resident = queue ? lin_resident_clusters(g, V) : 0;
+        const bool persist = env().persist < 0 ? (resident > 0 && utt_count > resident) : (env().persist > 0 && queue && resident > 0);
+        if (persist) {
+            lp.queue = queue;
+            n_clusters = std::min(resident, utt_count);
+        } else {
+            // CTA placement for a launch that fits one wave with an incomplete last "layer" (C2: 256 clusters on
+            // 74 SM pairs = 3 full layers + 34 clusters): the batch is sorted by length (dataloader.py:53), so with
+            // the identity mapping the LONGEST utterances share their SMs with a fourth CTA.  Rotating the
+            // utterances by whole layers moves them to the SM pairs that host only three (measured on B200, C2:
+            // 0.263 ms -> 0.248 ms with a rotation of two layers; rotations that are not whole layers: 0.27 ms).
             const int pairs = std::max(1, num_sms() / 2), layers = utt_count / pairs;
             int rot = (utt_count > pairs && utt_count <= 4 * pairs && utt_count % pairs != 0)
                           ? pairs * std::max(1, layers - 1) : 0;
-            const int e = env_int("CTC_B200_UTT_ROT", -1);
-            if (e >= 0) rot = e;
+            if (env().utt_rot >= 0) rot = env().utt_rot;
             lp.utt_rot = std::max(0, std::min(rot, utt_count - 1));
         }
-        int* fl = flags - 2 * (ptrdiff_t)utt_begin;   // kernels index flags by absolute utterance
-        if (g.lR == 1) {
-            switch (g.lP) {
-                case 1: rc = launch_lin_r1<1>(lp, fl, g, utt_count, st); break;
-                case 2: rc = launch_lin_r1<2>(lp, fl, g, utt_count, st); break;
-                case 4: rc = launch_lin_r1<4>(lp, fl, g, utt_count, st); break;
-                case 8: rc = launch_lin_r1<8>(lp, fl, g, utt_count, st); break;
-                default: rc = CTC_B200_UNSUPPORTED;
-            }
-        } else {
-            rc = g.lP == 8 ? launch_lin_rn(lp, fl, g, utt_count, st) : CTC_B200_UNSUPPORTED;
-        }
-        if (rc != CTC_B200_OK) return rc;
+        CTC_CUDA(launch_lin(lp, fl, g, n_clusters, st));
 #ifdef CTC_B200_DEV_KNOBS   // developer builds only: look at the linear kernel's own output for flagged utterances
-        if (env_int("CTC_B200_NOFALLBACK", 0)) return CTC_B200_OK;
+        if (Env::geti("CTC_B200_NOFALLBACK", 0)) return CTC_B200_OK;
 #endif
     }
-    if (g.pipe) {
+    if (g.base == 1) {
         PipeParams pp;
         pp.f = prm;
-        pp.redo = g.pipe == 2 ? flags - 2 * (ptrdiff_t)utt_begin : nullptr;
+        pp.redo = use_lin ? fl : nullptr;
         pp.utt_rot = 0;
+        pp.queue = nullptr;
+        pp.n_utt = utt_count;
         pp.R = g.R;
         pp.H = g.G;
         pp.NP = g.NP;
         pp.D = g.D;
-        pp.rotate = env_int("CTC_B200_ROTATE", 1) ? num_sms() : 0;
-        switch (g.P) {
-            case 1: return launch_pipe_p<1>(pp, g, utt_count, st);
-            case 2: return launch_pipe_p<2>(pp, g, utt_count, st);
-            case 4: return launch_pipe_p<4>(pp, g, utt_count, st);
-        }
-        return CTC_B200_UNSUPPORTED;
+        pp.rotate = env().rotate ? num_sms() : 0;
+        CTC_CUDA(launch_pipe(pp, g, utt_count, pp.redo != nullptr && t_allow_pdl && env().pdl, st));
+        return CTC_B200_OK;
     }
-    switch (g.P) {
-        case 1: return launch_fused_p<1>(prm, g, utt_count, st);
-        case 2: return launch_fused_p<2>(prm, g, utt_count, st);
-        case 4: return launch_fused_p<4>(prm, g, utt_count, st);
-    }
-    return CTC_B200_UNSUPPORTED;
+    prm.redo = use_lin ? fl : nullptr;
+    CTC_CUDA(launch_generic(prm, g, utt_count, st));
+    return CTC_B200_OK;
 }
 
 int status_from_bits(int bits) {
@@ -439,7 +355,7 @@ int status_from_bits(int bits) {
 
 extern "C" {
 
-int ctc_b200_version(void) { return 1000; }
+int ctc_b200_version(void) { return 2000; }
 
 const char* ctc_b200_status_string(int status) {
     switch (status) {
@@ -471,11 +387,32 @@ int ctc_b200_get_geometry(int T, int n_utt, int V, int S_max, ctc_b200_geometry*
     out->chunk = lin ? g.lchunk : g.chunk;
     out->row_stride = lin ? g.lRS : g.RS;
     out->smem_bytes = lin ? g.lsmem : g.smem;
-    // [256 B header: status word][redo flags: 2 ints per utterance][lattice]
+    // [256 B header: status word, utterance queue][redo flags: 2 ints per utterance][lattice]
     out->workspace_bytes = kHeaderBytes + flag_bytes(n_utt) +
-                           (g.lattice_floats_per_utt() * sizeof(float) * (size_t)n_utt + 255) / 256 * 256 +
-                           0;
+                           (g.lattice_floats_per_utt() * sizeof(float) * (size_t)n_utt + 255) / 256 * 256;
+    out->variant = lin ? lin_variant(g, V) : (g.pipe == 1 ? pipe_variant(g) : generic_variant(g));
+    out->fallback_kernel = lin ? g.base : -1;
+    out->comb_groups = lin ? g.lD : 0;
+    out->persistent = 0;
+    if (lin && env().persist != 0) {
+        int ndev = 0;
+        if (cudaGetDeviceCount(&ndev) == cudaSuccess && ndev > 0) {
+            const int resident = lin_resident_clusters(g, V);
+            out->persistent = (env().persist > 0 && resident > 0) || (resident > 0 && n_utt > resident) ? 1 : 0;
+        } else {
+            cudaGetLastError();
+        }
+    }
     return CTC_B200_OK;
+}
+
+const char* ctc_b200_variant_name(int kernel, int variant) {
+    switch (kernel) {
+        case 2: return lin_variant_name(variant);
+        case 1: return pipe_variant_name(variant);
+        case 0: return generic_variant_name(variant);
+    }
+    return "?";
 }
 
 int ctc_b200_workspace_bytes(int T, int N, int V, int S_max, size_t* bytes) {
@@ -486,12 +423,11 @@ int ctc_b200_workspace_bytes(int T, int N, int V, int S_max, size_t* bytes) {
     return rc;
 }
 
-int ctc_b200_fwd_bwd_range_f32(const float* acts, const int32_t* targets,
-                               const int32_t* tgt_offsets, const int32_t* in_lens,
-                               const int32_t* tgt_lens, int T, int N, int V, int S_max,
-                               int blank, int zero_infinity, int utt_begin, int utt_count,
-                               float* nll, float* grad, const float* grad_scale,
-                               void* workspace, size_t workspace_bytes, void* stream) {
+int ctc_b200_fwd_bwd_ex_f32(const float* acts, const int32_t* targets, const int32_t* tgt_offsets,
+                            const int32_t* in_lens, const int32_t* tgt_lens, int T, int N, int V,
+                            int S_max, int blank, int zero_infinity, int utt_begin, int utt_count,
+                            float* nll, float* grad, const float* grad_scale, void* workspace,
+                            size_t workspace_bytes, const ctc_b200_options* opt, void* stream) {
     const size_t head = (size_t)kHeaderBytes + flag_bytes(utt_count);
     if (!workspace || workspace_bytes < head) return CTC_B200_WORKSPACE_TOO_SMALL;
     if (reinterpret_cast<uintptr_t>(workspace) & 255) return CTC_B200_INVALID_ARGUMENT;
@@ -500,7 +436,18 @@ int ctc_b200_fwd_bwd_range_f32(const float* acts, const int32_t* targets,
                         zero_infinity, utt_begin, utt_count, nll, grad, grad_scale,
                         reinterpret_cast<float*>(ws + head), workspace_bytes - head,
                         reinterpret_cast<int*>(ws), reinterpret_cast<int*>(ws + kHeaderBytes),
-                        static_cast<cudaStream_t>(stream));
+                        reinterpret_cast<int*>(ws + kQueueOffset), opt, static_cast<cudaStream_t>(stream));
+}
+
+int ctc_b200_fwd_bwd_range_f32(const float* acts, const int32_t* targets,
+                               const int32_t* tgt_offsets, const int32_t* in_lens,
+                               const int32_t* tgt_lens, int T, int N, int V, int S_max,
+                               int blank, int zero_infinity, int utt_begin, int utt_count,
+                               float* nll, float* grad, const float* grad_scale,
+                               void* workspace, size_t workspace_bytes, void* stream) {
+    return ctc_b200_fwd_bwd_ex_f32(acts, targets, tgt_offsets, in_lens, tgt_lens, T, N, V, S_max, blank,
+                                   zero_infinity, utt_begin, utt_count, nll, grad, grad_scale, workspace,
+                                   workspace_bytes, nullptr, stream);
 }
 
 int ctc_b200_fwd_bwd_f32(const float* acts, const int32_t* targets, const int32_t* tgt_offsets,
@@ -513,31 +460,58 @@ int ctc_b200_fwd_bwd_f32(const float* acts, const int32_t* targets, const int32_
                                       workspace, workspace_bytes, stream);
 }
 
-int ctc_b200_scale_grad_f32(float* grad, const float* scale, int per_utt, int T, int N, int V,
-                            void* stream) {
+int ctc_b200_scale_grad_ex_f32(float* grad, const float* scale, int per_utt, int T, int N, int V,
+                               int layout, void* stream) {
     if (!grad || !scale || T < 0 || N < 0 || V < 1) return CTC_B200_INVALID_ARGUMENT;
+    if (layout != CTC_B200_LAYOUT_TNV && layout != CTC_B200_LAYOUT_NTV) return CTC_B200_INVALID_ARGUMENT;
     if (T == 0 || N == 0) return CTC_B200_OK;
     const int threads = 256;
     const size_t per_utt_elems = (size_t)T * V;
     int gy = (int)std::min<size_t>((per_utt_elems + threads * 8 - 1) / (threads * 8), 64);
     gy = std::max(gy, 1);
+    const Layout lay = make_layout(layout, T, N, V);
     ctc_scale_grad_kernel<<<dim3(N, gy), threads, 0, static_cast<cudaStream_t>(stream)>>>(
-        grad, scale, per_utt, T, N, V);
+        grad, scale, per_utt, T, N, V, lay.frame_stride, lay.utt_stride);
+    CTC_CUDA(cudaGetLastError());
+    return CTC_B200_OK;
+}
+
+int ctc_b200_scale_grad_f32(float* grad, const float* scale, int per_utt, int T, int N, int V,
+                            void* stream) {
+    return ctc_b200_scale_grad_ex_f32(grad, scale, per_utt, T, N, V, CTC_B200_LAYOUT_TNV, stream);
+}
+
+static int launch_reduce(const float* nll, const int32_t* in_lens, const int32_t* tgt_lens, int N,
+                         int reduction, int zero_on_short, float* out2, float* loss, float* result4,
+                         void* stream) {
+    if (!nll || !tgt_lens || !out2 || N < 0) return CTC_B200_INVALID_ARGUMENT;
+    const int mode = reduction == CTC_B200_REDUCE_MEAN ? 1 : 2;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (t_allow_pdl && env().pdl)
+        CTC_CUDA(launch_pdl(ctc_reduce_loss_kernel, dim3(1), dim3(256), (size_t)0, st, nll, in_lens, tgt_lens, N,
+                            mode, zero_on_short, out2, loss, result4));
+    else
+        ctc_reduce_loss_kernel<<<1, 256, 0, st>>>(nll, in_lens, tgt_lens, N, mode, zero_on_short, out2, loss, result4);
     CTC_CUDA(cudaGetLastError());
     return CTC_B200_OK;
 }
 
 int ctc_b200_reduce_loss_f32(const float* nll, const int32_t* tgt_lens, int N, int reduction,
                              float* out2, float* loss, void* stream) {
-    if (!nll || !tgt_lens || !out2 || N < 0) return CTC_B200_INVALID_ARGUMENT;
-    if (t_allow_pdl && env_int("CTC_B200_PDL", 1))
-        CTC_CUDA(launch_pdl(ctc_reduce_loss_kernel, dim3(1), dim3(256), (size_t)0, static_cast<cudaStream_t>(stream),
-                            nll, tgt_lens, N, reduction == CTC_B200_REDUCE_MEAN ? 1 : 2, out2, loss));
-    else
-        ctc_reduce_loss_kernel<<<1, 256, 0, static_cast<cudaStream_t>(stream)>>>(
-            nll, tgt_lens, N, reduction == CTC_B200_REDUCE_MEAN ? 1 : 2, out2, loss);
-    CTC_CUDA(cudaGetLastError());
-    return CTC_B200_OK;
+    return launch_reduce(nll, nullptr, tgt_lens, N, reduction, 0, out2, loss, nullptr, stream);
+}
+
+int ctc_b200_reduce_loss_status_f32(const float* nll, const int32_t* in_lens, const int32_t* tgt_lens,
+                                    int N, int reduction, int zero_on_short, float* out2,
+                                    float* loss, float* result4, void* stream) {
+    if (!result4) return CTC_B200_INVALID_ARGUMENT;
+    return launch_reduce(nll, in_lens, tgt_lens, N, reduction, zero_on_short, out2, loss, result4, stream);
+}
+
+static std::atomic<long long> g_peer_timeout_ms{600000};
+
+long long ctc_b200_set_peer_timeout_ms(long long ms) {
+    return g_peer_timeout_ms.exchange(ms < 0 ? 0 : ms);
 }
 
 static int launch_loss_allreduce(const float* nll, const int32_t* tgt_lens, int N, int reduction,
@@ -554,12 +528,15 @@ static int launch_loss_allreduce(const float* nll, const int32_t* tgt_lens, int 
     }
     const int mode = reduction == CTC_B200_REDUCE_MEAN ? 1 : 2;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    if (t_allow_pdl && env_int("CTC_B200_PDL", 1))
-        CTC_CUDA(launch_pdl(ctc_reduce_loss_allreduce_kernel, dim3(1), dim3(256), (size_t)0, st, nll, tgt_lens,
-                            N, mode, pair_in, pb, rank, world_size, seq, out2, loss, static_cast<int*>(workspace)));
+    const unsigned long long timeout_ns = (unsigned long long)g_peer_timeout_ms.load() * 1000000ull;
+    const int threads = pair_in ? 32 : 256;   // the exchange-only form needs one warp
+    if (t_allow_pdl && env().pdl)
+        CTC_CUDA(launch_pdl(ctc_reduce_loss_allreduce_kernel, dim3(1), dim3(threads), (size_t)0, st, nll, tgt_lens,
+                            N, mode, pair_in, pb, rank, world_size, seq, timeout_ns, out2, loss,
+                            static_cast<int*>(workspace)));
     else
-        ctc_reduce_loss_allreduce_kernel<<<1, 256, 0, st>>>(nll, tgt_lens, N, mode, pair_in, pb, rank, world_size,
-                                                            seq, out2, loss, static_cast<int*>(workspace));
+        ctc_reduce_loss_allreduce_kernel<<<1, threads, 0, st>>>(nll, tgt_lens, N, mode, pair_in, pb, rank, world_size,
+                                                                seq, timeout_ns, out2, loss, static_cast<int*>(workspace));
     CTC_CUDA(cudaGetLastError());
     return CTC_B200_OK;
 }
@@ -575,6 +552,22 @@ int ctc_b200_allreduce_pair_f32(float* out2, int reduction, void* const* peer_bu
                                 unsigned seq, float* loss, void* status_word, void* stream) {
     return launch_loss_allreduce(nullptr, nullptr, 0, reduction, out2, peer_bufs, rank, world_size, seq, out2,
                                  loss, status_word, stream);
+}
+
+int ctc_b200_greedy_decode_ler_i32(const float* acts, int T, int N, int V, int layout,
+                                   const int32_t* in_lens, const int32_t* targets,
+                                   const int32_t* tgt_offsets, const int32_t* tgt_lens, int blank,
+                                   int32_t* hyp, int32_t* hyp_len, int32_t* dist,
+                                   long long* totals, void* stream) {
+    if (!acts || !in_lens || !hyp || !hyp_len || T < 0 || N < 0 || V < 1 || blank < 0 || blank >= V)
+        return CTC_B200_INVALID_ARGUMENT;
+    if (layout != CTC_B200_LAYOUT_TNV && layout != CTC_B200_LAYOUT_NTV) return CTC_B200_INVALID_ARGUMENT;
+    if (targets && (!tgt_offsets || !tgt_lens || !dist)) return CTC_B200_INVALID_ARGUMENT;
+    if (reinterpret_cast<uintptr_t>(acts) & 3) return CTC_B200_INVALID_ARGUMENT;
+    const Layout lay = make_layout(layout, T, N, V);
+    CTC_CUDA(launch_decode_ler(acts, T, N, V, lay.frame_stride, lay.utt_stride, in_lens, targets, tgt_offsets,
+                               tgt_lens, blank, hyp, hyp_len, dist, totals, static_cast<cudaStream_t>(stream)));
+    return CTC_B200_OK;
 }
 
 int ctc_b200_check_status(const void* workspace, void* stream) {
@@ -603,6 +596,7 @@ struct ctc_b200_session {
     float* d_lattice = nullptr;
     size_t lattice_bytes = 0;
     int* d_flags = nullptr;    // [2 * N] redo flags of the linear kernel
+    int* d_queue = nullptr;    // [2 * n_slices] utterance queues (persistent launches), zeroed once
     char* d_small = nullptr;   // [targets | tgt_off | in_lens | tgt_lens | scale]
     char* h_small = nullptr;   // pinned mirror
     size_t small_bytes = 0;
@@ -643,6 +637,8 @@ int ctc_b200_session_create(int T, int N, int V, int S_max, int max_targets, int
     ok(cudaMalloc(&s->d_grad, nact));
     ok(cudaMalloc(&s->d_lattice, s->lattice_bytes));
     ok(cudaMalloc(&s->d_flags, flag_bytes(N)));
+    ok(cudaMalloc(&s->d_queue, (size_t)s->n_slices * 2 * sizeof(int)));
+    if (e == cudaSuccess) ok(cudaMemset(s->d_queue, 0, (size_t)s->n_slices * 2 * sizeof(int)));
     ok(cudaMalloc(&s->d_small, s->small_bytes));
     ok(cudaMalloc(&s->d_res, s->res_bytes));
     ok(cudaMallocHost(&s->h_small, s->small_bytes));
@@ -670,7 +666,7 @@ int ctc_b200_session_destroy(ctc_b200_session* s) {
     for (auto st : s->s_slice) if (st) cudaStreamDestroy(st);
     if (s->s_copy) cudaStreamDestroy(s->s_copy);
     if (s->s_comp) cudaStreamDestroy(s->s_comp);
-    cudaFree(s->d_acts); cudaFree(s->d_grad); cudaFree(s->d_lattice); cudaFree(s->d_flags);
+    cudaFree(s->d_acts); cudaFree(s->d_grad); cudaFree(s->d_lattice); cudaFree(s->d_flags); cudaFree(s->d_queue);
     cudaFree(s->d_small); cudaFree(s->d_res);
     if (s->h_small) cudaFreeHost(s->h_small);
     if (s->h_res) cudaFreeHost(s->h_res);
@@ -738,7 +734,7 @@ int ctc_b200_session_run_host_f32(ctc_b200_session* s, const float* acts_host,
                                    pitch, (size_t)(b1 - b0) * V * sizeof(float), (size_t)T,
                                    cudaMemcpyHostToDevice, s->s_copy));
         CTC_CUDA(cudaEventRecord(s->ev[k], s->s_copy));
-        cudaStream_t sk = env_int("CTC_B200_SLICE_STREAMS", 1) ? s->s_slice[k] : s->s_comp;
+        cudaStream_t sk = env().slice_streams ? s->s_slice[k] : s->s_comp;
         CTC_CUDA(cudaStreamWaitEvent(sk, s->ev[s->n_slices], 0));   // targets / lengths / cleared status
         CTC_CUDA(cudaStreamWaitEvent(sk, s->ev[k], 0));              // this slice's logits
         t_allow_pdl = false;
@@ -746,15 +742,15 @@ int ctc_b200_session_run_host_f32(ctc_b200_session* s, const float* acts_host,
                               zero_infinity, b0, b1 - b0, d_nll, want_grad ? s->d_grad : nullptr,
                               d_sc, s->d_lattice + (size_t)b0 * s->geo.lattice_floats_per_utt(),
                               s->lattice_bytes - (size_t)b0 * s->geo.lattice_floats_per_utt() * sizeof(float),
-                              d_status, s->d_flags + 2 * (size_t)b0, sk);
+                              d_status, s->d_flags + 2 * (size_t)b0, s->d_queue + 2 * k, nullptr, sk);
         t_allow_pdl = true;
         if (rc != CTC_B200_OK) return rc;
         CTC_CUDA(cudaEventRecord(s->ev_done[k], sk));
         CTC_CUDA(cudaStreamWaitEvent(s->s_comp, s->ev_done[k], 0));
-        launches += s->geo.pipe == 2 ? 2 : 1;
+        launches += (s->geo.pipe == 2 && want_grad) ? 2 : 1;
     }
     ctc_reduce_loss_kernel<<<1, 256, 0, s->s_comp>>>(
-        d_nll, d_tl, N, reduction == CTC_B200_REDUCE_MEAN ? 1 : 2, d_out2, nullptr);
+        d_nll, nullptr, d_tl, N, reduction == CTC_B200_REDUCE_MEAN ? 1 : 2, 0, d_out2, nullptr, nullptr);
     CTC_CUDA(cudaGetLastError());
     ++launches;
     CTC_CUDA(cudaMemcpyAsync(s->h_res, s->d_res, nll_host ? s->res_bytes : 16,

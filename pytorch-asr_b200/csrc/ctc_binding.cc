@@ -58,20 +58,28 @@ std::vector<int64_t> lengths_to_host(const torch::Tensor& t, int64_t N, const ch
     return std::vector<int64_t>(p, p + N);
 }
 
-// forward(acts, targets, input_lengths, target_lengths, blank, reduction, zero_infinity, want_grad)
-//   -> (loss, nll[N], grad[T,N,V] or empty, out2[2])
+// forward(acts, targets, input_lengths, target_lengths, blank, reduction, zero_infinity, want_grad,
+//         batch_major, use_clamp, clamp_min, clamp_max, zero_on_short)
+//   -> (loss, nll[N], grad (acts' shape) or empty, out2[2], status4[4])
 // reduction: 0 none, 1 mean, 2 sum.  grad already carries the reduction's scale
 // (1/(N*max(S_b,1)) for mean), i.e. it is d loss / d acts for grad_output == 1.
+// batch_major: acts (and grad) are [N,T,V], the network's own layout (folds trainer.py:418).
+// use_clamp: fused Hardtanh(clamp_min, clamp_max) (network.py:370); grad is then w.r.t. the raw logits.
+// status4 = [loss, flags (int bits: 1 NaN, 2 inf, 4 some T_b < 2 S_b), backward factor, #short]
+// (trainer.py:423-430 in one read); zero_on_short applies the reference's loss.mul_(0) on the device.
 std::vector<torch::Tensor> forward(const torch::Tensor& acts, const torch::Tensor& targets,
                                    const torch::Tensor& input_lengths,
                                    const torch::Tensor& target_lengths, int64_t blank,
-                                   int64_t reduction, bool zero_infinity, bool want_grad) {
+                                   int64_t reduction, bool zero_infinity, bool want_grad,
+                                   bool batch_major, bool use_clamp, double clamp_min, double clamp_max,
+                                   bool zero_on_short) {
     TORCH_CHECK(acts.is_cuda(), "ctc_b200: acts must be a CUDA tensor (no CPU fallback)");
     TORCH_CHECK(acts.scalar_type() == torch::kFloat32, "ctc_b200: acts must be float32");
-    TORCH_CHECK(acts.dim() == 3, "ctc_b200: acts must be [T, N, V]");
+    TORCH_CHECK(acts.dim() == 3, "ctc_b200: acts must be [T, N, V] (or [N, T, V] with batch_major)");
     TORCH_CHECK(reduction >= 0 && reduction <= 2, "ctc_b200: bad reduction");
+    TORCH_CHECK(!use_clamp || clamp_min < clamp_max, "ctc_b200: clamp_min must be < clamp_max");
     torch::Tensor x = acts.contiguous();
-    const int64_t T = x.size(0), N = x.size(1), V = x.size(2);
+    const int64_t T = batch_major ? x.size(1) : x.size(0), N = batch_major ? x.size(0) : x.size(1), V = x.size(2);
     TORCH_CHECK(blank >= 0 && blank < V, "ctc_b200: blank must be in label range");
     TORCH_CHECK(T < (1LL << 30) && N < (1LL << 30) && V < (1LL << 30), "ctc_b200: size overflow");
 
@@ -176,9 +184,15 @@ std::vector<torch::Tensor> forward(const torch::Tensor& acts, const torch::Tenso
 
     auto fopt = x.options();
     torch::Tensor nll = torch::empty({N}, fopt);
-    torch::Tensor grad = want_grad ? torch::empty({T, N, V}, fopt) : torch::empty({0}, fopt);
+    torch::Tensor grad = want_grad ? torch::empty_like(x) : torch::empty({0}, fopt);
     torch::Tensor out2 = torch::empty({2}, fopt);
+    torch::Tensor status4 = torch::empty({4}, fopt);
     torch::Tensor loss = torch::empty({}, fopt);
+    ctc_b200_options opt;
+    opt.layout = batch_major ? CTC_B200_LAYOUT_NTV : CTC_B200_LAYOUT_TNV;
+    opt.use_clamp = use_clamp ? 1 : 0;
+    opt.clamp_min = (float)clamp_min;
+    opt.clamp_max = (float)clamp_max;
 
     cudaStream_t stream = at::cuda::getCurrentCUDAStream();
     if (N > 0) {
@@ -188,41 +202,48 @@ std::vector<torch::Tensor> forward(const torch::Tensor& acts, const torch::Tenso
         torch::Tensor ws = torch::empty({(int64_t)ws_bytes},
                                         torch::TensorOptions().dtype(torch::kUInt8).device(x.device()));
         check_status(ctc_b200_clear_status(ws.data_ptr(), stream), "ctc_b200_clear_status");
-        check_status(ctc_b200_fwd_bwd_f32(x.data_ptr<float>(), d_tg, d_off, d_il, d_tl, (int)T,
-                                          (int)N, (int)V, (int)S_max, (int)blank,
-                                          zero_infinity ? 1 : 0, nll.data_ptr<float>(),
-                                          want_grad ? grad.data_ptr<float>() : nullptr, d_sc,
-                                          ws.data_ptr(), ws_bytes, stream),
-                     "ctc_b200_fwd_bwd_f32");
+        check_status(ctc_b200_fwd_bwd_ex_f32(x.data_ptr<float>(), d_tg, d_off, d_il, d_tl, (int)T,
+                                             (int)N, (int)V, (int)S_max, (int)blank,
+                                             zero_infinity ? 1 : 0, 0, (int)N, nll.data_ptr<float>(),
+                                             want_grad ? grad.data_ptr<float>() : nullptr, d_sc,
+                                             ws.data_ptr(), ws_bytes, &opt, stream),
+                     "ctc_b200_fwd_bwd_ex_f32");
+        // CUDA-resident targets could not be validated on the host: read the device-side check back
+        // (one sync on this rare path; torch synchronises for CUDA-resident targets as well)
+        if (!tg_on_host) check_status(ctc_b200_check_status(ws.data_ptr(), stream), "ctc_b200: targets");
     }
-    check_status(ctc_b200_reduce_loss_f32(nll.data_ptr<float>(), d_tl, (int)N,
-                                          reduction == 1 ? CTC_B200_REDUCE_MEAN : CTC_B200_REDUCE_SUM,
-                                          out2.data_ptr<float>(), loss.data_ptr<float>(), stream),
-                 "ctc_b200_reduce_loss_f32");
+    // loss reduction + the trainer's post-loss checks (trainer.py:423-430) in ONE launch
+    check_status(ctc_b200_reduce_loss_status_f32(nll.data_ptr<float>(), d_il, d_tl, (int)N,
+                                                 reduction == 1 ? CTC_B200_REDUCE_MEAN : CTC_B200_REDUCE_SUM,
+                                                 zero_on_short ? 1 : 0, out2.data_ptr<float>(),
+                                                 loss.data_ptr<float>(), status4.data_ptr<float>(), stream),
+                 "ctc_b200_reduce_loss_status_f32");
     // `d`, `ws` go back to the caching allocator here; it is stream-ordered, so the
     // kernels enqueued above still own them.
-    return {loss, nll, grad, out2};
+    return {loss, nll, grad, out2, status4};
 }
 
 // grad *= scale (scalar tensor, or [N] per utterance), in place; ==1 is free.
-void scale_grad(torch::Tensor grad, const torch::Tensor& scale) {
+void scale_grad(torch::Tensor grad, const torch::Tensor& scale, bool batch_major) {
     TORCH_CHECK(grad.is_cuda() && grad.is_contiguous() && grad.dim() == 3 &&
                 grad.scalar_type() == torch::kFloat32, "ctc_b200: bad grad tensor");
     const c10::cuda::CUDAGuard guard(grad.device());
     torch::Tensor s = scale.to(grad.device(), torch::kFloat32).contiguous();
     const int per_utt = s.numel() == 1 ? 0 : 1;
-    TORCH_CHECK(per_utt == 0 || s.numel() == grad.size(1), "ctc_b200: scale must be scalar or [N]");
-    check_status(ctc_b200_scale_grad_f32(grad.data_ptr<float>(), s.data_ptr<float>(), per_utt,
-                                         (int)grad.size(0), (int)grad.size(1), (int)grad.size(2),
-                                         at::cuda::getCurrentCUDAStream()),
-                 "ctc_b200_scale_grad_f32");
+    const int64_t T = batch_major ? grad.size(1) : grad.size(0), N = batch_major ? grad.size(0) : grad.size(1);
+    TORCH_CHECK(per_utt == 0 || s.numel() == N, "ctc_b200: scale must be scalar or [N]");
+    check_status(ctc_b200_scale_grad_ex_f32(grad.data_ptr<float>(), s.data_ptr<float>(), per_utt,
+                                            (int)T, (int)N, (int)grad.size(2),
+                                            batch_major ? CTC_B200_LAYOUT_NTV : CTC_B200_LAYOUT_TNV,
+                                            at::cuda::getCurrentCUDAStream()),
+                 "ctc_b200_scale_grad_ex_f32");
 }
 
 std::vector<int64_t> geometry(int64_t T, int64_t N, int64_t V, int64_t S_max) {
     ctc_b200_geometry g;
     check_status(ctc_b200_get_geometry((int)T, (int)N, (int)V, (int)S_max, &g), "ctc_b200_get_geometry");
     return {g.kernel, g.rec_warps, g.grad_warps, g.pairs_per_thread, g.threads, g.chunk, g.row_stride, g.smem_bytes,
-            (int64_t)g.workspace_bytes};
+            (int64_t)g.workspace_bytes, g.variant, g.fallback_kernel, g.comb_groups, g.persistent};
 }
 
 }  // namespace

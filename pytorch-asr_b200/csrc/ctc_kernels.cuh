@@ -66,6 +66,16 @@ struct FusedParams {
     int utt_begin;                         // first utterance handled by this launch
     int row_stride;                        // floats per lattice row = 2*NP + Wp
     int chunk;                             // frames per chunk (<= kMaxChunk)
+    // Layout of acts / grad: element (t, b, v) lives at t * frame_stride + b * utt_stride + v.
+    //   time-major  [T,N,V] (trainer.py:418):  frame_stride = N*V, utt_stride = V
+    //   batch-major [N,T,V] (what network.py:380-396 emits; folds trainer.py:418's transpose+copy):
+    //                                          frame_stride = V,   utt_stride = T*V
+    long long frame_stride, utt_stride;
+    // Fused Hardtanh(clamp_lo, clamp_hi) in front of the log_softmax (network.py:370); its backward
+    // mask (gradient 0 where the raw logit is outside the open interval) is applied to the gradient.
+    int use_clamp;
+    float clamp_lo, clamp_hi;
+    const int* __restrict__ redo;          // [2 * N] or nullptr: run only utterances the linear kernel flagged
 };
 
 enum StatusBits : int {
@@ -88,6 +98,23 @@ __device__ __forceinline__ float lg2f(float x) {
 __device__ __forceinline__ float lse2(float a, float b) {
     return fmaxf(a, b) + lg2f(1.0f + ex2f(-fabsf(a - b)));
 }
+// Fused Hardtanh (network.py:370) in front of the log_softmax.  `cin` is the value that enters the
+// softmax; `cmask` says whether Hardtanh's backward blocks the gradient (raw logit outside the OPEN
+// interval, torch's hardtanh_backward).  The log-domain kernels keep the mask in the lowest mantissa bit
+// of the stored log2-probability (1 ulp, only when the clamp is on); the linear kernel in the sign bit
+// of the stored probability.
+struct Clamp {
+    bool on;
+    float lo, hi;
+    __device__ __forceinline__ float cin(float x) const { return on ? fminf(fmaxf(x, lo), hi) : x; }
+    __device__ __forceinline__ bool cmask(float x) const { return on && !(x > lo && x < hi); }
+    __device__ __forceinline__ float tag(float lp, float raw) const {
+        if (!on) return lp;
+        return __int_as_float((__float_as_int(lp) & ~1) | (cmask(raw) ? 1 : 0));
+    }
+    __device__ __forceinline__ bool tagged(float lp) const { return on && (__float_as_int(lp) & 1); }
+};
+
 __device__ __forceinline__ float warp_max(float x) {
     float m;
     asm volatile("redux.sync.max.f32 %0, %1, 0xffffffff;" : "=f"(m) : "f"(x));
@@ -186,9 +213,16 @@ ctc_fused_kernel(const FusedParams p) {
     const int NT = blockDim.x, W = NT >> 5, NP = NT * P;
     const int b = p.utt_begin + (blockIdx.x >> 1);
     const bool rev = (blockIdx.x & 1) != 0;
-    const int T = p.T, N = p.N, V = p.V, blank = p.blank;
+    // fallback mode (vocabularies the log-domain pipe kernel cannot take, V % 4 != 0): both CTAs of the
+    // cluster leave unless the linear kernel flagged the utterance
+    if (p.redo != nullptr) {
+        asm volatile("griddepcontrol.wait;" ::: "memory");
+        if ((p.redo[2 * b] | p.redo[2 * b + 1]) == 0) return;
+    }
+    const int T = p.T, V = p.V, blank = p.blank;
     const int RS = p.row_stride, TC = p.chunk;
-    const bool vec4 = (V & 3) == 0;
+    const bool vec4 = (V & 3) == 0 && ((p.frame_stride | p.utt_stride) & 3) == 0;
+    const Clamp clp{p.use_clamp != 0, p.clamp_lo, p.clamp_hi};
 
     const SmemLayout lay(NP, W, V, TC, RS);
     const int Vs = lay.Vs;
@@ -210,9 +244,9 @@ ctc_fused_kernel(const FusedParams p) {
     const int32_t* tg = p.targets + p.tgt_off[b];
     const bool want_grad = p.grad != nullptr;
     const float gscale = p.grad_scale ? p.grad_scale[b] : 1.0f;
-    const size_t frame_stride = (size_t)N * V;               // floats between frames
-    const float* acts_b = p.acts + (size_t)b * V;
-    float* grad_b = want_grad ? p.grad + (size_t)b * V : nullptr;
+    const size_t frame_stride = (size_t)p.frame_stride;      // floats between frames
+    const float* acts_b = p.acts + (size_t)b * (size_t)p.utt_stride;
+    float* grad_b = want_grad ? p.grad + (size_t)b * (size_t)p.utt_stride : nullptr;
 
     // ---- mandatory zero fill of gradient rows t >= T_b (no compute) ----------
     if (want_grad) {
@@ -537,46 +571,47 @@ ctc_fused_kernel(const FusedParams p) {
                 if (V4 <= 32) {  // whole row in one float4 per lane: single pass
                     float4 q = make_float4(-CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F);
                     if (lane < V4) q = row4[lane];
+                    const float4 raw = q;
+                    q.x = clp.cin(q.x); q.y = clp.cin(q.y); q.z = clp.cin(q.z); q.w = clp.cin(q.w);
                     m = warp_max(fmaxf(fmaxf(q.x, q.y), fmaxf(q.z, q.w)));
                     q.x = (q.x - m) * kLog2e; q.y = (q.y - m) * kLog2e;
                     q.z = (q.z - m) * kLog2e; q.w = (q.w - m) * kLog2e;
                     z = warp_sum(ex2f(q.x) + ex2f(q.y) + ex2f(q.z) + ex2f(q.w));
                     const float lz = lg2f(z);
                     if (lane < V4)
-                        row4[lane] = make_float4(fmaxf(q.x - lz, kNeg), fmaxf(q.y - lz, kNeg),
-                                                 fmaxf(q.z - lz, kNeg), fmaxf(q.w - lz, kNeg));
+                        row4[lane] = make_float4(clp.tag(fmaxf(q.x - lz, kNeg), raw.x), clp.tag(fmaxf(q.y - lz, kNeg), raw.y),
+                                                 clp.tag(fmaxf(q.z - lz, kNeg), raw.z), clp.tag(fmaxf(q.w - lz, kNeg), raw.w));
                 } else {
                     for (int c4 = lane; c4 < V4; c4 += 32) {
                         const float4 q = row4[c4];
-                        m = fmaxf(m, fmaxf(fmaxf(q.x, q.y), fmaxf(q.z, q.w)));
+                        m = fmaxf(m, fmaxf(fmaxf(clp.cin(q.x), clp.cin(q.y)), fmaxf(clp.cin(q.z), clp.cin(q.w))));
                     }
                     m = warp_max(m);
                     for (int c4 = lane; c4 < V4; c4 += 32) {
-                        float4 q = row4[c4];
-                        q.x = (q.x - m) * kLog2e; q.y = (q.y - m) * kLog2e;
-                        q.z = (q.z - m) * kLog2e; q.w = (q.w - m) * kLog2e;
-                        z += ex2f(q.x) + ex2f(q.y) + ex2f(q.z) + ex2f(q.w);
-                        row4[c4] = q;
+                        const float4 q = row4[c4];
+                        z += ex2f((clp.cin(q.x) - m) * kLog2e) + ex2f((clp.cin(q.y) - m) * kLog2e) +
+                             ex2f((clp.cin(q.z) - m) * kLog2e) + ex2f((clp.cin(q.w) - m) * kLog2e);
                     }
                     z = warp_sum(z);
                     const float lz = lg2f(z);
                     for (int c4 = lane; c4 < V4; c4 += 32) {
-                        float4 q = row4[c4];
-                        row4[c4] = make_float4(fmaxf(q.x - lz, kNeg), fmaxf(q.y - lz, kNeg),
-                                               fmaxf(q.z - lz, kNeg), fmaxf(q.w - lz, kNeg));
+                        const float4 q = row4[c4];
+                        row4[c4] = make_float4(clp.tag(fmaxf((clp.cin(q.x) - m) * kLog2e - lz, kNeg), q.x),
+                                               clp.tag(fmaxf((clp.cin(q.y) - m) * kLog2e - lz, kNeg), q.y),
+                                               clp.tag(fmaxf((clp.cin(q.z) - m) * kLog2e - lz, kNeg), q.z),
+                                               clp.tag(fmaxf((clp.cin(q.w) - m) * kLog2e - lz, kNeg), q.w));
                     }
                 }
             } else {
-                for (int v = lane; v < V; v += 32) m = fmaxf(m, row[v]);
+                for (int v = lane; v < V; v += 32) m = fmaxf(m, clp.cin(row[v]));
                 m = warp_max(m);
-                for (int v = lane; v < V; v += 32) {
-                    const float q = (row[v] - m) * kLog2e;
-                    z += ex2f(q);
-                    row[v] = q;
-                }
+                for (int v = lane; v < V; v += 32) z += ex2f((clp.cin(row[v]) - m) * kLog2e);
                 z = warp_sum(z);
                 const float lz = lg2f(z);
-                for (int v = lane; v < V; v += 32) row[v] = fmaxf(row[v] - lz, kNeg);
+                for (int v = lane; v < V; v += 32) {
+                    const float raw = row[v];
+                    row[v] = clp.tag(fmaxf((clp.cin(raw) - m) * kLog2e - lz, kNeg), raw);
+                }
             }
             if (lane == 0) row[V] = kNeg;  // what padding pairs gather
         }
@@ -615,7 +650,8 @@ ctc_fused_kernel(const FusedParams p) {
                     float occ = (v == blank) ? bs : 0.f;
                     const int k1 = s_cstart[v + 1];
                     for (int k = s_cstart[v]; k < k1; ++k) occ += ex2f(eY[k]);
-                    g[v] = gscale * (ex2f(lp2[v]) - occ);
+                    const float lpv = lp2[v];
+                    g[v] = clp.tagged(lpv) ? 0.0f : gscale * (ex2f(lpv) - occ);
                 }
             }
             pb ^= 1;
@@ -624,134 +660,6 @@ ctc_fused_kernel(const FusedParams p) {
         __syncthreads();
     }
     if (n_store == Tb) cluster_sync_all();  // T_b == 1: the beta CTA has nothing to consume
-}
-
-// ---------------------------------------------------------------------------
-// grad[t, b, :] *= scale[b] (or *= scale[0] when `per_utt` is 0), skipped
-// entirely -- no memory traffic -- for factors equal to 1.  This is the whole
-// "backward": the fused kernel already wrote d nll / d logits; autograd only
-// has to apply the upstream grad_output (trainer.py:429 loss.mul_(0), AMP loss
-// scaling at :435-436), which is exactly 1 in the plain fp32 step.
-// ---------------------------------------------------------------------------
-__global__ void ctc_scale_grad_kernel(float* __restrict__ grad, const float* __restrict__ scale,
-                                      int per_utt, int T, int N, int V) {
-    const int b = blockIdx.x;
-    const float s = per_utt ? scale[b] : scale[0];
-    if (s == 1.0f) return;
-    const size_t total = (size_t)T * V;
-    for (size_t idx = (size_t)blockIdx.y * blockDim.x + threadIdx.x; idx < total;
-         idx += (size_t)gridDim.y * blockDim.x) {
-        const size_t t = idx / V, v = idx - t * V;
-        float* g = grad + (t * N + b) * V + v;
-        *g = (s == 0.0f) ? 0.0f : *g * s;
-    }
-}
-
-// ---------------------------------------------------------------------------
-// out[0] = sum_b nll_b / max(S_b, 1)   (mode 1, 'mean' numerator; trainer.py:153)
-//        = sum_b nll_b                 (mode 2, 'sum')
-// out[1] = N  (the normaliser that is all-reduced together with out[0])
-// Single CTA, fixed summation order => bit-reproducible.
-// ---------------------------------------------------------------------------
-__global__ void ctc_reduce_loss_kernel(const float* __restrict__ nll,
-                                       const int32_t* __restrict__ tgt_lens, int N, int mode,
-                                       float* __restrict__ out, float* __restrict__ loss) {
-    __shared__ double s_part[32];
-    // may be launched with programmatic stream serialization: the producer of `nll` must be complete
-    asm volatile("griddepcontrol.wait;" ::: "memory");
-    double acc = 0.0;
-    for (int b = threadIdx.x; b < N; b += blockDim.x) {
-        double v = (double)nll[b];
-        if (mode == 1) v /= (double)max(tgt_lens[b], 1);
-        acc += v;
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-    if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = acc;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        double s = 0.0;
-        for (int i = 0; i < (int)(blockDim.x >> 5); ++i) s += s_part[i];
-        out[0] = (float)s;
-        out[1] = (float)N;
-        if (loss) loss[0] = (mode == 1) ? (float)(s / (double)max(N, 1)) : (float)s;
-    }
-}
-
-// ---------------------------------------------------------------------------
-// Loss reduction fused with the job's only collective: the (sum, count) pair goes straight into
-// every peer's exchange buffer (P2P stores over NVLink), the pairs addressed to this rank are
-// awaited and added in rank order.  Exchange buffer: slot[parity][rank] = {sum, seq, count, seq}.
-// ---------------------------------------------------------------------------
-struct PeerBufs { float4* p[8]; };
-
-// pair_in != nullptr: the local pair was already reduced (ctc_reduce_loss_kernel); exchange only.
-__global__ void ctc_reduce_loss_allreduce_kernel(const float* __restrict__ nll,
-                                                 const int32_t* __restrict__ tgt_lens, int N, int mode,
-                                                 const float* pair_in,
-                                                 PeerBufs peers, int rank, int world, unsigned seq,
-                                                 float* __restrict__ out2, float* __restrict__ loss,
-                                                 int* __restrict__ status) {
-    __shared__ double s_part[32];
-    __shared__ float s_pair[2];
-    __shared__ float2 s_in[8];
-    asm volatile("griddepcontrol.wait;" ::: "memory");
-    if (pair_in != nullptr) {
-        if (threadIdx.x < 2) s_pair[threadIdx.x] = pair_in[threadIdx.x];
-    } else {
-        double acc = 0.0;
-        for (int b = threadIdx.x; b < N; b += blockDim.x) {
-            double v = (double)nll[b];
-            if (mode == 1) v /= (double)max(tgt_lens[b], 1);
-            acc += v;
-        }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-        if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = acc;
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            double s = 0.0;
-            for (int i = 0; i < (int)(blockDim.x >> 5); ++i) s += s_part[i];
-            s_pair[0] = (float)s;
-            s_pair[1] = (float)N;
-        }
-    }
-    __syncthreads();
-    const int par = (int)(seq & 1u);
-    if ((int)threadIdx.x < world) {
-        // one 16-byte store per peer, each 8-byte half carrying its own copy of the sequence number
-        // (8 bytes is the unit NVLink delivers atomically: the NCCL "LL" convention)
-        float4 v = make_float4(s_pair[0], __uint_as_float(seq), s_pair[1], __uint_as_float(seq));
-        float4* dst = peers.p[threadIdx.x] + par * 8 + rank;
-        asm volatile("st.volatile.global.v4.f32 [%0], {%1, %2, %3, %4};"
-                     ::"l"(dst), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
-        __threadfence_system();
-        // the pair rank `threadIdx.x` addressed to me
-        const float4* src = peers.p[rank] + par * 8 + threadIdx.x;
-        float4 r;
-        unsigned spins = 0;
-        for (;;) {
-            asm volatile("ld.volatile.global.v4.f32 {%0, %1, %2, %3}, [%4];"
-                         : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(src) : "memory");
-            if (__float_as_uint(r.y) == seq && __float_as_uint(r.w) == seq) break;
-            if (++spins > (1u << 22)) {   // ~2 s: a missing peer must fail loudly, not hang the stream
-                atomicOr(status, kStatusPeerTimeout);
-                r.x = CUDART_NAN_F;
-                r.z = 0.f;
-                break;
-            }
-            __nanosleep(200);
-        }
-        s_in[threadIdx.x] = make_float2(r.x, r.z);
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        double s = 0.0, n = 0.0;
-        for (int r = 0; r < world; ++r) { s += (double)s_in[r].x; n += (double)s_in[r].y; }
-        out2[0] = (float)s;
-        out2[1] = (float)n;
-        if (loss) loss[0] = (mode == 1) ? (float)(s / fmax(n, 1.0)) : (float)s;
-    }
 }
 
 }  // namespace ctcb200

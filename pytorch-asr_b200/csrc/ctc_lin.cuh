@@ -187,11 +187,12 @@ ctc_lin_kernel(const PipeParams pp, int* __restrict__ flags) {
     const int w = ((int)(threadIdx.x >> 5) + NW - shift) % NW;   // role (virtual) warp id
     // which utterance this cluster works on: the batch is sorted by length (dataloader.py:53); utt_rot
     // moves the longest utterances to the clusters whose SMs end up with the fewest co-resident CTAs
-    int b_local = (int)(blockIdx.x >> 1) + pp.utt_rot;
-    if (b_local >= (int)(gridDim.x >> 1)) b_local -= (int)(gridDim.x >> 1);
-    const int b = p.utt_begin + b_local;
     const bool rev = (blockIdx.x & 1) != 0;
-    const int T = p.T, N = p.N, V = FIX ? 48 : p.V, blank = p.blank;
+    const int T = p.T, V = FIX ? 48 : p.V, blank = p.blank;
+    // rows of acts / grad start on 16-byte boundaries (always, in the V <= 60 emission-ring variants);
+    // otherwise (the reference's own V = 177, params.py:27) the helpers use 4-byte copies and scalar stores
+    const bool al = YS == 80 ? true : ((V & 3) == 0 && ((p.frame_stride | p.utt_stride) & 3) == 0);
+    const Clamp clp{p.use_clamp != 0, p.clamp_lo, p.clamp_hi};
     // the V <= 60 emission-ring variants (YS = 80) are only launched with chunks of 4 frames
     const int RS = RC > 0 ? lin_row_stride(32 * P * RC, P) : p.row_stride, TC = (YS == 80 && CTC_LIN_TC4) ? 4 : p.chunk;
     const int NC = FIX ? 2 : pp.D;           // combine groups: group g takes the rows r == g (mod NC) of a chunk
@@ -215,6 +216,36 @@ ctc_lin_kernel(const PipeParams pp, int* __restrict__ flags) {
     uint64_t* bar_acts = reinterpret_cast<uint64_t*>(smem_raw + lay.bars);   // [NL]
     uint64_t* bar_part = bar_acts + NL;                                      // [NS]
 
+    // Persistent launch (more utterances than co-resident clusters): the clusters pull utterances from an
+    // atomic queue in index order -- the batch is sorted by length, longest first, so this is the
+    // longest-processing-time-first schedule and the tail of the launch is filled with the SHORT utterances.
+    int& s_next = s_flag[3];
+    for (;;) {
+    int b_local;
+    if (pp.queue != nullptr) {
+        __syncthreads();                     // the previous utterance is done with this CTA's shared memory
+        if (threadIdx.x == 0 && (blockIdx.x & 1) == 0) s_next = atomicAdd(pp.queue, 1);
+        cluster_sync_all();                  // rank 0's ticket is visible to rank 1 (release / acquire)
+        {
+            unsigned remote;
+            asm volatile("mapa.shared::cluster.u32 %0, %1, 0;" : "=r"(remote) : "r"(smem_u32(&s_next)));
+            asm volatile("ld.shared::cluster.s32 %0, [%1];" : "=r"(b_local) : "r"(remote) : "memory");
+        }
+        cluster_sync_all();                  // both CTAs have read it before rank 0 draws the next one
+        if (b_local >= pp.n_utt) {
+            // the last cluster to run dry re-arms the queue for the next launch on this stream
+            if (threadIdx.x == 0 && (blockIdx.x & 1) == 0 &&
+                atomicAdd(pp.queue + 1, 1) == (int)(gridDim.x >> 1) - 1) {
+                pp.queue[0] = 0;
+                pp.queue[1] = 0;
+            }
+            break;
+        }
+    } else {
+        b_local = (int)(blockIdx.x >> 1) + pp.utt_rot;
+        if (b_local >= (int)(gridDim.x >> 1)) b_local -= (int)(gridDim.x >> 1);
+    }
+    const int b = p.utt_begin + b_local;
     int Tb = p.in_lens[b], S = p.tgt_lens[b];
     if (Tb < 0 || Tb > T || S < 0 || S > NP - P) {
         if (threadIdx.x == 0) atomicOr(p.status, kStatusBadLength);
@@ -224,9 +255,9 @@ ctc_lin_kernel(const PipeParams pp, int* __restrict__ flags) {
     const int32_t* tg = p.targets + p.tgt_off[b];
     const bool want_grad = p.grad != nullptr;
     const float gscale = p.grad_scale ? p.grad_scale[b] : 1.0f;
-    const size_t frame_stride = (size_t)N * V;
-    const float* acts_b = p.acts + (size_t)b * V;
-    float* grad_b = want_grad ? p.grad + (size_t)b * V : nullptr;
+    const size_t frame_stride = (size_t)p.frame_stride;
+    const float* acts_b = p.acts + (size_t)b * (size_t)p.utt_stride;
+    float* grad_b = want_grad ? p.grad + (size_t)b * (size_t)p.utt_stride : nullptr;
     const int V4 = V >> 2, V2 = V >> 1;
 
     // helper roles: SOFT warps [0, nA), GRAD warps [nA, H); a single helper does both
@@ -234,7 +265,7 @@ ctc_lin_kernel(const PipeParams pp, int* __restrict__ flags) {
     const bool isA = hw >= 0 && (H == 1 || hw < nA), isB = hw >= 0 && (H == 1 || hw >= nA);
     const int ha = hw, hb = H == 1 ? 0 : hw - nA;
     // wide vocabulary: logits rows come in by TMA bulk copies (one per row) instead of cp.async
-    const bool wide_rows = CTC_LIN_TMA_Y ? true : (YS == 0 && nA > 1 && V > 256);
+    const bool wide_rows = CTC_LIN_TMA_Y ? true : (YS == 0 && nA > 1 && V > 256 && al);
 
     // ---- GRAD warps: mandatory zero fill of gradient rows t >= T_b (no compute) --------
     if (want_grad && isB) {
@@ -242,7 +273,10 @@ ctc_lin_kernel(const PipeParams pp, int* __restrict__ flags) {
         const int mine = (nrows + (rev ? 0 : 1)) >> 1;  // rows Tb+rev, Tb+rev+2, ...
         float* g = grad_b + (size_t)(Tb + (rev ? 1 : 0) + 2 * hb) * frame_stride;
         const size_t ginc = 2 * (size_t)nB * frame_stride;
-        if (YS == 80 || V4 < 32) {
+        if (!al) {
+            for (int r = hb; r < mine; r += nB, g += ginc)
+                for (int c = lane; c < V; c += 32) g[c] = 0.f;
+        } else if (YS == 80 || V4 < 32) {
             // narrow rows: the 32 lanes of a store cover 32 / V4 rows (V = 48: 12 lanes per row otherwise)
             int r = hb, c = lane;
             while (c >= V4) { c -= V4; r += nB; g += ginc; }
@@ -261,6 +295,7 @@ ctc_lin_kernel(const PipeParams pp, int* __restrict__ flags) {
             flags[2 * b + (rev ? 1 : 0)] = 0;
             if (!rev) p.nll[b] = (S == 0 || p.zero_infinity) ? 0.0f : CUDART_INF_F;
         }
+        if (pp.queue != nullptr) continue;
         return;  // both CTAs of the cluster take this exit
     }
 
@@ -435,7 +470,7 @@ ctc_lin_kernel(const PipeParams pp, int* __restrict__ flags) {
         // one recursion step: a[t] <- a[t-1]; xs / ins = the cells BEFORE the emission (scale `off`);
         // yo = float offset of this step's row inside the chunk of the emission ring
         auto advance = [&](const float* yb_ptr, int yo, float (&xs)[P], float (&ins)[P]) {
-            const float yb = yb_ptr[yo];
+            const float yb = fabsf(yb_ptr[yo]);   // (the sign bit carries the fused Hardtanh's backward mask)
             float v = __shfl_up_sync(0xffffffffu, aY[P - 1], 1);
             int o = __shfl_up_sync(0xffffffffu, off, 1);
             if constexpr (RC == 1) {
@@ -448,7 +483,7 @@ ctc_lin_kernel(const PipeParams pp, int* __restrict__ flags) {
 #pragma unroll
             for (int k = P - 1; k >= 0; --k) {
                 const float prev = k > 0 ? aY[k > 0 ? k - 1 : 0] : am1;
-                const float yl = yk[k][yo];
+                const float yl = fabsf(yk[k][yo]);
                 const float x = aB[k] + prev;
                 const float in = fmaf(skf[k], prev, aY[k] + aB[k]);
                 xs[k] = x;
@@ -868,7 +903,7 @@ ctc_lin_kernel(const PipeParams pp, int* __restrict__ flags) {
         ptrdiff_t cp_src[2];
 #pragma unroll
         for (int j = 0; j < 2; ++j) {
-            const int idx = lane + 32 * j, r = idx / V4, c = idx - r * V4;
+            const int idx = lane + 32 * j, r = idx / max(V4, 1), c = idx - r * V4;
             cp_row[j] = idx < n4 ? r : 0x7fffffff;
             cp_dst[j] = r * Vs + 4 * c;
             cp_src[j] = r * a_inc + 4 * c;
@@ -882,10 +917,15 @@ ctc_lin_kernel(const PipeParams pp, int* __restrict__ flags) {
                 if (lane == 0) issue_logits_tma(ka, slot_a);
                 return;
             }
+            if (!al) {
+                for (int r = 0; r < rows; ++r)
+                    for (int c = lane; c < V; c += 32) cp_async4(dst + r * Vs + c, src + r * a_inc + c);
+            } else {
 #pragma unroll
             for (int j = 0; j < 2; ++j)
                 if (cp_row[j] < rows) cp_async16(dst + cp_dst[j], src + cp_src[j]);
-            if (n4 > 64) {
+            }
+            if (al && n4 > 64) {
                 int r = 64 / V4, c = 64 - r * V4 + lane;
                 while (c >= V4) { c -= V4; ++r; }
                 while (r < rows) {
@@ -908,6 +948,15 @@ ctc_lin_kernel(const PipeParams pp, int* __restrict__ flags) {
             float2 x[3];
 #pragma unroll
             for (int j = 0; j < 3; ++j) x[j] = act ? lg[j] : make_float2(0.f, 0.f);
+            unsigned mk = 0u;                  // fused Hardtanh: bit 2j / 2j+1 = gradient blocked
+            if (clp.on) {
+#pragma unroll
+                for (int j = 0; j < 3; ++j) {
+                    mk |= (clp.cmask(x[j].x) ? 1u : 0u) << (2 * j) | (clp.cmask(x[j].y) ? 1u : 0u) << (2 * j + 1);
+                    x[j].x = clp.cin(x[j].x);
+                    x[j].y = clp.cin(x[j].y);
+                }
+            }
             float m = fmaxf(fmaxf(fmaxf(x[0].x, x[0].y), fmaxf(x[1].x, x[1].y)), fmaxf(x[2].x, x[2].y));
             m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 4));
             m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 2));
@@ -930,7 +979,8 @@ ctc_lin_kernel(const PipeParams pp, int* __restrict__ flags) {
             if (act) {
 #pragma unroll
                 for (int j = 0; j < 3; ++j) {
-                    row2[glA + 8 * j] = make_float2(x[j].x * rs, x[j].y * rs);
+                    const float a = x[j].x * rs, c = x[j].y * rs;
+                    row2[glA + 8 * j] = make_float2((mk >> (2 * j)) & 1u ? -a : a, (mk >> (2 * j + 1)) & 1u ? -c : c);
                 }
                 if (glA == 0) row[V] = 0.f;     // what padding pairs gather
             }
@@ -945,6 +995,21 @@ ctc_lin_kernel(const PipeParams pp, int* __restrict__ flags) {
             const bool act = f < rows;
             float* row = base + min(f, rows - 1) * Vs;
             float2* row2 = reinterpret_cast<float2*>(row);
+            if (!al) {      // rows that are not 16-byte aligned in HBM (V % 4 != 0): scalar passes
+                float m = -CUDART_INF_F, z = 0.f;
+                for (int c = gl; c < V; c += G) m = fmaxf(m, clp.cin(row[c]));
+                m = group_max(m, G);
+                for (int c = gl; c < V; c += G) z += ex2f((clp.cin(row[c]) - m) * kLog2e);
+                const float rs = 1.0f / group_sum(z, G);
+                if (act) {
+                    for (int c = gl; c < V; c += G) {
+                        const float raw = row[c], y = ex2f((clp.cin(raw) - m) * kLog2e) * rs;
+                        row[c] = clp.cmask(raw) ? -y : y;
+                    }
+                    for (int c = V + gl; c < Vs; c += G) row[c] = 0.f;   // slot V: what padding pairs gather
+                }
+                return;
+            }
             if (G == 8 && V2 == 24) {      // V = 48, four frames per pass: straight-line code, no guards
                 float2 lg[3];
 #pragma unroll
@@ -955,10 +1020,16 @@ ctc_lin_kernel(const PipeParams pp, int* __restrict__ flags) {
             if (V2 <= 4 * G) {      // at most 4 float2 per lane: the row stays in registers
                 float2 x[4];
                 float m = -CUDART_INF_F;
+                unsigned mk = 0u;
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                     const int c = gl + j * G;
                     x[j] = c < V2 ? row2[c] : make_float2(-CUDART_INF_F, -CUDART_INF_F);
+                    if (clp.on && c < V2) {
+                        mk |= (clp.cmask(x[j].x) ? 1u : 0u) << (2 * j) | (clp.cmask(x[j].y) ? 1u : 0u) << (2 * j + 1);
+                        x[j].x = clp.cin(x[j].x);
+                        x[j].y = clp.cin(x[j].y);
+                    }
                     m = fmaxf(m, fmaxf(x[j].x, x[j].y));
                 }
                 asm volatile("redux.sync.max.f32 %0, %1, %2;" : "=f"(m) : "f"(m), "r"(gmask));
@@ -975,7 +1046,10 @@ ctc_lin_kernel(const PipeParams pp, int* __restrict__ flags) {
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
                         const int c = gl + j * G;
-                        if (c < V2) row2[c] = make_float2(x[j].x * rs, x[j].y * rs);
+                        if (c < V2) {
+                            const float a = x[j].x * rs, d = x[j].y * rs;
+                            row2[c] = make_float2((mk >> (2 * j)) & 1u ? -a : a, (mk >> (2 * j + 1)) & 1u ? -d : d);
+                        }
                     }
                 }
             } else if (YS == 0 && V4 <= 8 * G) {
@@ -985,10 +1059,17 @@ ctc_lin_kernel(const PipeParams pp, int* __restrict__ flags) {
                 float4* row4 = reinterpret_cast<float4*>(row);
                 float4 x[8];
                 float m = -CUDART_INF_F;
+                unsigned mk = 0u;
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
                     const int c = gl + j * G;
                     x[j] = c < V4 ? row4[c] : make_float4(-CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F);
+                    if (clp.on && c < V4) {
+                        mk |= ((clp.cmask(x[j].x) ? 1u : 0u) | (clp.cmask(x[j].y) ? 2u : 0u) |
+                               (clp.cmask(x[j].z) ? 4u : 0u) | (clp.cmask(x[j].w) ? 8u : 0u)) << (4 * j);
+                        x[j].x = clp.cin(x[j].x); x[j].y = clp.cin(x[j].y);
+                        x[j].z = clp.cin(x[j].z); x[j].w = clp.cin(x[j].w);
+                    }
                     m = fmaxf(m, fmaxf(fmaxf(x[j].x, x[j].y), fmaxf(x[j].z, x[j].w)));
                 }
                 m = group_max(m, G);
@@ -1008,28 +1089,30 @@ ctc_lin_kernel(const PipeParams pp, int* __restrict__ flags) {
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
                         const int c = gl + j * G;
-                        if (c < V4) row4[c] = make_float4(x[j].x * rs, x[j].y * rs, x[j].z * rs, x[j].w * rs);
+                        if (c < V4) {
+                            const unsigned q = mk >> (4 * j);
+                            const float a = x[j].x * rs, d = x[j].y * rs, e = x[j].z * rs, h = x[j].w * rs;
+                            row4[c] = make_float4(q & 1u ? -a : a, q & 2u ? -d : d, q & 4u ? -e : e, q & 8u ? -h : h);
+                        }
                     }
                 }
             } else {
                 float m = -CUDART_INF_F, z = 0.f;
                 for (int c = gl; c < V2; c += G) {
                     const float2 x = row2[c];
-                    m = fmaxf(m, fmaxf(x.x, x.y));
+                    m = fmaxf(m, fmaxf(clp.cin(x.x), clp.cin(x.y)));
                 }
                 asm volatile("redux.sync.max.f32 %0, %1, %2;" : "=f"(m) : "f"(m), "r"(gmask));
                 for (int c = gl; c < V2; c += G) {
-                    float2 x = row2[c];
-                    x.x = ex2f((x.x - m) * kLog2e);
-                    x.y = ex2f((x.y - m) * kLog2e);
-                    z += x.x + x.y;
-                    if (act) row2[c] = x;
+                    const float2 x = row2[c];
+                    z += ex2f((clp.cin(x.x) - m) * kLog2e) + ex2f((clp.cin(x.y) - m) * kLog2e);
                 }
                 const float rs = 1.0f / group_sum(z, G);
                 if (act)
                     for (int c = gl; c < V2; c += G) {
                         const float2 x = row2[c];
-                        row2[c] = make_float2(x.x * rs, x.y * rs);
+                        const float a = ex2f((clp.cin(x.x) - m) * kLog2e) * rs, d = ex2f((clp.cin(x.y) - m) * kLog2e) * rs;
+                        row2[c] = make_float2(clp.cmask(x.x) ? -a : a, clp.cmask(x.y) ? -d : d);
                     }
             }
             if (act && gl == 0) row[V] = 0.f;  // what padding pairs gather
@@ -1079,7 +1162,9 @@ ctc_lin_kernel(const PipeParams pp, int* __restrict__ flags) {
                 for (int j = 0; j < 3; ++j) {
                     const bool mine = cb == gl + 8 * j;
                     const float ox = o[j].x + (mine ? addx : 0.f), oy = o[j].y + (mine ? addy : 0.f);
-                    if (act) g2[gl + 8 * j] = make_float2(gscale * (y[j].x - ox), gscale * (y[j].y - oy));
+                    // (a set sign bit of y: the fused Hardtanh blocks this entry's gradient)
+                    if (act) g2[gl + 8 * j] = make_float2(__float_as_int(y[j].x) < 0 ? 0.f : gscale * (y[j].x - ox),
+                                                          __float_as_int(y[j].y) < 0 ? 0.f : gscale * (y[j].y - oy));
                 }
                 if (act && !(fabsf(tot + bs - 1.0f) <= kMassTol)) s_flag[0] = 1;   // NaN-safe
 #ifdef CTC_B200_MASSDEV
@@ -1089,7 +1174,7 @@ ctc_lin_kernel(const PipeParams pp, int* __restrict__ flags) {
             }
             float bs = 0.f;
             for (int i = gl; i < 32 * R; i += G) bs += orow[(i >> 5) * OW + VO + (i & 31)];
-            if (R == 1 && V2 <= 4 * G) {     // at most 4 float2 per lane: everything stays in registers
+            if (al && R == 1 && V2 <= 4 * G) {     // at most 4 float2 per lane: everything stays in registers
                 float2 o[4], y[4];
                 float tot = 0.f;
 #pragma unroll
@@ -1117,14 +1202,15 @@ ctc_lin_kernel(const PipeParams pp, int* __restrict__ flags) {
                         const int c = gl + j * G;
                         if (c < V2) {
                             if ((blank >> 1) == c) { if (blank & 1) o[j].y += bs; else o[j].x += bs; }
-                            g2[c] = make_float2(gscale * (y[j].x - o[j].x), gscale * (y[j].y - o[j].y));
+                            g2[c] = make_float2(__float_as_int(y[j].x) < 0 ? 0.f : gscale * (y[j].x - o[j].x),
+                                                __float_as_int(y[j].y) < 0 ? 0.f : gscale * (y[j].y - o[j].y));
                         }
                     }
                     if (!(fabsf(tot + bs - 1.0f) <= kMassTol)) s_flag[0] = 1;   // NaN-safe
                 }
                 return;
             }
-            if (YS == 0 && R == 1 && V4 <= 8 * G) {     // wide vocabulary: at most 8 x 128 bit per lane, all loads up front
+            if (al && YS == 0 && R == 1 && V4 <= 8 * G) {     // wide vocabulary: at most 8 x 128 bit per lane, all loads up front
                 uint4* o4 = reinterpret_cast<uint4*>(orow);
                 const float4* y4 = reinterpret_cast<const float4*>(y2);
                 float4* g4 = reinterpret_cast<float4*>(g2);
@@ -1168,8 +1254,10 @@ ctc_lin_kernel(const PipeParams pp, int* __restrict__ flags) {
                             o[j].y += (mine && kb == 1) ? bs : 0.f;
                             o[j].z += (mine && kb == 2) ? bs : 0.f;
                             o[j].w += (mine && kb == 3) ? bs : 0.f;
-                            g4[c] = make_float4(gscale * (y[j].x - o[j].x), gscale * (y[j].y - o[j].y),
-                                                gscale * (y[j].z - o[j].z), gscale * (y[j].w - o[j].w));
+                            g4[c] = make_float4(__float_as_int(y[j].x) < 0 ? 0.f : gscale * (y[j].x - o[j].x),
+                                                __float_as_int(y[j].y) < 0 ? 0.f : gscale * (y[j].y - o[j].y),
+                                                __float_as_int(y[j].z) < 0 ? 0.f : gscale * (y[j].z - o[j].z),
+                                                __float_as_int(y[j].w) < 0 ? 0.f : gscale * (y[j].w - o[j].w));
                         }
                     }
                     if (!(fabsf(tot + bs - 1.0f) <= kMassTol)) s_flag[0] = 1;   // NaN-safe
@@ -1181,6 +1269,28 @@ ctc_lin_kernel(const PipeParams pp, int* __restrict__ flags) {
             }
             bs = group_sum(bs, G);
             float tot = 0.f;
+            if (!al) {      // gradient rows that are not 16-byte aligned in HBM: scalar loads / stores
+                float* g1 = reinterpret_cast<float*>(g2);
+                const float* y1 = reinterpret_cast<const float*>(y2);
+                for (int c = gl; c < V; c += G) {
+                    float o = 0.f;
+                    for (int rw = 0; rw < R; ++rw) {
+                        unsigned* p1 = reinterpret_cast<unsigned*>(orow + rw * OW) + c;
+                        o += __uint2float_rn(*p1) * (1.0f / kQ31);
+                        if (act) *p1 = 0u;
+                    }
+                    tot += o;
+                    if (c == blank) o += bs;
+                    const float y = y1[c];
+                    if (act) g1[c] = __float_as_int(y) < 0 ? 0.f : gscale * (y - o);
+                }
+                tot = group_sum(tot, G) + bs;
+                if (act && !(fabsf(tot - 1.0f) <= kMassTol)) s_flag[0] = 1;   // NaN-safe
+#ifdef CTC_B200_MASSDEV
+                if (act) atomicMax(&s_flag[2], __float_as_int(fabsf(tot - 1.0f)));
+#endif
+                return;
+            }
             for (int c = gl; c < V2; c += G) {
                 float2 o = make_float2(0.f, 0.f);
                 for (int rw = 0; rw < R; ++rw) {
@@ -1195,7 +1305,8 @@ ctc_lin_kernel(const PipeParams pp, int* __restrict__ flags) {
                     if (blank & 1) o.y += bs; else o.x += bs;
                 }
                 const float2 y = y2[c];
-                if (act) g2[c] = make_float2(gscale * (y.x - o.x), gscale * (y.y - o.y));
+                if (act) g2[c] = make_float2(__float_as_int(y.x) < 0 ? 0.f : gscale * (y.x - o.x),
+                                             __float_as_int(y.y) < 0 ? 0.f : gscale * (y.y - o.y));
             }
             tot = group_sum(tot, G) + bs;
             if (act && !(fabsf(tot - 1.0f) <= kMassTol)) s_flag[0] = 1;   // NaN-safe
@@ -1273,6 +1384,12 @@ ctc_lin_kernel(const PipeParams pp, int* __restrict__ flags) {
 #else
     if (threadIdx.x == 0) flags[2 * b + (rev ? 1 : 0)] = s_flag[0];
 #endif
+    if (pp.queue == nullptr) break;
+    if (threadIdx.x == 0) {   // the barriers are initialised afresh for the next utterance
+        for (int i = 0; i < NL + NS; ++i)
+            asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(smem_u32(bar_acts + i)) : "memory");
+    }
+    }   // for (;;): next utterance of the queue
 }
 
 }  // namespace ctcb200

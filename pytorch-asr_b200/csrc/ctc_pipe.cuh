@@ -35,6 +35,8 @@ struct PipeParams {
     int rotate;    // CTAs per launch "layer" (= #SMs): co-resident CTAs rotate their warp roles
     const int* redo;  // [2 * N] or nullptr: run only utterances the linear kernel flagged (ctc_lin.cuh)
     int utt_rot;      // linear kernel: cluster c works on utterance (c + utt_rot) mod n_utt (CTA placement)
+    int* queue;       // linear kernel, persistent launch: {next utterance, clusters that ran dry}; nullptr: one cluster per utterance
+    int n_utt;        // utterances of this launch (queue mode)
 };
 
 // class-sorted label cell k lives at float index ypad(k) of the eY row: one float4 of
@@ -147,8 +149,9 @@ ctc_pipe_kernel(const PipeParams pp) {
     // (launched with programmatic stream serialization: wait for the linear kernel's flags)
     if (pp.redo != nullptr) asm volatile("griddepcontrol.wait;" ::: "memory");
     if (pp.redo != nullptr && (pp.redo[2 * b] | pp.redo[2 * b + 1]) == 0) return;
-    const int T = p.T, N = p.N, V = p.V, blank = p.blank;
+    const int T = p.T, V = p.V, blank = p.blank;
     const int RS = p.row_stride, TC = p.chunk, D = pp.D;
+    const Clamp clp{p.use_clamp != 0, p.clamp_lo, p.clamp_hi};
     const bool is_rec = w < R;
     const int hw = w - R;  // helper index (>= 0 for helpers)
 
@@ -176,9 +179,9 @@ ctc_pipe_kernel(const PipeParams pp) {
     const int32_t* tg = p.targets + p.tgt_off[b];
     const bool want_grad = p.grad != nullptr;
     const float gscale = p.grad_scale ? p.grad_scale[b] : 1.0f;
-    const size_t frame_stride = (size_t)N * V;
-    const float* acts_b = p.acts + (size_t)b * V;
-    float* grad_b = want_grad ? p.grad + (size_t)b * V : nullptr;
+    const size_t frame_stride = (size_t)p.frame_stride;
+    const float* acts_b = p.acts + (size_t)b * (size_t)p.utt_stride;
+    float* grad_b = want_grad ? p.grad + (size_t)b * (size_t)p.utt_stride : nullptr;
     const int V4 = V >> 2;
 
     // ---- helpers: mandatory zero fill of gradient rows t >= T_b (no compute) --------
@@ -636,31 +639,35 @@ ctc_pipe_kernel(const PipeParams pp) {
             if (V4 <= 16) {  // the whole row is one float4 per lane of the half-warp
                 float4 x = make_float4(-CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F);
                 if (q16 < V4) x = row4[q16];
+                const float4 raw = x;
+                x.x = clp.cin(x.x); x.y = clp.cin(x.y); x.z = clp.cin(x.z); x.w = clp.cin(x.w);
                 const float m = half_max(fmaxf(fmaxf(x.x, x.y), fmaxf(x.z, x.w)));
                 x.x = (x.x - m) * kLog2e; x.y = (x.y - m) * kLog2e;
                 x.z = (x.z - m) * kLog2e; x.w = (x.w - m) * kLog2e;
                 const float lz = lg2f(half_sum((ex2f(x.x) + ex2f(x.y)) + (ex2f(x.z) + ex2f(x.w))));
                 if (act && q16 < V4)
-                    row4[q16] = make_float4(fmaxf(x.x - lz, kNeg), fmaxf(x.y - lz, kNeg),
-                                            fmaxf(x.z - lz, kNeg), fmaxf(x.w - lz, kNeg));
+                    row4[q16] = make_float4(clp.tag(fmaxf(x.x - lz, kNeg), raw.x), clp.tag(fmaxf(x.y - lz, kNeg), raw.y),
+                                            clp.tag(fmaxf(x.z - lz, kNeg), raw.z), clp.tag(fmaxf(x.w - lz, kNeg), raw.w));
             } else {
                 float m = -CUDART_INF_F, z = 0.f;
                 for (int c = q16; c < V4; c += 16) {
                     const float4 x = row4[c];
-                    m = fmaxf(m, fmaxf(fmaxf(x.x, x.y), fmaxf(x.z, x.w)));
+                    m = fmaxf(m, fmaxf(fmaxf(clp.cin(x.x), clp.cin(x.y)), fmaxf(clp.cin(x.z), clp.cin(x.w))));
                 }
                 m = half_max(m);
                 for (int c = q16; c < V4; c += 16) {
                     const float4 x = row4[c];
-                    z += (ex2f((x.x - m) * kLog2e) + ex2f((x.y - m) * kLog2e)) +
-                         (ex2f((x.z - m) * kLog2e) + ex2f((x.w - m) * kLog2e));
+                    z += (ex2f((clp.cin(x.x) - m) * kLog2e) + ex2f((clp.cin(x.y) - m) * kLog2e)) +
+                         (ex2f((clp.cin(x.z) - m) * kLog2e) + ex2f((clp.cin(x.w) - m) * kLog2e));
                 }
                 const float lz = lg2f(half_sum(z));
                 if (act)
                     for (int c = q16; c < V4; c += 16) {
                         const float4 x = row4[c];
-                        row4[c] = make_float4(fmaxf((x.x - m) * kLog2e - lz, kNeg), fmaxf((x.y - m) * kLog2e - lz, kNeg),
-                                              fmaxf((x.z - m) * kLog2e - lz, kNeg), fmaxf((x.w - m) * kLog2e - lz, kNeg));
+                        row4[c] = make_float4(clp.tag(fmaxf((clp.cin(x.x) - m) * kLog2e - lz, kNeg), x.x),
+                                              clp.tag(fmaxf((clp.cin(x.y) - m) * kLog2e - lz, kNeg), x.y),
+                                              clp.tag(fmaxf((clp.cin(x.z) - m) * kLog2e - lz, kNeg), x.z),
+                                              clp.tag(fmaxf((clp.cin(x.w) - m) * kLog2e - lz, kNeg), x.w));
                     }
             }
             if (act && q16 == 0) row[V] = kNeg;  // what padding pairs gather
@@ -721,7 +728,8 @@ ctc_pipe_kernel(const PipeParams pp) {
                     const float hi = (k1 < S) ? eY[ypad(k1)] : carry;   // PS[S] = total
                     const float lo = (k0 < S) ? eY[ypad(k0)] : carry;
                     const float occ = (hi - lo) + (v == blank ? bs : 0.f);
-                    g[v] = gscale * (ex2f(lp2row[v]) - occ);
+                    const float lpv = lp2row[v];
+                    g[v] = clp.tagged(lpv) ? 0.0f : gscale * (ex2f(lpv) - occ);
                 }
         };
 

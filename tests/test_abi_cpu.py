@@ -32,7 +32,7 @@ def test_library_exports_every_declared_symbol():
 
 def test_version_and_status_strings():
     lib = cabi.load()
-    assert lib.ctc_b200_version() >= 1000
+    assert lib.ctc_b200_version() >= 2000
     seen = {lib.ctc_b200_status_string(i).decode() for i in range(8)}
     assert len(seen) == 8 and "ok" in seen
     assert lib.ctc_b200_status_string(99).decode() == "unknown status"
@@ -51,7 +51,10 @@ def test_geometry_and_workspace():
     assert 32 * g3["rec_warps"] * g3["pairs_per_thread"] >= 801 + 7 and g3["smem_bytes"] <= 227 * 1024
     assert cabi.geometry(100, 1, 48, 1500)["threads"] <= 1024
     assert cabi.geometry(100, 1, 48, 4095)["pairs_per_thread"] in (4, 8)
-    assert cabi.geometry(100, 4, 177, 30)["kernel"] == 0           # V % 4 != 0: generic kernel
+    g177 = cabi.geometry(750, 64, 177, 100)         # the reference's own vocabulary (params.py:27), V % 4 != 0
+    assert g177["kernel"] == 2 and g177["fallback_kernel"] == 0 and g177["variant_name"] == "ctc_lin_kernel<8,1,0,128,4>"
+    assert g["variant_name"] == "ctc_lin_kernel<8,1,80,128,4,FIX>" and g["fallback_kernel"] == 1
+    assert g3["variant_name"] == "ctc_lin_kernel<8,4,80,512,1>"
     with pytest.raises(cabi.CtcB200Error) as e:
         cabi.geometry(100, 1, 48, 4096)
     assert e.value.status == cabi.UNSUPPORTED

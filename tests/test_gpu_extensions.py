@@ -1,0 +1,220 @@
+"""GPU tests of the rows SURVEY.md section 8(f) lists next to the loss call:
+(1) batch-major logits / gradient, (2) fused Hardtanh + LogSoftmax, (3) the trainer's post-loss host
+checks as one device->host read, (4) greedy decode + label error rate for `validate` -- each against
+the reference's own code path run on the CPU (torch) or a plain Python restatement of it.
+Plus the autograd / hook semantics VERDICT r01 asked for."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+import oracle
+from pytorch_asr_b200 import CTCLoss, cabi, decode, synth
+
+pytestmark = pytest.mark.gpu
+
+
+def _ref_head_and_loss(raw_ntv, tg, il, tl, clamp=None):
+    """The reference's path from the FC output to the loss, on the CPU:
+    Hardtanh(-50,50) (network.py:370) -> LogSoftmax (:375,395) -> transpose(0,1).contiguous()
+    (trainer.py:418) -> nn.CTCLoss (trainer.py:153,422) -> backward (:438)."""
+    x = raw_ntv.clone().requires_grad_(True)
+    h = F.hardtanh(x, clamp[0], clamp[1]) if clamp else x
+    lp = F.log_softmax(h, -1).transpose(0, 1).contiguous()
+    loss = torch.nn.CTCLoss(blank=0, reduction="mean")(lp, tg, il, tl)
+    loss.backward()
+    return float(loss), x.grad
+
+
+@pytest.mark.parametrize("V,clamp", [(48, None), (48, (-50.0, 50.0)), (177, (-50.0, 50.0)), (1024, (-2.5, 2.5))])
+def test_module_batch_major_and_fused_head(V, clamp):
+    """8(f)1 + 8(f)2 through the nn.Module: the model hands over its raw [N,T,V] FC output; loss and
+    the gradient w.r.t. that tensor equal the reference's Hardtanh -> LogSoftmax -> transpose -> CTC."""
+    acts, tg, il, tl = synth.make_batch(6, 150, V, 30, seed=60 + V)
+    raw = (acts * (20.0 if clamp and clamp[1] == 50.0 else 1.5)).transpose(0, 1).contiguous()   # [N,T,V]
+    ref_loss, ref_grad = _ref_head_and_loss(raw, tg, il, tl, clamp)
+    x = raw.cuda().requires_grad_(True)
+    crit = CTCLoss(blank=0, reduction="mean", batch_major=True, clamp=clamp)
+    loss = crit(x, tg, il, tl)
+    loss.backward()
+    assert x.grad.shape == x.shape and x.grad.is_contiguous()
+    assert abs(float(loss) - ref_loss) <= 1e-5 * abs(ref_loss)
+    assert (x.grad.cpu() - ref_grad).abs().max() <= 1e-4
+    if clamp:
+        blocked = ~((raw > clamp[0]) & (raw < clamp[1]))
+        assert blocked.any() and not x.grad.cpu()[blocked].any()
+    # ... and the time-major call on the transposed tensor gives the same numbers bit for bit
+    x2 = raw.transpose(0, 1).contiguous().cuda().requires_grad_(True)
+    loss2 = CTCLoss(blank=0, reduction="mean", clamp=clamp)(x2, tg, il, tl)
+    loss2.backward()
+    assert float(loss2) == float(loss)
+    assert torch.equal(x2.grad.transpose(0, 1), x.grad)
+
+
+def _unit_train_reference(loss, frame_lens, label_lens):
+    """trainer.py:423-430, verbatim control flow (three device->host syncs)."""
+    if torch.isnan(loss) or loss.item() == float("inf") or loss.item() == -float("inf"):
+        return None
+    if frame_lens.cpu().lt(2 * label_lens).nonzero().numel():
+        loss.mul_(0)
+    return loss.item()
+
+
+@pytest.mark.parametrize("case", ["ok", "short", "inf"])
+def test_post_loss_checks_with_one_sync(case):
+    """8(f)3: `status()` returns, with ONE device->host read, what trainer.py:423-430 derives with
+    isnan + .item() + a host-side length comparison; zero_on_short applies loss.mul_(0) on the device."""
+    acts, tg, il, tl = synth.make_batch(5, 80, 48, 16, seed=71)
+    if case == "short":
+        il = il.clone(); il[3] = 2 * int(tl[3]) - 1          # feasible, but T_b < 2 S_b
+    if case == "inf":
+        il = il.clone(); il[2] = int(tl[2]) - 1              # infeasible: nll = +inf
+    il[0] = 80
+    # the reference
+    xr = acts.cuda().requires_grad_(True)
+    lr = torch.nn.CTCLoss(blank=0, reduction="mean")(F.log_softmax(xr, -1), tg, il, tl)
+    want = _unit_train_reference(lr, il, tl)
+    if want is not None:
+        lr.backward()
+    # the engine: one read
+    x = acts.cuda().requires_grad_(True)
+    crit = CTCLoss(blank=0, reduction="mean", zero_on_short=True)
+    loss = crit(x, tg, il, tl)
+    st = crit.status()
+    if want is None:
+        assert st["nan"] or st["inf"]
+        return
+    assert not (st["nan"] or st["inf"])
+    assert st["short"] == (case == "short") and st["n_short"] == (1 if case == "short" else 0)
+    assert abs(st["loss"] - want) <= 1e-5 * max(abs(want), 1e-30)
+    assert st["factor"] == (0.0 if case == "short" else 1.0)
+    loss.backward()
+    assert (x.grad - xr.grad).abs().max() <= 1e-4
+    if case == "short":
+        assert st["loss"] == 0.0 and float(loss) == 0.0 and not x.grad.any()
+
+
+def test_retain_graph_second_backward_and_legacy_hook():
+    """nn.CTCLoss allows backward twice over a retained graph; deepspeech_var registers the LEGACY
+    module backward hook and zeroes NaNs of grad_input in place (deepspeech_var/train.py:24-33)."""
+    acts, tg, il, tl = synth.make_batch(4, 60, 48, 12, seed=81)
+    x = acts.cuda().requires_grad_(True)
+    loss = CTCLoss()(x, tg, il, tl)
+    loss.backward(retain_graph=True)
+    g1 = x.grad.clone()
+    loss.backward()
+    assert torch.allclose(x.grad, 2 * g1, rtol=1e-6, atol=0)
+    xr = acts.clone().requires_grad_(True)
+    lr = torch.nn.CTCLoss()(F.log_softmax(xr, -1), tg, il, tl)
+    lr.backward(retain_graph=True); lr.backward()
+    assert (x.grad.cpu() - xr.grad).abs().max() <= 2e-4
+
+    # infeasible utterance -> NaN gradient rows (as torch); the hook of deepspeech_var zeroes them in place
+    il2 = il.clone(); il2[1] = int(tl[1]) - 1
+    crit = CTCLoss()
+    calls = []
+
+    def backward_hook(module, grad_input, grad_output):       # deepspeech_var/train.py:24-31
+        calls.append(1)
+        for g in grad_input:
+            if g is not None:
+                g[g != g] = 0
+
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        crit.register_backward_hook(backward_hook)
+    x2 = acts.cuda().requires_grad_(True)
+    y = x2 * 1.0                                              # non-leaf input, as the model output is
+    l2 = crit(y, tg, il2, tl)
+    assert float(l2) == float("inf")
+    l2.backward()
+    assert calls
+    assert torch.isfinite(x2.grad).all() or torch.isnan(x2.grad[:, 1]).all()   # hook semantics differ by torch version
+    assert torch.isfinite(x2.grad[:, [0, 2, 3]]).all()
+
+
+def test_cuda_resident_bad_label_is_reported():
+    """CUDA-resident targets cannot be validated on the host: the device-side check must surface."""
+    acts, tg, il, tl = synth.make_batch(3, 40, 16, 6, seed=83)
+    bad = tg.clone(); bad[2] = 99
+    with pytest.raises(RuntimeError, match="label"):
+        CTCLoss()(acts.cuda(), bad.cuda(), il, tl)
+
+
+def _py_decode(acts_ntv, il, blank=0):
+    """unit_validate (trainer.py:450-463): onehot2int + remove_duplicates(blank=0) (misc.py:44-51,78-84)."""
+    hyps = []
+    for yh, s in zip(acts_ntv, il.tolist()):
+        idx = yh[:s].argmax(-1).tolist()
+        p, out = -1, []
+        for c in idx:
+            if c != p:
+                p = c
+                if c != blank:
+                    out.append(c)
+        hyps.append(out)
+    return hyps
+
+
+def _py_edit_distance(r, h):
+    """Levenshtein distance with unit costs (what Lev.distance returns, trainer.py:336-343)."""
+    d = list(range(len(h) + 1))
+    for i in range(1, len(r) + 1):
+        prev, d[0] = d[0], i
+        for j in range(1, len(h) + 1):
+            cur = min(d[j] + 1, d[j - 1] + 1, prev + (r[i - 1] != h[j - 1]))
+            prev, d[j] = d[j], cur
+    return d[len(h)]
+
+
+@pytest.mark.parametrize("B,T,V,S,batch_major", [(8, 300, 48, 60, True), (5, 257, 177, 40, True),
+                                                 (4, 1100, 48, 200, False), (3, 64, 1024, 10, True)])
+def test_greedy_decode_and_ler(B, T, V, S, batch_major):
+    """8(f)4: arg-max -> collapse -> drop blanks -> edit distance, bit-exact against the reference's
+    Python loops (integer work: no tolerance)."""
+    acts, tg, il, tl = synth.make_batch(B, T, V, S, seed=90 + V, peaky=True)
+    # make the hypotheses resemble the targets: push the target labels up along a rough alignment
+    offs = torch.cat([torch.zeros(1, dtype=torch.int64), tl.long().cumsum(0)])
+    for b in range(B):
+        Tb, Sb = int(il[b]), int(tl[b])
+        for k in range(Sb):
+            t = int((k + 0.5) * Tb / max(Sb, 1))
+            if (k + b) % 7:                       # leave some labels out: deletions
+                acts[t, b, int(tg[offs[b] + k])] += 30.0
+    a_ntv = acts.transpose(0, 1).contiguous()
+    hyps = _py_decode(a_ntv, il)
+    refs = [tg[offs[b]:offs[b + 1]].tolist() for b in range(B)]
+    want = [_py_edit_distance(r, h) for r, h in zip(refs, hyps)]
+    dev = (a_ntv if batch_major else acts.contiguous()).cuda()
+    out = decode.greedy_decode_ler(dev, il, tg, tl, blank=0, batch_major=batch_major)
+    torch.cuda.synchronize()
+    hl = out["hyp_len"].cpu().tolist()
+    assert hl == [len(h) for h in hyps]
+    hyp = out["hyp"].cpu()
+    for b in range(B):
+        assert hyp[b, :hl[b]].tolist() == hyps[b]
+    assert out["dist"].cpu().tolist() == want
+    tot = out["totals"].cpu().tolist()
+    assert tot == [sum(want), int(tl.sum())]
+    assert abs(decode.ler_percent(out) - 100.0 * sum(want) / int(tl.sum())) < 1e-9
+    assert sum(want) > 0 and sum(want) < int(tl.sum())        # a non-trivial error rate
+
+
+def test_decode_edge_cases():
+    """T_b = 0, all-blank rows, ties (lowest index wins), empty references, hypotheses longer than a tile."""
+    T, V = 600, 8
+    acts = torch.full((4, T, V), -1.0)
+    acts[0, :, 0] = 1.0                                  # all blank -> empty hypothesis
+    acts[1, torch.arange(T), (torch.arange(T) % 7) + 1] = 1.0   # 600 distinct-neighbour labels, no blanks
+    acts[2, :, 3] = 1.0; acts[2, :, 5] = 1.0             # tie between 3 and 5 -> 3, collapsed to one label
+    il = torch.tensor([T, T, 17, 0], dtype=torch.int32)
+    tl = torch.tensor([0, 3, 1, 2], dtype=torch.int32)
+    tg = torch.tensor([1, 2, 3, 3, 6, 6], dtype=torch.int32)
+    out = decode.greedy_decode_ler(acts.cuda(), il, tg, tl, blank=0, batch_major=True)
+    assert out["hyp_len"].cpu().tolist() == [0, T, 1, 0]
+    assert out["hyp"][1].cpu().tolist() == [(t % 7) + 1 for t in range(T)]
+    assert int(out["hyp"][2, 0]) == 3
+    refs = [[], [1, 2, 3], [3], [6, 6]]
+    hyps = [[], [(t % 7) + 1 for t in range(T)], [3], []]
+    assert out["dist"].cpu().tolist() == [_py_edit_distance(r, h) for r, h in zip(refs, hyps)]

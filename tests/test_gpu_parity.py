@@ -6,11 +6,12 @@
        trainer.py:153,422,438), and
   (3) the fp64 C oracle (oracle/ctc_oracle.c).
 
-Tolerances (BASELINE.json north_star): per-utterance loss relative 1e-5,
-gradient absolute 1e-4.  The gradient bound is checked on the reduction='mean'
+Tolerances (BASELINE.json north_star), FLAT at every length: per-utterance loss relative
+1e-5, gradient absolute 1e-4.  The gradient bound is checked on the reduction='mean'
 gradient the reference actually produces AND, much stricter, on the UNSCALED
-(reduction='sum') gradient against the fp64 oracle, where torch's own fp32 path is
-up to ~2e-3 away from fp64 at T=1000 (it is compared with that documented slack).
+(reduction='sum') gradient against the fp64 oracle (measured: 1e-6 ... 7e-5).  torch's own
+fp32 path is up to 4e-2 away from fp64 on the unscaled gradient at T=4000; where the engine
+is compared with torch fp32 the bound is 1e-4 plus torch's own measured distance from fp64.
 """
 import math
 
@@ -28,12 +29,9 @@ GRAD_ATOL = 1e-4     # north_star: absolute 1e-4 on gradients
 
 
 def grad_atol_fp64(T):
-    """Bound on the UNSCALED (reduction='sum') gradient against the fp64 oracle.  fp32
-    log-domain rounding is a random walk over the T recursion steps, so the bound grows
-    with sqrt(T): 1e-4 up to T=250, 2e-4 at T=1000, 4e-4 at T=4000.  (torch's own fp32
-    path, which carries un-normalised log-alphas of magnitude ~T, measures 1e-3 / 3e-3 /
-    4e-2 at those lengths -- see test_c1_unscaled_gradient_vs_fp64.)"""
-    return GRAD_ATOL * max(1.0, (T / 250.0) ** 0.5)
+    """Bound on the UNSCALED (reduction='sum') gradient against the fp64 oracle: the north_star's
+    1e-4 absolute at every length (no slack for long utterances)."""
+    return GRAD_ATOL
 
 
 def run_engine(acts, tg, il, tl, blank=0, reduction="sum", zero_infinity=False, want_grad=True):
@@ -125,11 +123,11 @@ def test_reference_call_convention_mean():
     ref = oracle.torch_reference(acts, tg, il, tl, reduction="mean")
     assert abs(loss - float(ref["loss"])) <= NLL_RTOL * abs(float(ref["loss"]))
     assert_parity(nll, grad, ref["nll"].numpy(), ref["grad"].numpy(), what="C1 mean")
-    # the 1e-4 absolute bound is loose for a gradient scaled by 1/(N*S): also demand
-    # 2e-2 relative to the largest reference entry of each utterance
-    g_ref = ref["grad"].numpy()
-    scale = np.abs(g_ref).max(axis=(0, 2), keepdims=True)
-    assert (np.abs(grad - g_ref) / scale).max() < 2e-2
+    # the 1e-4 absolute bound is loose for a gradient scaled by 1/(N*S) (entries ~1e-4): the same
+    # gradient, unscaled, must meet 1e-4 against the fp64 oracle -- i.e. ~3e-8 on this scale
+    orc = oracle.ctc_oracle_f64(acts.numpy(), tg.numpy(), il.numpy(), tl.numpy())
+    scale = (1.0 / (acts.shape[1] * np.maximum(tl.numpy(), 1))).astype(np.float64).reshape(1, -1, 1)
+    assert np.abs(grad - orc["grad"] * scale).max() <= GRAD_ATOL * scale.max()
 
 
 def test_c1_unscaled_gradient_vs_fp64():
@@ -186,7 +184,7 @@ def test_fallback_on_saturated_logits():
     torch.cuda.synchronize()
     prob.check_status()
     if cabi.geometry(T, B, V, prob.S_max)["kernel"] == 2:
-        flags = prob.ws[256:256 + 8 * B].view(torch.int32).view(-1, 2).cpu()
+        flags = prob.flags_view().cpu()
         assert int((flags.sum(1) > 0).sum()) >= 1          # the safety net was exercised
     orc = oracle.ctc_oracle_f64(acts.numpy(), tg.numpy(), il.numpy(), tl.numpy())
     assert_parity(prob.nll.cpu().numpy(), prob.grad.cpu().numpy(), orc["nll"], orc["grad"],
@@ -240,9 +238,11 @@ def test_forward_only_matches():
     acts, tg, il, tl = synth.make_batch(5, 90, 48, 18, seed=5, repeat_frac=0.2)
     nll_g, _, _ = run_engine(acts, tg, il, tl)
     nll_f, _, loss = run_engine(acts, tg, il, tl, want_grad=False)
-    # same arithmetic in both modes; an utterance whose posterior-mass check (gradient mode only)
-    # hands it to the log-domain fallback may differ in the last bits
-    np.testing.assert_allclose(nll_g, nll_f, rtol=1e-6)
+    # forward-only calls run the log-domain kernel (no posterior-mass check without a gradient pass):
+    # both modes meet the north_star tolerance against the fp64 oracle
+    orc = oracle.ctc_oracle_f64(acts.numpy(), tg.numpy(), il.numpy(), tl.numpy())
+    np.testing.assert_allclose(nll_g, orc["nll"], rtol=NLL_RTOL)
+    np.testing.assert_allclose(nll_f, orc["nll"], rtol=NLL_RTOL)
 
 
 def test_long_target_multiple_pairs_per_thread():
@@ -281,7 +281,7 @@ def test_properties_at_full_size():
     prob2.run()
     torch.cuda.synchronize()
     assert ((prob2.nll.cpu() - nll).abs() / nll.abs()).max() < 1e-5
-    assert (prob2.grad.cpu() - grad).abs().max() < 4e-4
+    assert (prob2.grad.cpu() - grad).abs().max() < 2e-4   # two independent fp32 evaluations, 1e-4 each
     # batch-permutation equivariance + parity with the fp64 oracle on 8 utterances
     sel = [0, 17, 64, 100, 128, 200, 254, 255]
     offs = torch.cat([torch.zeros(1, dtype=torch.int64), tl.long().cumsum(0)])

@@ -1,0 +1,181 @@
+"""One GPU parity test per kernel instantiation ("next round" item 1).
+
+`ctc_b200_get_geometry` reports which template instantiation a problem size launches
+(`variant_name`); every branch of the launchers in csrc/ctc_launch_lin.cu / ctc_launch_log.cu that
+the default configuration can reach is exercised here on the committed tree, through the C ABI,
+and compared with the fp64 oracle at FLAT tolerances: per-utterance nll relative 1e-5, UNSCALED
+gradient absolute 1e-4 (semantics: trainer.py:422,438).  Also covered: the log-domain kernels
+behind CTC_B200_KERNEL (they are the per-utterance fallback of the linear kernel; they are forced here
+through saturated logits), the persistent-queue launch, and the strided (batch-major) / clamped forms of
+every linear instantiation.
+"""
+import numpy as np
+import pytest
+import torch
+
+import oracle
+from pytorch_asr_b200 import cabi, synth
+
+pytestmark = pytest.mark.gpu
+
+NLL_RTOL, GRAD_ATOL = 1e-5, 1e-4
+
+
+def _check(prob, acts, tg, il, tl, what, grad_scale=None):
+    torch.cuda.synchronize()
+    prob.check_status()
+    orc = oracle.ctc_oracle_f64(acts.numpy(), tg.numpy(), il.numpy(), tl.numpy())
+    nll = prob.nll.cpu().numpy().astype(np.float64)
+    fin = np.isfinite(orc["nll"])
+    assert np.array_equal(np.isfinite(nll), fin), what
+    rel = np.abs(nll[fin] - orc["nll"][fin]) / np.maximum(np.abs(orc["nll"][fin]), 1e-30)
+    assert rel.max() <= NLL_RTOL, (what, rel.max())
+    g = prob.grad.cpu().numpy()
+    if prob.layout == cabi.LAYOUT_NTV:
+        g = g.transpose(1, 0, 2)
+    assert not np.isnan(g[:, fin]).any(), what
+    err = np.abs(g[:, fin] - orc["grad"][:, fin]).max()
+    assert err <= GRAD_ATOL, (what, err)
+    for b in range(acts.shape[1]):          # rows t >= T_b: exact zeros, written by the kernel
+        assert not g[int(il[b]):, b].any(), what
+    return rel.max(), err
+
+
+# (B, T, V, S, fixed lengths, expected instantiation)
+LIN_CASES = [
+    (6, 200, 48, 40, False, "ctc_lin_kernel<8,1,80,128,4,FIX>"),       # C1 / C2 / C5 shape class
+    (4, 1000, 48, 200, False, "ctc_lin_kernel<8,1,80,128,4,FIX>"),     # C2 slice at full length
+    (5, 150, 32, 30, False, "ctc_lin_kernel<8,1,80,128,4>"),           # V <= 60, not 48
+    (5, 150, 60, 30, False, "ctc_lin_kernel<8,1,80,128,4>"),
+    (4, 160, 128, 30, False, "ctc_lin_kernel<8,1,0,128,4>"),           # 60 < V <= 256
+    (4, 750, 177, 100, False, "ctc_lin_kernel<8,1,0,128,4>"),          # the reference's real shape (params.py:27)
+    (4, 120, 29, 20, False, "ctc_lin_kernel<8,1,0,128,4>"),            # characters + blank: V % 4 != 0, V < 60
+    (8, 1000, 1024, 200, False, "ctc_lin_kernel<8,1,0,256,2>"),        # C4 slice at full size
+    (80, 120, 1024, 20, False, "ctc_lin_kernel<8,1,0,256,2>"),         # C4's geometry: >= 75 utterances -> chunks of 2 frames
+    (4, 700, 48, 300, False, "ctc_lin_kernel<8,2,80,512,1>"),          # two recursion warps
+    (4, 4000, 48, 800, True, "ctc_lin_kernel<8,4,80,512,1>"),          # C3 slice: B=4 of T=4000, S=800
+    (3, 700, 128, 300, False, "ctc_lin_kernel<8,0,0,256,2>"),          # run-time strides, R = 2
+    (2, 1500, 48, 600, False, "ctc_lin_kernel<8,0,0,512,1>"),          # R = 3 (no fixed-stride instantiation)
+    (2, 2600, 12, 1200, True, "ctc_lin_kernel<8,0,0,512,1>"),          # R = 5, one combine group
+    (2, 4400, 20, 2000, True, "ctc_lin_kernel<8,0,0,1024,1>"),         # R = 8
+]
+
+
+@pytest.mark.parametrize("B,T,V,S,fixed,variant", LIN_CASES)
+def test_linear_kernel_instantiation(B, T, V, S, fixed, variant):
+    acts, tg, il, tl = synth.make_batch(B, T, V, S, seed=100 + V + S, fixed_lengths=fixed, repeat_frac=0.15)
+    geo = cabi.geometry(T, B, V, int(tl.max()))
+    assert geo["kernel"] == 2 and geo["variant_name"] == variant, geo
+    if B == 80:
+        assert geo["chunk"] == 2, geo
+    prob = cabi.DeviceProblem(acts, tg, il, tl, reduction="sum")
+    prob.grad.fill_(float("nan"))
+    prob.run()
+    rel, err = _check(prob, acts, tg, il, tl, variant)
+    assert int(prob.flags_view().abs().sum()) == 0, "N(0,1) logits must not need the fallback"
+    print(f"{variant}: nll rel {rel:.2e}, unscaled grad abs {err:.2e}")
+
+
+@pytest.mark.parametrize("B,T,V,S,fixed,variant", [c for c in LIN_CASES if c[1] <= 1500])
+def test_linear_kernel_batch_major_and_clamp(B, T, V, S, fixed, variant):
+    """The same instantiations with [N,T,V] strides and the fused Hardtanh (8(f)2):
+    logits scaled so that a few per cent of them leave (-3, 3); the gradient is with respect to the raw
+    logits, i.e. 0 where Hardtanh's backward blocks it."""
+    acts, tg, il, tl = synth.make_batch(B, T, V, S, seed=200 + V + S, fixed_lengths=fixed)
+    acts = acts * 1.5
+    lo, hi = -3.0, 3.0
+    prob = cabi.DeviceProblem(acts.transpose(0, 1).contiguous(), tg, il, tl, reduction="sum",
+                              batch_major=True, clamp=(lo, hi))
+    prob.grad.fill_(float("nan"))
+    prob.run()
+    torch.cuda.synchronize()
+    prob.check_status()
+    clamped = acts.clamp(lo, hi)
+    orc = oracle.ctc_oracle_f64(clamped.numpy(), tg.numpy(), il.numpy(), tl.numpy())
+    mask = ((acts > lo) & (acts < hi)).numpy()
+    assert 0.001 < 1.0 - mask.mean() < 0.2
+    want = orc["grad"] * mask
+    g = prob.grad.cpu().numpy().transpose(1, 0, 2)
+    nll = prob.nll.cpu().numpy()
+    assert (np.abs(nll - orc["nll"]) / np.abs(orc["nll"])).max() <= NLL_RTOL
+    assert np.abs(g - want).max() <= GRAD_ATOL
+    assert not g[~mask].any()               # blocked entries are exact zeros
+
+
+@pytest.mark.parametrize("B,T,V,S,kernel_char", [
+    (6, 200, 48, 40, "pipe"),          # fallback of the V % 4 == 0 shapes: ctc_pipe_kernel
+    (4, 300, 177, 60, "generic"),      # fallback of V % 4 != 0: ctc_fused_kernel with the redo flags
+    (3, 700, 48, 300, "pipe"),
+    (2, 300, 1024, 40, "pipe"),
+])
+def test_log_domain_fallback_kernels(B, T, V, S, kernel_char):
+    """Hardtanh-saturated logits (every entry +-50, network.py:370) underflow the probability-domain
+    recursion: every utterance must be flagged and recomputed by the log-domain kernel of its shape
+    class, to the same tolerances."""
+    g = torch.Generator().manual_seed(11 + V)
+    acts = torch.where(torch.rand(T, B, V, generator=g) < 0.5, 50.0, -50.0)
+    _, tg, il, tl = synth.make_batch(B, T, V, S, seed=3 + V)
+    geo = cabi.geometry(T, B, V, int(tl.max()))
+    assert geo["kernel"] == 2 and geo["fallback_kernel"] == (1 if kernel_char == "pipe" else 0)
+    prob = cabi.DeviceProblem(acts, tg, il, tl, reduction="sum")
+    prob.grad.fill_(float("nan"))
+    prob.run()
+    torch.cuda.synchronize()
+    assert int((prob.flags_view().cpu().sum(1) > 0).sum()) >= 1
+    _check(prob, acts, tg, il, tl, f"fallback {kernel_char}")
+
+
+def test_forward_only_is_safe_on_saturated_logits():
+    """without a gradient there is no posterior-mass check, so forward-only calls take the
+    log-domain kernel; saturated and peaky logits give the fp64 oracle's nll."""
+    g = torch.Generator().manual_seed(5)
+    B, T, V, S = 6, 120, 48, 20
+    sat = torch.where(torch.rand(T, B, V, generator=g) < 0.5, 50.0, -50.0)
+    peaky, tg, il, tl = synth.make_batch(B, T, V, S, seed=8, peaky=True)
+    for acts in (sat, peaky):
+        prob = cabi.DeviceProblem(acts, tg, il, tl, reduction="sum")
+        prob.run(want_grad=False)
+        torch.cuda.synchronize()
+        prob.check_status()
+        orc = oracle.ctc_oracle_f64(acts.numpy(), tg.numpy(), il.numpy(), tl.numpy())
+        nll = prob.nll.cpu().numpy()
+        assert (np.abs(nll - orc["nll"]) / np.abs(orc["nll"])).max() <= NLL_RTOL
+
+
+def test_persistent_queue_launch():
+    """More utterances than co-resident clusters: the launch is persistent, clusters pull utterances from
+    the device-side queue; same results as the one-cluster-per-utterance launch of every utterance
+    alone, twice in a row on the same workspace (the queue re-arms itself)."""
+    B, T, V, S = 700, 96, 48, 16
+    acts, tg, il, tl = synth.make_batch(B, T, V, S, seed=77)
+    geo = cabi.geometry(T, B, V, int(tl.max()))
+    assert geo["kernel"] == 2 and geo["persistent"] == 1, geo
+    prob = cabi.DeviceProblem(acts, tg, il, tl, reduction="sum")
+    for rep in range(2):
+        prob.grad.fill_(float("nan"))
+        prob.nll.fill_(float("nan"))
+        prob.run()
+        torch.cuda.synchronize()
+        prob.check_status()
+        q = prob.ws[16:24].view(torch.int32).cpu().tolist()
+        assert q == [0, 0], q                    # re-armed by the last cluster
+        nll, grad = prob.nll.cpu().numpy(), prob.grad.cpu().numpy()
+        assert np.isfinite(nll).all() and np.isfinite(grad).all()
+    sel = [0, 1, 295, 296, 297, 400, 591, 592, 698, 699]
+    offs = torch.cat([torch.zeros(1, dtype=torch.int64), tl.long().cumsum(0)])
+    sub_t = torch.cat([tg[offs[b]:offs[b + 1]] for b in sel])
+    sub = (acts[:, sel].contiguous(), sub_t, il[sel].contiguous(), tl[sel].contiguous())
+    orc = oracle.ctc_oracle_f64(sub[0].numpy(), sub[1].numpy(), sub[2].numpy(), sub[3].numpy())
+    assert (np.abs(nll[sel] - orc["nll"]) / np.abs(orc["nll"])).max() <= NLL_RTOL
+    assert np.abs(grad[:, sel] - orc["grad"]).max() <= GRAD_ATOL
+    # the whole batch against the one-wave launch of its two halves (bit-identical: same kernel, same data)
+    for lo, hi in ((0, 280), (280, 560), (560, 700)):
+        idx = list(range(lo, hi))
+        st = torch.cat([tg[offs[b]:offs[b + 1]] for b in idx])
+        p2 = cabi.DeviceProblem(acts[:, lo:hi].contiguous(), st, il[lo:hi].contiguous(), tl[lo:hi].contiguous(),
+                                reduction="sum")
+        assert cabi.geometry(T, hi - lo, V, p2.S_max)["persistent"] == 0
+        p2.run()
+        torch.cuda.synchronize()
+        assert np.array_equal(p2.nll.cpu().numpy(), nll[lo:hi])
+        assert np.array_equal(p2.grad.cpu().numpy(), grad[:, lo:hi])
