@@ -7,7 +7,9 @@ A "step" is one pass of the hot path (fused log_softmax + CTC forward + gradient
 w.r.t. the logits + loss reduction) over one synthetic batch.  N=1 runs
 BASELINE.json configs[1] (C2: B=256, T=1000, V=48, variable lengths); N>1 runs one
 such batch per GPU (utterance-sharded, weak scaling) plus the path's only
-collective, the NCCL all-reduce of the (loss sum, count) pair.
+collective, the all-reduce of the (loss sum, count) pair, issued off the critical path.
+Next to the headline the line carries a `c5` block: BASELINE.json configs[4] (ONE batch of
+4096 utterances dealt over the N ranks, strong scaling).
 
 Prints ONE JSON line (rank 0).  Keys are documented in DESIGN.md section "Measurement".
 """
@@ -103,55 +105,273 @@ class ClockSampler:
                 "reasons": sorted(self.reasons), "samples": len(s)}
 
 
-def cpu_reference_pass(acts, tg, il, tl):
-    """The reference's own CPU implementation of the path (trainer.py:153,422,438)."""
+def cpu_reference_pass(acts, tg, il, tl, ctc_only=False):
+    """The reference's own CPU implementation of the path (trainer.py:153,422,438).
+    ctc_only: the loss on ready-made log-probs (figure (ii))."""
     import torch
     import torch.nn.functional as F
     x = acts.clone().requires_grad_(True)
     t0 = time.perf_counter()
-    lp = F.log_softmax(x, -1)
+    lp = x if ctc_only else F.log_softmax(x, -1)
     loss = torch.nn.CTCLoss(blank=0, reduction="mean")(lp, tg, il, tl)
     loss.backward()
-    return time.perf_counter() - t0, float(loss)
+    return time.perf_counter() - t0, float(loss.detach())
 
 
-def time_cpu_reference(acts, tg, il, tl, n_utt, steps, warmup):
-    """Bounded sample: the first n_utt utterances of the workload."""
+def time_cpu_reference(acts, tg, il, tl, n_utt, steps, warmup, threads=None, ctc_only=False):
+    """Times the first n_utt utterances of the workload (n_utt = B: the whole batch)."""
     import torch
-    torch.set_num_threads(os.cpu_count() or 1)
+    import torch.nn.functional as F
+    torch.set_num_threads(threads or os.cpu_count() or 1)
     offs = int(tl[:n_utt].sum())
     a, t, i, l = acts[:, :n_utt].contiguous(), tg[:offs].contiguous(), il[:n_utt], tl[:n_utt]
+    if ctc_only:
+        a = F.log_softmax(a, -1)
     for _ in range(warmup):
-        cpu_reference_pass(a, t, i, l)
-    times = [cpu_reference_pass(a, t, i, l)[0] for _ in range(steps)]
+        cpu_reference_pass(a, t, i, l, ctc_only)
+    times = [cpu_reference_pass(a, t, i, l, ctc_only)[0] for _ in range(steps)]
     T = acts.shape[0]
     per = sum(times) / len(times)
-    return n_utt * T / per, per, torch.get_num_threads()
+    used = torch.get_num_threads()
+    torch.set_num_threads(os.cpu_count() or 1)
+    return n_utt * T / per, per, used
+
+
+def workload_string(workload, B, T, V, S, fixed, peaky):
+    return (f"{workload}: B={B} T={T} V={V} S~{S} per GPU, "
+            f"{'fixed' if fixed else 'variable'} lengths, {'peaky' if peaky else 'N(0,1)'} logits")
 
 
 def run_reference(args, workload):
-    """--impl reference: torch's CPU CTC (what the reference executes) on host cores."""
+    """--impl reference: torch's CPU CTC (what the reference executes) on the host cores, on the SAME
+    workload (the whole batch) and with the driver's steps / warm-up.  Extra figures of BASELINE.md's
+    protocol (1 thread; CTC only) ride along under `cpu_baseline`."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     from pytorch_asr_b200 import synth
     idx, B, T, V, S, fixed = synth.CONFIGS[workload]
-    acts, tg, il, tl = synth.make_config(workload)
-    n_utt = min(B, args.ref_utts)
-    steps, warmup = max(1, min(args.steps, 10)), max(1, min(args.warmup, 2))
-    value, per, cores = time_cpu_reference(acts, tg, il, tl, n_utt, steps, warmup)
-    sample = f"first {n_utt} of {B} utterances of {workload}, {steps} timed passes after {warmup} warm-up"
+    if workload == "C5":
+        B = B // max(1, int(os.environ.get("WORLD_SIZE", "1")))
+    acts, tg, il, tl = synth.make_batch(B, T, V, S, seed=1234 + idx, fixed_lengths=fixed, peaky=args.peaky)
+    steps, warmup = max(1, args.steps), max(1, args.warmup)
+    # bound the run to a few minutes whatever the flags: a C2 pass costs 0.3-1.2 s on 16-32 cores
+    t_probe, _ = cpu_reference_pass(acts, tg, il, tl)
+    budget = 150.0
+    if (steps + warmup) * t_probe > budget:
+        steps = max(1, int(budget / t_probe) - warmup)
+    value, per, cores = time_cpu_reference(acts, tg, il, tl, B, steps, warmup)
+    sample = f"the whole {workload} batch ({B} utterances), {steps} timed passes after {warmup} warm-up"
+    extra = {}
+    if not args.no_cpu_baseline:
+        v_ctc, per_ctc, _ = time_cpu_reference(acts, tg, il, tl, B, min(steps, 5), 1, ctc_only=True)
+        n1 = min(B, 32)
+        v_1t, per_1t, _ = time_cpu_reference(acts, tg, il, tl, n1, 2, 1, threads=1)
+        extra = {"ctc_only": {"value": v_ctc, "ms_per_pass": per_ctc * 1e3,
+                              "what": "nn.CTCLoss fwd+bwd on ready-made log-probs, all cores, whole batch"},
+                 "one_thread": {"value": v_1t, "ms_per_pass": per_1t * 1e3, "cores": 1,
+                                "sample": f"first {n1} of {B} utterances, 2 timed passes after 1 warm-up"}}
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": steps, "warmup": warmup, "ms_per_step": per * 1e3, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{workload}: B={B} T={T} V={V} S~{S} variable lengths", "sample": sample},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "reference",
-                         "sample": sample + "; torch.nn.CTCLoss CPU fp32 + log_softmax + backward"},
+        "scaling": "strong" if workload == "C5" else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_string(workload, B, T, V, S, fixed, args.peaky),
+                   "frames": "padded B*T", "valid_frames_per_step": int(il.sum())},
+        "cpu_baseline": dict({"value": value, "unit": UNIT, "cores": cores, "kind": "reference",
+                              "sample": sample + "; torch.nn.CTCLoss CPU fp32 + log_softmax + backward"}, **extra),
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
+
+
+class Exchange:
+    """The path's only collective, off the critical path: each step's (sum, count) pair lives in a ring
+    slot; the exchange runs on a side stream (P2P kernel) or as an asynchronous NCCL all-reduce, and
+    the main stream only waits for a slot's previous exchange before overwriting it."""
+    RING = 4
+
+    def __init__(self, dist, reducer, device):
+        import torch
+        self.torch, self.dist, self.reducer = torch, dist, reducer
+        self.slots = [torch.zeros(2, dtype=torch.float32, device=device) for _ in range(self.RING)]
+        self.pending = [None] * self.RING
+        self.k = 0
+
+    def slot(self):
+        """The (sum, count) buffer of this step; the main stream is ordered after its previous use."""
+        i = self.k % self.RING
+        h = self.pending[i]
+        if h is not None:
+            h.wait()
+            self.pending[i] = None
+        return self.slots[i]
+
+    def post(self):
+        i = self.k % self.RING
+        if self.reducer is not None:
+            from pytorch_asr_b200 import cabi
+            self.pending[i] = self.reducer.exchange_async(self.slots[i], cabi.REDUCE_MEAN)
+        elif self.dist is not None:
+            self.pending[i] = self.dist.all_reduce(self.slots[i], async_op=True)
+        self.k += 1
+
+    def drain(self):
+        """Orders the main stream after every exchange still in flight; returns the last global pair."""
+        for i in range(self.RING):
+            if self.pending[i] is not None:
+                self.pending[i].wait()
+                self.pending[i] = None
+        return self.slots[(self.k - 1) % self.RING]
+
+
+def run_workload(torch, cabi, synth, workload, rank, world, K, W, args, dist, reducer, flush):
+    """Times K steps of `workload` on this rank's shard; returns a dict of raw results (all ranks)."""
+    idx, B, T, V, S, fixed = synth.CONFIGS[workload]
+    strong = workload == "C5"
+    if strong:
+        # BASELINE.json configs[4]: ONE global batch of 4096 utterances dealt across the ranks
+        B = B // world
+    # utterance-sharded: every rank owns one batch of the named shape (its own seed)
+    acts, tg, il, tl = synth.make_batch(B, T, V, S, seed=1234 + idx + 1000 * rank,
+                                        fixed_lengths=fixed, peaky=args.peaky)
+    prob = cabi.DeviceProblem(acts, tg, il, tl, blank=0, reduction="mean")
+    geo = cabi.geometry(T, B, V, prob.S_max)
+    bytes_p, bytes_s = algorithmic_bytes(T, B, V, il, tl)
+    st = torch.cuda.current_stream()
+    xch = Exchange(dist, reducer, prob.acts.device)
+    n_fused = 2 if geo["kernel"] == 2 else 1     # fused kernel (+ its fallback launch)
+
+    def fused():
+        cabi._check(prob.lib.ctc_b200_fwd_bwd_f32(
+            prob.acts.data_ptr(), prob.targets.data_ptr(), prob.tgt_off.data_ptr(),
+            prob.in_lens.data_ptr(), prob.tgt_lens.data_ptr(), T, B, V, prob.S_max, 0, 0,
+            prob.nll.data_ptr(), prob.grad.data_ptr(), prob.scale.data_ptr(),
+            prob.ws.data_ptr(), prob.ws_bytes, st.cuda_stream), "fwd_bwd")
+
+    def reduce_and_post():
+        out2 = xch.slot()
+        cabi._check(prob.lib.ctc_b200_reduce_loss_f32(
+            prob.nll.data_ptr(), prob.tgt_lens.data_ptr(), B, cabi.REDUCE_MEAN,
+            out2.data_ptr(), prob.loss.data_ptr(), st.cuda_stream), "reduce")
+        xch.post()
+
+    for _ in range(W):
+        fused()
+        reduce_and_post()
+    pair = xch.drain()
+    torch.cuda.synchronize()
+    if dist is not None:
+        # the exchanged pair against a plain (synchronous) NCCL all-reduce of the same local pair
+        local = torch.empty(2, dtype=torch.float32, device="cuda")
+        cabi._check(prob.lib.ctc_b200_reduce_loss_f32(
+            prob.nll.data_ptr(), prob.tgt_lens.data_ptr(), B, cabi.REDUCE_MEAN,
+            local.data_ptr(), prob.loss.data_ptr(), st.cuda_stream), "reduce")
+        dist.all_reduce(local)
+        got, ref2 = pair.cpu(), local.cpu()
+        assert float(got[1]) == float(ref2[1]) == world * B, (got, ref2)
+        assert abs(float(got[0]) - float(ref2[0])) <= 1e-6 * abs(float(ref2[0])), (got, ref2)
+
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True),
+           torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+    e_tail = torch.cuda.Event(enable_timing=True)
+    sampler = ClockSampler(int(os.environ.get("LOCAL_RANK", "0")))
+    if dist is not None:
+        dist.barrier()
+    torch.cuda.synchronize()
+    sampler.start()
+    launches = 0
+    for k in range(K):
+        if flush is not None:
+            flush.fill_(k & 0xFF)               # evict L2 (256 MB > 126 MB), outside the events
+        e0, e1, e2 = ev[k]
+        e0.record(st)
+        fused()
+        e1.record(st)                            # e0..e1 = the dominant kernel alone
+        reduce_and_post()
+        launches += n_fused + 1 + (1 if reducer is not None else 0)
+        e2.record(st)
+    pair = xch.drain()                           # every exchange of the timed steps has completed ...
+    e_tail.record(st)                            # ... before the clock stops
+    torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
+    clocks = sampler.stop()
+    step_ms = sum(a.elapsed_time(c) for a, _, c in ev) + ev[-1][2].elapsed_time(e_tail)
+    kern_ms = sum(a.elapsed_time(b) for a, b, _ in ev) / K
+    t = torch.tensor([step_ms, kern_ms], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    step_ms, kern_ms = float(t[0]), float(t[1])
+    prob.check_status()
+    if reducer is not None:
+        reducer.check()
+    local_loss = float((prob.nll.double() / prob.tgt_lens.clamp(min=1).double()).mean())
+    loss = float(pair[0] / pair[1]) if dist is not None else float(prob.loss.cpu())
+    return {"B": B, "T": T, "V": V, "S": S, "fixed": fixed, "strong": strong, "geo": geo, "prob": prob,
+            "acts": acts, "tg": tg, "il": il, "tl": tl, "bytes_p": bytes_p, "bytes_s": bytes_s,
+            "ms_per_step": step_ms / K, "kern_ms": kern_ms, "launches": launches, "clocks": clocks,
+            "loss": loss, "local_loss": local_loss, "value": world * B * T / (step_ms / K * 1e-3)}
+
+
+def roofline_block(r, peak, peak_src, workload):
+    ach_s = r["bytes_s"] / (r["kern_ms"] * 1e-3) / 1e9
+    ach_p = r["bytes_p"] / (r["kern_ms"] * 1e-3) / 1e9
+    return {
+        "bound": "hbm", "kernel": r["geo"]["variant_name"], "achieved": ach_s, "peak": peak,
+        "unit": "GB/s", "frac": ach_s / peak, "traffic": _traffic(workload),
+        "peak_source": peak_src, "kernel_ms": r["kern_ms"],
+        "algorithmic_bytes": r["bytes_s"], "definition": "(S) logits read + grad write + one fp32 lattice written and read once, exact lengths",
+        "achieved_compulsory_io": ach_p, "frac_compulsory_io": ach_p / peak,
+        "compulsory_io_bytes": r["bytes_p"],
+    }
+
+
+def time_module_path(torch, r, steps):
+    """The real drop-in call site (trainer.py:418-438): CUDA logits, CPU int32 targets / lengths,
+    `loss = crit(...)`, `.item()`, `.backward()`, synchronize -- wall clock per iteration; and the same
+    for torch.nn.CTCLoss on the same GPU (what the reference executes today: log_softmax + native
+    ctc_loss_gpu kernels; cuDNN cannot take variable lengths)."""
+    import torch.nn.functional as F
+    from pytorch_asr_b200 import CTCLoss
+    acts, tg, il, tl = r["acts"], r["tg"], r["il"], r["tl"]
+    x = acts.cuda().requires_grad_(True)
+    crit = CTCLoss(blank=0, reduction="mean")
+    ref = torch.nn.CTCLoss(blank=0, reduction="mean")
+
+    def ours():
+        x.grad = None
+        loss = crit(x, tg, il, tl)           # trainer.py:422
+        v = loss.item()                      # trainer.py:423,430
+        loss.backward()                      # trainer.py:438
+        torch.cuda.synchronize()             # trainer.py:441-442
+        return v
+
+    def theirs():
+        x.grad = None
+        with torch.backends.cudnn.flags(enabled=False):
+            loss = ref(F.log_softmax(x, -1), tg, il, tl)
+        v = loss.item()
+        loss.backward()
+        torch.cuda.synchronize()
+        return v
+
+    out = {}
+    for name, fn in (("b200", ours), ("torch_native_gpu", theirs)):
+        try:
+            for _ in range(3):
+                v = fn()
+            t0 = time.perf_counter()
+            for _ in range(steps):
+                v = fn()
+            dt = (time.perf_counter() - t0) / steps
+            out[name] = {"ms_per_iter": dt * 1e3, "frames_per_s": r["B"] * r["T"] / dt, "loss": v}
+        except Exception as e:  # noqa: BLE001
+            out[name] = {"error": f"{type(e).__name__}: {str(e)[:160]}"}
+    out["what"] = ("CTCLoss()(acts_cuda, targets_cpu_i32, in_lens_cpu, tgt_lens_cpu) + .item() + .backward() + "
+                   "synchronize, host wall clock; torch_native_gpu: F.log_softmax + torch.nn.CTCLoss (cuDNN off) "
+                   "on the same tensors")
+    return out
 
 
 def main():
@@ -162,11 +382,12 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="C2")
     ap.add_argument("--peaky", action="store_true")
-    ap.add_argument("--ref-utts", type=int, default=64, help="utterances in the CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-flush", action="store_true")
+    ap.add_argument("--no-c5", action="store_true", help="skip the c5 block (BASELINE.json configs[4])")
+    ap.add_argument("--no-module", action="store_true", help="skip the e2e_module block")
     ap.add_argument("--collective", default="auto", choices=["auto", "fused", "nccl"],
-                    help="N>1: loss reduction fused with a P2P all-reduce (one kernel), or reduction + NCCL all-reduce")
+                    help="N>1: exchange of the (sum, count) pair by the P2P kernel or by an NCCL all-reduce (both asynchronous)")
     ap.add_argument("--slices", type=int, default=8, help="batch slices of the host-buffer e2e path")
     args = ap.parse_args()
     workload = args.workload
@@ -188,30 +409,18 @@ def main():
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     W, K = max(args.warmup, 3), max(args.steps, 1)
-
-    idx, B, T, V, S, fixed = synth.CONFIGS[workload]
-    strong = workload == "C5"
-    if strong:
-        # BASELINE.json configs[4]: ONE global batch of 4096 utterances dealt across the ranks
-        B = B // world
-    # utterance-sharded: every rank owns one batch of the named shape (its own seed)
-    acts, tg, il, tl = synth.make_batch(B, T, V, S, seed=1234 + idx + 1000 * rank,
-                                        fixed_lengths=fixed, peaky=args.peaky)
-    prob = cabi.DeviceProblem(acts, tg, il, tl, blank=0, reduction="mean")
-    geo = cabi.geometry(T, B, V, prob.S_max)
-    bytes_p, bytes_s = algorithmic_bytes(T, B, V, il, tl)
     flush = None if args.no_flush else torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 
     # N>1: the path's only collective is the all-reduce of the (loss sum, count) pair.  Preferred form:
-    # ONE kernel that reduces the loss and exchanges the pair over peer memory (NVLink P2P stores);
-    # otherwise the reduction kernel followed by an NCCL all-reduce of the 8 bytes.
+    # ONE kernel on a side stream that exchanges the pair over peer memory (NVLink P2P stores);
+    # otherwise an asynchronous NCCL all-reduce of the 8 bytes.  Either way off the critical path.
     reducer, collective = None, "none"
     if dist is not None:
-        collective = "nccl"
+        collective = "nccl-async"
         if args.collective in ("auto", "fused"):
             try:
                 reducer = cabi.PeerLossReducer()
-                collective = "p2p-fused"
+                collective = "p2p-kernel-async"
             except Exception as e:  # noqa: BLE001
                 if args.collective == "fused":
                     raise
@@ -220,75 +429,11 @@ def main():
         flag = torch.tensor([1 if reducer is not None else 0], device="cuda")
         dist.all_reduce(flag, op=dist.ReduceOp.MIN)      # all ranks take the same path
         if int(flag) == 0:
-            reducer, collective = None, "nccl"
-    st = torch.cuda.current_stream()
+            reducer, collective = None, "nccl-async"
 
-    def reduce_and_exchange():
-        if reducer is not None:
-            reducer(prob.nll, prob.tgt_lens, B, cabi.REDUCE_MEAN, prob.out2, prob.loss, prob.ws, st.cuda_stream)
-            return
-        cabi._check(prob.lib.ctc_b200_reduce_loss_f32(
-            prob.nll.data_ptr(), prob.tgt_lens.data_ptr(), B, cabi.REDUCE_MEAN,
-            prob.out2.data_ptr(), prob.loss.data_ptr(), st.cuda_stream), "reduce")
-        if dist is not None:
-            dist.all_reduce(prob.out2)
-
-    def step():
-        prob.run(want_grad=True, reduce=False)
-        reduce_and_exchange()
-
-    for _ in range(W):
-        step()
-    torch.cuda.synchronize()
-    if reducer is not None:
-        # the fused kernel against the reduction kernel + NCCL all-reduce on the same nll
-        fused = prob.out2.clone()
-        cabi._check(prob.lib.ctc_b200_reduce_loss_f32(
-            prob.nll.data_ptr(), prob.tgt_lens.data_ptr(), B, cabi.REDUCE_MEAN,
-            prob.out2.data_ptr(), prob.loss.data_ptr(), st.cuda_stream), "reduce")
-        dist.all_reduce(prob.out2)
-        ref2 = prob.out2.cpu()
-        assert float(fused[1]) == float(ref2[1]) == world * B, (fused, ref2)
-        assert abs(float(fused[0]) - float(ref2[0])) <= 1e-6 * abs(float(ref2[0])), (fused, ref2)
-
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True),
-           torch.cuda.Event(enable_timing=True)) for _ in range(K)]
-    sampler = ClockSampler(local)
-    if dist is not None:
-        dist.barrier()
-    torch.cuda.synchronize()
-    sampler.start()
-    launches = 0
-    for k in range(K):
-        if flush is not None:
-            flush.fill_(k & 0xFF)               # evict L2 (256 MB > 126 MB), outside the events
-        e0, e1, e2 = ev[k]
-        e0.record(st)
-        cabi._check(prob.lib.ctc_b200_fwd_bwd_f32(
-            prob.acts.data_ptr(), prob.targets.data_ptr(), prob.tgt_off.data_ptr(),
-            prob.in_lens.data_ptr(), prob.tgt_lens.data_ptr(), T, B, V, prob.S_max, 0, 0,
-            prob.nll.data_ptr(), prob.grad.data_ptr(), prob.scale.data_ptr(),
-            prob.ws.data_ptr(), prob.ws_bytes, st.cuda_stream), "fwd_bwd")
-        e1.record(st)                            # e0..e1 = the dominant kernel alone
-        reduce_and_exchange()
-        launches += 3 if geo["kernel"] == 2 else 2   # fused kernel (+ its fallback launch) + loss reduction
-        e2.record(st)
-    torch.cuda.synchronize()
-    if dist is not None:
-        dist.barrier()
-    clocks = sampler.stop()
-    step_ms = sum(a.elapsed_time(c) for a, _, c in ev)
-    kern_ms = sum(a.elapsed_time(b) for a, b, _ in ev) / K
-    t = torch.tensor([step_ms, kern_ms], dtype=torch.float64, device="cuda")
-    if dist is not None:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    step_ms, kern_ms = float(t[0]), float(t[1])
-    ms_per_step = step_ms / K
-    value = world * B * T / (ms_per_step * 1e-3)
-    prob.check_status()
-    # this rank's own mean (what the single-rank e2e session must reproduce) and the reported loss
-    local_loss = float((prob.nll.double() / prob.tgt_lens.clamp(min=1).double()).mean())
-    loss = float(prob.out2[0] / prob.out2[1]) if dist is not None else float(prob.loss.cpu())
+    r = run_workload(torch, cabi, synth, workload, rank, world, K, W, args, dist, reducer, flush)
+    B, T, V, S = r["B"], r["T"], r["V"], r["S"]
+    acts, tg, il, tl, prob = r["acts"], r["tg"], r["il"], r["tl"], r["prob"]
 
     # ---- e2e: the host-buffer C-ABI call, H2D + compute + D2H(loss) timed on the host ----
     K2 = max(3, min(K, 50))
@@ -311,7 +456,21 @@ def main():
     e2e_value = world * B * T * K2 / e2e_s
     h2d = acts.numel() * 4 + int(tg.numel()) * 4 + 16 * B   # logits + labels + 4 int32/f32 per utterance
     ses.close()
-    assert abs(e2e_loss - local_loss) <= 2e-6 * abs(local_loss), (e2e_loss, local_loss)
+    assert abs(e2e_loss - r["local_loss"]) <= 2e-6 * abs(r["local_loss"]), (e2e_loss, r["local_loss"])
+
+    module = None
+    if world == 1 and not args.no_module:
+        module = time_module_path(torch, r, max(3, min(K, 30)))
+    del prob
+    r["prob"] = None
+
+    # ---- c5 block: BASELINE.json configs[4], one batch of 4096 utterances dealt over the ranks ----
+    c5 = None
+    if workload != "C5" and not args.no_c5:
+        torch.cuda.empty_cache()
+        rc = run_workload(torch, cabi, synth, "C5", rank, world, max(3, min(K, 20)), 3, args, dist, reducer, flush)
+        rc["prob"] = None
+        c5 = rc
 
     if rank != 0:
         if dist is not None:
@@ -319,41 +478,42 @@ def main():
         return
 
     peak, peak_src = _peaks()
-    ach_s = bytes_s / (kern_ms * 1e-3) / 1e9
-    ach_p = bytes_p / (kern_ms * 1e-3) / 1e9
     line = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
-        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong" if strong else "weak",
+        "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+        "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "strong" if r["strong"] else "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {
-            "workload": f"{workload}: B={B} T={T} V={V} S~{S} per GPU, "
-                        f"{'fixed' if fixed else 'variable'} lengths, {'peaky' if args.peaky else 'N(0,1)'} logits",
+            "workload": workload_string(workload, B, T, V, S, r["fixed"], args.peaky),
             "frames": "padded B*T", "valid_frames_per_step": int(il.sum()) * world,
             "parallelism": f"utterance-sharded x{world}", "collective": collective,
             "l2": "no flush" if flush is None else "256 MB L2 flush between timed steps (outside the events)",
-            "geometry": geo, "loss": loss,
+            "geometry": r["geo"], "loss": r["loss"],
         },
-        "roofline": {
-            "bound": "hbm", "kernel": {2: "ctc_lin_kernel", 1: "ctc_pipe_kernel", 0: "ctc_fused_kernel"}[geo["kernel"]], "achieved": ach_s, "peak": peak,
-            "unit": "GB/s", "frac": ach_s / peak, "traffic": _traffic(workload),
-            "peak_source": peak_src, "kernel_ms": kern_ms,
-            "algorithmic_bytes": bytes_s, "definition": "(S) logits read + grad write + one fp32 lattice written and read once, exact lengths",
-            "achieved_compulsory_io": ach_p, "frac_compulsory_io": ach_p / peak,
-            "compulsory_io_bytes": bytes_p,
-        },
+        "roofline": roofline_block(r, peak, peak_src, workload),
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
                 "d2h_bytes_per_step": 16, "steps": K2, "ms_per_step": e2e_s / K2 * 1e3,
                 "api": "ctc_b200_session_run_host_f32 (pinned host logits, sliced H2D overlapped with compute)",
+                "result": "the 16 bytes read back are the step's result as the trainer consumes it (loss, status); "
+                          "the gradient (same size as the logits) stays on the device by design: its consumer is the "
+                          "network's backward pass on the same GPU (trainer.py:438)",
                 "launches_per_step": e2e_launches},
-        "gpu_launches": launches,
-        "clocks": clocks,
+        "gpu_launches": r["launches"],
+        "clocks": r["clocks"],
     }
+    if module is not None:
+        line["e2e_module"] = module
+    if c5 is not None:
+        line["c5"] = {
+            "workload": f"C5: B=4096 T={c5['T']} V={c5['V']} S~{c5['S']} dealt over {world} GPU(s): {c5['B']} per GPU",
+            "scaling": "strong", "ms_per_step": c5["ms_per_step"], "value": c5["value"], "unit": UNIT,
+            "steps": max(3, min(K, 20)), "roofline": roofline_block(c5, peak, peak_src, "C5"),
+            "geometry": c5["geo"], "loss": c5["loss"], "clocks": c5["clocks"],
+        }
     if world == 1 and not args.no_cpu_baseline:
-        n_utt = min(B, args.ref_utts)
-        v, per, cores = time_cpu_reference(acts, tg, il, tl, n_utt, 3, 1)
+        v, per, cores = time_cpu_reference(acts, tg, il, tl, B, 3, 1)
         line["cpu_baseline"] = {
             "value": v, "unit": UNIT, "cores": cores, "kind": "reference",
-            "sample": f"first {n_utt} of {B} utterances of {workload}, 3 timed passes after 1 warm-up; "
+            "sample": f"the whole {workload} batch ({B} utterances), 3 timed passes after 1 warm-up; "
                       f"torch.nn.CTCLoss CPU fp32 + log_softmax + backward ({per * 1e3:.0f} ms/pass)"}
     print(json.dumps(line), flush=True)
     if dist is not None:

@@ -25,11 +25,12 @@ _vp, _i, _sz = C.c_void_p, C.c_int, C.c_size_t
 class Geometry(C.Structure):
     _fields_ = [("kernel", _i), ("rec_warps", _i), ("grad_warps", _i), ("pairs_per_thread", _i), ("threads", _i), ("chunk", _i), ("row_stride", _i),
                 ("smem_bytes", _i), ("workspace_bytes", _sz), ("variant", _i), ("fallback_kernel", _i),
-                ("comb_groups", _i), ("persistent", _i)]
+                ("comb_groups", _i), ("resident_clusters", _i)]
 
 
 class Options(C.Structure):
-    _fields_ = [("layout", _i), ("use_clamp", _i), ("clamp_min", C.c_float), ("clamp_max", C.c_float)]
+    _fields_ = [("layout", _i), ("use_clamp", _i), ("clamp_min", C.c_float), ("clamp_max", C.c_float),
+                ("persistent", _i)]
 
 
 SYMBOLS = {
@@ -112,7 +113,7 @@ class DeviceProblem:
     libctc_b200.so with raw pointers and the current stream."""
 
     def __init__(self, acts, targets, in_lens, tgt_lens, blank=0, reduction="mean",
-                 zero_infinity=False, device="cuda", batch_major=False, clamp=None):
+                 zero_infinity=False, device="cuda", batch_major=False, clamp=None, persistent=False):
         """acts: [T,N,V] (or [N,T,V] with batch_major=True: both acts and grad then use that layout);
         clamp=(lo, hi): fused Hardtanh in front of the log_softmax."""
         import torch
@@ -124,7 +125,8 @@ class DeviceProblem:
         else:
             self.T, self.N, self.V = acts.shape
         self.opt = Options(LAYOUT_NTV if batch_major else LAYOUT_TNV, 1 if clamp else 0,
-                           float(clamp[0]) if clamp else 0.0, float(clamp[1]) if clamp else 0.0)
+                           float(clamp[0]) if clamp else 0.0, float(clamp[1]) if clamp else 0.0,
+                           1 if persistent else 0)
         self.layout = self.opt.layout
         tl = tgt_lens.to(torch.int64).cpu()
         self.S_max = int(tl.max()) if self.N else 0

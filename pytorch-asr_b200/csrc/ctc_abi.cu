@@ -88,9 +88,7 @@ inline size_t flag_bytes(int n_utt) { return ((size_t)std::max(n_utt, 1) * 8 + 2
 
 // Generic kernel: every warp does recursion + its share of softmax / gradient rows.
 int pick_generic(int T, int V, int pairs, Geometry* g) {
-    int P = pairs > 1024 ? (pairs > 2048 ? 4 : 2) : 1;
-    const int q = env().pairs;  // tuning override (1, 2 or 4)
-    if ((q == 1 || q == 2 || q == 4) && (pairs + q - 1) / q <= 1024) P = q;
+    const int P = pairs > 1024 ? (pairs > 2048 ? 4 : 2) : 1;
     int NT = ((pairs + P - 1) / P + 31) / 32 * 32;
     NT = std::max(NT, P == 1 ? 128 : kMinThreads);
     g->base = 0;
@@ -120,12 +118,9 @@ int pick_generic(int T, int V, int pairs, Geometry* g) {
 // Warp-specialised log-domain kernel: R recursion warps (P pairs per thread) + H helper warps.
 bool pick_pipe(int T, int V, int pairs, int n_utt, Geometry* g) {
     if (V % 4) return false;   // TMA row copies need 16-byte aligned logit rows
-    int P = pairs > 64 ? 4 : (pairs > 32 ? 2 : 1);
-    const int q = env().pairs;
-    if (q == 1 || q == 2 || q == 4) P = q;
+    const int P = pairs > 64 ? 4 : (pairs > 32 ? 2 : 1);
     const int R = (pairs + 32 * P - 1) / (32 * P);
-    int H = env().helpers;
-    if (H < 1 || H > 8) H = pairs > 700 ? 4 : 2;
+    const int H = pairs > 700 ? 4 : 2;
     const int NT = 32 * (R + H);
     if (NT > 1024) return false;
     // (chunk, fetch distance) candidates.  All CTAs should be co-resident (one wave: the
@@ -155,7 +150,7 @@ bool pick_pipe(int T, int V, int pairs, int n_utt, Geometry* g) {
             g->chunk = TC;
             g->smem = lay.total;
             g->lat_utt_stride = (size_t)std::max(T, 1) * (size_t)RS;
-            return true;
+            return pipe_variant(*g) >= 0;
         }
     }
     return false;
@@ -300,11 +295,12 @@ int launch_fused(const float* acts, const int32_t* targets, const int32_t* tgt_o
         lp.n_utt = utt_count;
         lp.utt_rot = 0;
         int n_clusters = utt_count;
-        // More utterances than co-resident clusters (C5: 512 per GPU and more): persistent clusters that pull
-        // utterances from a device-side queue, longest first, instead of a second, mostly idle wave.
-        const int resident = queue ? lin_resident_clusters(g, V) : 0;
-        const bool persist = env().persist < 0 ? (resident > 0 && utt_count > resident) : (env().persist > 0 && queue && resident > 0);
-        if (persist) {
+        // Optional (opt->persistent): with more utterances than co-resident clusters, launch only those and
+        // let them pull utterances from a device-side queue, longest first.  Off by default -- the hardware
+        // CTA scheduler already hands the next cluster of the grid to the first free slot, in the same order.
+        const bool want_persist = env().persist > 0 || (env().persist < 0 && opt && opt->persistent);
+        const int resident = (want_persist && queue) ? lin_resident_clusters(g, V) : 0;
+        if (resident > 0 && utt_count > resident) {
             lp.queue = queue;
             n_clusters = std::min(resident, utt_count);
         } else {
@@ -393,15 +389,11 @@ int ctc_b200_get_geometry(int T, int n_utt, int V, int S_max, ctc_b200_geometry*
     out->variant = lin ? lin_variant(g, V) : (g.pipe == 1 ? pipe_variant(g) : generic_variant(g));
     out->fallback_kernel = lin ? g.base : -1;
     out->comb_groups = lin ? g.lD : 0;
-    out->persistent = 0;
-    if (lin && env().persist != 0) {
+    out->resident_clusters = 0;
+    if (lin) {
         int ndev = 0;
-        if (cudaGetDeviceCount(&ndev) == cudaSuccess && ndev > 0) {
-            const int resident = lin_resident_clusters(g, V);
-            out->persistent = (env().persist > 0 && resident > 0) || (resident > 0 && n_utt > resident) ? 1 : 0;
-        } else {
-            cudaGetLastError();
-        }
+        if (cudaGetDeviceCount(&ndev) == cudaSuccess && ndev > 0) out->resident_clusters = lin_resident_clusters(g, V);
+        else cudaGetLastError();
     }
     return CTC_B200_OK;
 }

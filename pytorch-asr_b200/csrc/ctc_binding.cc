@@ -193,6 +193,7 @@ std::vector<torch::Tensor> forward(const torch::Tensor& acts, const torch::Tenso
     opt.use_clamp = use_clamp ? 1 : 0;
     opt.clamp_min = (float)clamp_min;
     opt.clamp_max = (float)clamp_max;
+    opt.persistent = 0;
 
     cudaStream_t stream = at::cuda::getCurrentCUDAStream();
     if (N > 0) {
@@ -243,7 +244,7 @@ std::vector<int64_t> geometry(int64_t T, int64_t N, int64_t V, int64_t S_max) {
     ctc_b200_geometry g;
     check_status(ctc_b200_get_geometry((int)T, (int)N, (int)V, (int)S_max, &g), "ctc_b200_get_geometry");
     return {g.kernel, g.rec_warps, g.grad_warps, g.pairs_per_thread, g.threads, g.chunk, g.row_stride, g.smem_bytes,
-            (int64_t)g.workspace_bytes, g.variant, g.fallback_kernel, g.comb_groups, g.persistent};
+            (int64_t)g.workspace_bytes, g.variant, g.fallback_kernel, g.comb_groups, g.resident_clusters};
 }
 
 }  // namespace

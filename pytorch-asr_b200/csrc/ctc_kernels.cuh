@@ -572,7 +572,7 @@ ctc_fused_kernel(const FusedParams p) {
                     float4 q = make_float4(-CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F);
                     if (lane < V4) q = row4[lane];
                     const float4 raw = q;
-                    q.x = clp.cin(q.x); q.y = clp.cin(q.y); q.z = clp.cin(q.z); q.w = clp.cin(q.w);
+                    if (lane < V4) { q.x = clp.cin(q.x); q.y = clp.cin(q.y); q.z = clp.cin(q.z); q.w = clp.cin(q.w); }
                     m = warp_max(fmaxf(fmaxf(q.x, q.y), fmaxf(q.z, q.w)));
                     q.x = (q.x - m) * kLog2e; q.y = (q.y - m) * kLog2e;
                     q.z = (q.z - m) * kLog2e; q.w = (q.w - m) * kLog2e;

@@ -31,19 +31,15 @@ struct Geometry {
 
 // Knobs read ONCE from the environment (developer tuning; the defaults are the product).
 struct Env {
-    int pairs, helpers, chunk, dist, lin_pairs, comb, rotate, utt_rot, nofix, pdl, slice_streams, persist;
+    int chunk, dist, rotate, utt_rot, nofix, pdl, slice_streams, persist;
     char kernel;   // 'g': generic, 'p': log-domain pipe, 0: default (linear)
     static int geti(const char* name, int dflt) {
         const char* e = std::getenv(name);
         return e ? std::atoi(e) : dflt;
     }
     Env() {
-        pairs = geti("CTC_B200_PAIRS", 0);
-        helpers = geti("CTC_B200_HELPERS", 0);
         chunk = geti("CTC_B200_CHUNK", 0);
         dist = geti("CTC_B200_DIST", 0);
-        lin_pairs = geti("CTC_B200_LIN_PAIRS", 0);
-        comb = geti("CTC_B200_COMB", 0);
         rotate = geti("CTC_B200_ROTATE", 1);
         utt_rot = geti("CTC_B200_UTT_ROT", -1);
         nofix = geti("CTC_B200_NOFIX", 0);

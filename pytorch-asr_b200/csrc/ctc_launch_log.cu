@@ -11,48 +11,41 @@ namespace {
 using PipeKernel = void (*)(const PipeParams);
 using GenericKernel = void (*)(const FusedParams);
 
-constexpr int kPipeShapes = 5;   // (MAXT, MINB): (128,4) (160,4) (256,2) (512,1) (1024,1)
-constexpr int kPipeCount = 3 * kPipeShapes;
-constexpr int kGenericCount = 6;
-
-template <int P>
-PipeKernel pipe_kernel_p(int shape) {
-    switch (shape) {
-        case 0: return ctc_pipe_kernel<P, 128, 4>;
-        case 1: return ctc_pipe_kernel<P, 160, 4>;
-        case 2: return ctc_pipe_kernel<P, 256, 2>;
-        case 3: return ctc_pipe_kernel<P, 512, 1>;
-        case 4: return ctc_pipe_kernel<P, 1024, 1>;
-    }
-    return nullptr;
-}
+// Only the (P, CTA size) combinations the geometry choice of ctc_abi.cu can produce are instantiated:
+// pipe:    P = 1 (<= 32 pairs) and P = 2 (<= 64 pairs) always fit 128 threads; P = 4 covers the rest
+// generic: P = 1 up to 1024 pairs, P = 2 up to 2048, P = 4 up to 4096 (always more than 256 threads)
+constexpr int kPipeCount = 7;
+constexpr int kGenericCount = 4;
 
 PipeKernel pipe_kernel(int id) {
-    if (id < 0 || id >= kPipeCount) return nullptr;
-    const int pi = id / kPipeShapes, shape = id % kPipeShapes;
-    return pi == 0 ? pipe_kernel_p<1>(shape) : (pi == 1 ? pipe_kernel_p<2>(shape) : pipe_kernel_p<4>(shape));
+    switch (id) {
+        case 0: return ctc_pipe_kernel<1, 128, 4>;
+        case 1: return ctc_pipe_kernel<2, 128, 4>;
+        case 2: return ctc_pipe_kernel<4, 128, 4>;
+        case 3: return ctc_pipe_kernel<4, 160, 4>;
+        case 4: return ctc_pipe_kernel<4, 256, 2>;
+        case 5: return ctc_pipe_kernel<4, 512, 1>;
+        case 6: return ctc_pipe_kernel<4, 1024, 1>;
+    }
+    return nullptr;
 }
 
 GenericKernel generic_kernel(int id) {
     switch (id) {
         case 0: return ctc_fused_kernel<1, 256>;
         case 1: return ctc_fused_kernel<1, 1024>;
-        case 2: return ctc_fused_kernel<2, 256>;
-        case 3: return ctc_fused_kernel<2, 1024>;
-        case 4: return ctc_fused_kernel<4, 256>;
-        case 5: return ctc_fused_kernel<4, 1024>;
+        case 2: return ctc_fused_kernel<2, 1024>;
+        case 3: return ctc_fused_kernel<4, 1024>;
     }
     return nullptr;
 }
 
 const char* const kPipeNames[kPipeCount] = {
-    "ctc_pipe_kernel<1,128,4>", "ctc_pipe_kernel<1,160,4>", "ctc_pipe_kernel<1,256,2>", "ctc_pipe_kernel<1,512,1>", "ctc_pipe_kernel<1,1024,1>",
-    "ctc_pipe_kernel<2,128,4>", "ctc_pipe_kernel<2,160,4>", "ctc_pipe_kernel<2,256,2>", "ctc_pipe_kernel<2,512,1>", "ctc_pipe_kernel<2,1024,1>",
-    "ctc_pipe_kernel<4,128,4>", "ctc_pipe_kernel<4,160,4>", "ctc_pipe_kernel<4,256,2>", "ctc_pipe_kernel<4,512,1>", "ctc_pipe_kernel<4,1024,1>",
+    "ctc_pipe_kernel<1,128,4>", "ctc_pipe_kernel<2,128,4>", "ctc_pipe_kernel<4,128,4>", "ctc_pipe_kernel<4,160,4>",
+    "ctc_pipe_kernel<4,256,2>", "ctc_pipe_kernel<4,512,1>", "ctc_pipe_kernel<4,1024,1>",
 };
 const char* const kGenericNames[kGenericCount] = {
-    "ctc_fused_kernel<1,256>", "ctc_fused_kernel<1,1024>", "ctc_fused_kernel<2,256>",
-    "ctc_fused_kernel<2,1024>", "ctc_fused_kernel<4,256>", "ctc_fused_kernel<4,1024>",
+    "ctc_fused_kernel<1,256>", "ctc_fused_kernel<1,1024>", "ctc_fused_kernel<2,1024>", "ctc_fused_kernel<4,1024>",
 };
 
 SmemMark g_pipe_marks[kPipeCount], g_generic_marks[kGenericCount];
@@ -60,10 +53,11 @@ SmemMark g_pipe_marks[kPipeCount], g_generic_marks[kGenericCount];
 }  // namespace
 
 int pipe_variant(const Geometry& g) {
-    const int pi = g.P == 1 ? 0 : (g.P == 2 ? 1 : (g.P == 4 ? 2 : -1));
-    if (pi < 0 || g.NT > 1024) return -1;
-    const int shape = g.NT <= 128 ? 0 : (g.NT <= 160 ? 1 : (g.NT <= 256 ? 2 : (g.NT <= 512 ? 3 : 4)));
-    return pi * kPipeShapes + shape;
+    if (g.NT > 1024) return -1;
+    if (g.P == 1) return g.NT <= 128 ? 0 : -1;
+    if (g.P == 2) return g.NT <= 128 ? 1 : -1;
+    if (g.P != 4) return -1;
+    return g.NT <= 128 ? 2 : (g.NT <= 160 ? 3 : (g.NT <= 256 ? 4 : (g.NT <= 512 ? 5 : 6)));
 }
 const char* pipe_variant_name(int id) { return id >= 0 && id < kPipeCount ? kPipeNames[id] : "?"; }
 
@@ -80,10 +74,11 @@ cudaError_t launch_pipe(const PipeParams& pp, const Geometry& g, int n_utt, bool
 }
 
 int generic_variant(const Geometry& g) {
-    const int pi = g.P == 1 ? 0 : (g.P == 2 ? 1 : (g.P == 4 ? 2 : -1));
-    if (pi < 0 || g.NT > 1024) return -1;
+    if (g.NT > 1024) return -1;
     // small CTAs get the full register file, large ones the 64-register cap
-    return 2 * pi + (g.NT <= 256 ? 0 : 1);
+    if (g.P == 1) return g.NT <= 256 ? 0 : 1;
+    if (g.P == 2) return 2;
+    return g.P == 4 ? 3 : -1;
 }
 const char* generic_variant_name(int id) { return id >= 0 && id < kGenericCount ? kGenericNames[id] : "?"; }
 

@@ -834,8 +834,10 @@ ctc_lin_kernel(const PipeParams pp, int* __restrict__ flags) {
 #pragma unroll
                         for (int q = 0; q < P; ++q) atomicAdd(ocl + rB * ER + lab[q], gB[q]);
                     }
-                    obl[rA * ER] = bsA;
-                    obl[rB * ER] = bsB;
+                    // (a thread outside its window may have read lattice cells nobody wrote: whatever they held
+                    // -- NaN bit patterns of a recycled allocation included -- must not reach the blank sum)
+                    obl[rA * ER] = winA ? bsA : 0.f;
+                    obl[rB * ER] = winB ? bsB : 0.f;
                 };
                 int r = r_begin;
                 if (!first && wgc && NT <= 128)

@@ -640,7 +640,7 @@ ctc_pipe_kernel(const PipeParams pp) {
                 float4 x = make_float4(-CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F);
                 if (q16 < V4) x = row4[q16];
                 const float4 raw = x;
-                x.x = clp.cin(x.x); x.y = clp.cin(x.y); x.z = clp.cin(x.z); x.w = clp.cin(x.w);
+                if (q16 < V4) { x.x = clp.cin(x.x); x.y = clp.cin(x.y); x.z = clp.cin(x.z); x.w = clp.cin(x.w); }
                 const float m = half_max(fmaxf(fmaxf(x.x, x.y), fmaxf(x.z, x.w)));
                 x.x = (x.x - m) * kLog2e; x.y = (x.y - m) * kLog2e;
                 x.z = (x.z - m) * kLog2e; x.w = (x.w - m) * kLog2e;

@@ -71,7 +71,7 @@ def test_post_loss_checks_with_one_sync(case):
         il = il.clone(); il[2] = int(tl[2]) - 1              # infeasible: nll = +inf
     il[0] = 80
     # the reference
-    xr = acts.cuda().requires_grad_(True)
+    xr = acts.clone().requires_grad_(True)          # (the reference's path on the CPU)
     lr = torch.nn.CTCLoss(blank=0, reduction="mean")(F.log_softmax(xr, -1), tg, il, tl)
     want = _unit_train_reference(lr, il, tl)
     if want is not None:
@@ -89,7 +89,7 @@ def test_post_loss_checks_with_one_sync(case):
     assert abs(st["loss"] - want) <= 1e-5 * max(abs(want), 1e-30)
     assert st["factor"] == (0.0 if case == "short" else 1.0)
     loss.backward()
-    assert (x.grad - xr.grad).abs().max() <= 1e-4
+    assert (x.grad.cpu() - xr.grad).abs().max() <= 1e-4
     if case == "short":
         assert st["loss"] == 0.0 and float(loss) == 0.0 and not x.grad.any()
 
@@ -173,15 +173,16 @@ def _py_edit_distance(r, h):
 def test_greedy_decode_and_ler(B, T, V, S, batch_major):
     """8(f)4: arg-max -> collapse -> drop blanks -> edit distance, bit-exact against the reference's
     Python loops (integer work: no tolerance)."""
-    acts, tg, il, tl = synth.make_batch(B, T, V, S, seed=90 + V, peaky=True)
-    # make the hypotheses resemble the targets: push the target labels up along a rough alignment
+    acts, tg, il, tl = synth.make_batch(B, T, V, S, seed=90 + V)
+    # a blank-dominated output whose peaks follow a rough alignment of the targets, some labels left out
+    acts[:, :, 0] += 9.0
     offs = torch.cat([torch.zeros(1, dtype=torch.int64), tl.long().cumsum(0)])
     for b in range(B):
         Tb, Sb = int(il[b]), int(tl[b])
         for k in range(Sb):
             t = int((k + 0.5) * Tb / max(Sb, 1))
-            if (k + b) % 7:                       # leave some labels out: deletions
-                acts[t, b, int(tg[offs[b] + k])] += 30.0
+            if (k + b) % 7:                       # every 7th label is missing: deletions
+                acts[t, b, int(tg[offs[b] + k])] += 20.0
     a_ntv = acts.transpose(0, 1).contiguous()
     hyps = _py_decode(a_ntv, il)
     refs = [tg[offs[b]:offs[b + 1]].tolist() for b in range(B)]

@@ -2,7 +2,7 @@
 # round 2, call A: the whole GPU test-suite, smoke, and bench lines for C2 / C5 (one GPU)
 cd "$GRAFT_REPO_ROOT" || exit 1
 mkdir -p gpurun_out
-timeout 1500 python -m pytest tests -m gpu -x -q -rs 2>&1 | tail -60 > gpurun_out/r02a_pytest.log
+timeout 1500 python -m pytest tests -m gpu -q -rs --tb=short 2>&1 | tail -150 > gpurun_out/r02a_pytest.log
 timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/r02a_smoke.log 2>&1
 timeout 300 python bench.py --steps 20 --warmup 5 --no-cpu-baseline > gpurun_out/r02a_bench_c2.json 2> gpurun_out/r02a_bench_c2.err
 timeout 300 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --workload C5 > gpurun_out/r02a_bench_c5.json 2> gpurun_out/r02a_bench_c5.err
