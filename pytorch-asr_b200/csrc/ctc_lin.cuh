@@ -54,6 +54,8 @@
 // P partner cells a thread needs are exactly ONE partner thread's P cells, reversed: 128-bit
 // conflict-free shared-memory loads and a single partner exponent per thread.
 #pragma once
+#include <type_traits>
+
 #include "ctc_pipe.cuh"
 
 namespace ctcb200 {
@@ -97,6 +99,70 @@ __device__ __forceinline__ float pow2c(int e) { return __int_as_float((clamp_exp
 // exponent of x >= 0 (zero / denormals give -127)
 __device__ __forceinline__ int expo(float x) { return (__float_as_int(x) >> 23) - 127; }
 __device__ __forceinline__ int warp_max_i(int x) { return __reduce_max_sync(0xffffffffu, x); }
+
+// Shared-memory accesses by explicit 32-bit address (the FIX hot loops).  In a kernel with cluster dimensions
+// the compiler derives every generic shared pointer from S2R SR_CgaCtaId (~50 cycles) and, at the
+// 128-register cap, re-derives it several times per loop iteration; a pinned 32-bit base avoids that.
+__device__ __forceinline__ float4 lds128(unsigned a) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ float2 lds64(unsigned a) {
+    float2 v;
+    asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ uint2 lds64u(unsigned a) {
+    uint2 v;
+    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ float lds32(unsigned a) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ int lds32i(unsigned a) {
+    int v;
+    asm volatile("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ void sts32(unsigned a, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(v) : "memory"); }
+__device__ __forceinline__ void sts64(unsigned a, float2 v) {
+    asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(a), "f"(v.x), "f"(v.y) : "memory");
+}
+__device__ __forceinline__ void sts64u(unsigned a, uint2 v) {
+    asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(a), "r"(v.x), "r"(v.y) : "memory");
+}
+__device__ __forceinline__ void reds_add_u32(unsigned a, unsigned v) {
+    asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory");
+}
+// class slot `byte_off` bytes into an occupancy row
+__device__ __forceinline__ unsigned* occ_slot(unsigned* row, int byte_off) {
+    return reinterpret_cast<unsigned*>(reinterpret_cast<char*>(row) + byte_off);
+}
+__device__ __forceinline__ void cp_async16_a(unsigned dst, const void* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+__device__ __forceinline__ void mbar_expect_tx_a(unsigned bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s_a(unsigned dst, const void* src, unsigned bytes, unsigned bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_a(unsigned addr, unsigned parity) {
+    unsigned ok = 0;
+    for (unsigned spins = 0; !ok; ++spins) {
+        asm volatile("{\n\t.reg .pred p;\n\t"
+                     "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                     "selp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
+        if (spins > (1u << 24)) __trap();
+    }
+}
 
 // A plane of a lattice row holds thread t's P cells at [P * t, P * t + P) -- except for P = 8, where
 // the two 128-bit halves of a thread are split: cells 0..3 at [4 t, 4 t + 4), cells 4..7 at
@@ -182,7 +248,12 @@ ctc_lin_kernel(const PipeParams pp, int* __restrict__ flags) {
     const FusedParams& p = pp.f;
     const int NT = FIX ? 128 : blockDim.x, NW = NT >> 5;
     const int R = RC > 0 ? RC : pp.R, H = FIX ? 1 : pp.H, NP = RC > 0 ? 32 * P * RC : pp.NP;
-    const int lane = threadIdx.x & 31;
+    // loop invariants the compiler would otherwise re-derive inside the role loops at the register cap
+    // (S2R SR_TID / SR_CgaCtaId cost ~50 cycles each): pinned in registers in the FIX instantiation
+    int lane_pin = threadIdx.x & 31;
+    unsigned sbase = smem_u32(smem_raw);
+    if constexpr (FIX) asm volatile("" : "+r"(lane_pin), "+r"(sbase));
+    const int lane = lane_pin;
     const int shift = pp.rotate > 0 ? (int)((blockIdx.x / pp.rotate) * R) % NW : 0;
     const int w = ((int)(threadIdx.x >> 5) + NW - shift) % NW;   // role (virtual) warp id
     // which utterance this cluster works on: the batch is sorted by length (dataloader.py:53); utt_rot
@@ -253,7 +324,9 @@ ctc_lin_kernel(const PipeParams pp, int* __restrict__ flags) {
         S = min(max(S, 0), NP - P);
     }
     const int32_t* tg = p.targets + p.tgt_off[b];
-    const bool want_grad = p.grad != nullptr;
+    int want_grad_pin = p.grad != nullptr ? 1 : 0;
+    if constexpr (FIX) asm volatile("" : "+r"(want_grad_pin));
+    const bool want_grad = want_grad_pin != 0;
     const float gscale = p.grad_scale ? p.grad_scale[b] : 1.0f;
     const size_t frame_stride = (size_t)p.frame_stride;
     const float* acts_b = p.acts + (size_t)b * (size_t)p.utt_stride;
@@ -575,12 +648,12 @@ ctc_lin_kernel(const PipeParams pp, int* __restrict__ flags) {
         // COMB: occupancies of the second half = REC's row x the partner's stored row
         // =============================================================================
         const int wc = (w - R) % R;      // which recursion warp I shadow
-        int lab[P];
+        int lab[P];                      // class of my label cell k, as a BYTE offset into an occupancy row
         bool vB[P], vY[P];
 #pragma unroll
         for (int k = 0; k < P; ++k) {
             const int i = i0 + k;
-            lab[k] = s_lab[s0 + k];
+            lab[k] = s_lab[s0 + k] * 4;
             vB[k] = i >= 0 && i <= S;
             vY[k] = i >= 0 && i < S;
         }
@@ -592,6 +665,15 @@ ctc_lin_kernel(const PipeParams pp, int* __restrict__ flags) {
         const unsigned win_cons = (i0 <= S && hasX) ? (unsigned)(C + P) : 0u;    // (tt - i0) < win
         const int offd = 2 * NP + tid - s0p;
         const int nbar = 32 * R;
+        // FIX fast path: byte offsets that never change (row A = cg, row B = cg + 2 of a full chunk; the
+        // reversed sweep walks the staged chunk backwards)
+        const unsigned fx_x = hasX ? (unsigned)X * 16u : 0u;                     // partner thread's cells in a plane
+        const unsigned fx_stA = (unsigned)(rev ? 3 - cg : cg) * (544u * 4u) + fx_x;
+        const unsigned fx_stB = (unsigned)(rev ? 1 - cg : cg + 2) * (544u * 4u) + fx_x;
+        const unsigned fx_e = 2048u + (hasX ? (unsigned)X * 4u : 0u) - fx_x;    // its exponent, from its blank cells
+        const unsigned fx_ar = (unsigned)cg * (544u * 4u) + (unsigned)lane * 16u;  // my cells in REC's row cg
+        const unsigned fx_o = 2048u + (unsigned)lane * 4u - (unsigned)lane * 16u;  // my exponent, from my blank cells
+        const unsigned fx_bl = (80u + (unsigned)lane) * 4u;                      // my blank partial sum in an occupancy row
         int E0 = 0;                      // integer part of log2 P(labels | logits)
         float rz = 0.f;                  // 1 / mantissa sum: occupancy = a * p~ * 2^(off+o-E0) * rz
         const bool iss_part = cg == 0 && wc == 0;   // this warp also requests the partner's rows (TMA)
@@ -613,267 +695,373 @@ ctc_lin_kernel(const PipeParams pp, int* __restrict__ flags) {
         int wgc_i = want_grad ? 1 : 0, nc_i = NC, n1_i = n1, nch_i = nch;
         asm volatile("" : "+r"(wgc_i), "+r"(nc_i), "+r"(n1_i), "+r"(nch_i));
         const bool wgc = wgc_i != 0;
-        for (int it = 0; it < n_it; ++it) {
-            LPROF_BEGIN();
-            // partner rows of chunk `it` (consumed in iteration it+2); the first two consume chunks
-            // are requested at the phase break
-            if (it >= n1_i + 2 && it + kLinPDist - 2 < nch_i && wgc) {
-                if (iss_part) issue_partner(it + kLinPDist - 2, iss_p.slot);
-                iss_p.advance();
-            }
-            const int k = it - 2;
-            if (k >= n1_i && k < nch_i) {
-                int tt0, rows;
-                chunk_at(k, tt0, rows);
-                // the chunk with the first combined row is done by group 0 alone (it yields E0 and
-                // 1/z, which the other groups pick up from shared memory one barrier later)
-                const bool first = k == n1_i;
-                if (k == n1_i + 1 && cg > 0) { E0 = s_red[100]; rz = __int_as_float(s_red[101]); }
-                const int r_begin = first ? 0 : cg, r_inc = first ? 1 : nc_i;
-                if (!first || cg == 0) {
-                mbar_wait(bar_part + ring_part.slot, ring_part.parity);   // TMA data landed
-                const float* st = s_stage + (size_t)ring_part.slot * TC * RS;
-                const float* arow = s_a + (size_t)a_buf * TC * RS + s0p;
-                float* orow = s_occ + (size_t)o_buf * TC * ER + wc * OW;
-                unsigned* ocl = reinterpret_cast<unsigned*>(orow);
-                float* obl = orow + VO + lane;
-                struct RowData { float aB[P], aY[P], pb[P], py[P]; int off, ob, oy; };
-                auto load_rd = [&](int r, RowData& d) {
-                    // the chunk was staged in frame order: the reversed sweep walks it backwards
-                    const float* str = st + (size_t)(rev ? rows - 1 - r : r) * RS;
-                    const float* stp = str + (hasX ? X * PW : 0);        // partner thread's P blanks
-                    const int* sto = reinterpret_cast<const int*>(str + 2 * NP) + (hasX ? X : 0);
-                    {
-                        float qb[P], qy[P];
-                        load_row<P>(stp + NP, qy, HS);     // first: the shuffles below wait for these
-                        d.ob = *sto;
-                        load_row<P>(stp, qb, HS);
-                        load_row<P>(arow + r * RS, d.aB, HS);
-                        load_row<P>(arow + r * RS + NP, d.aY, HS);
-                        d.off = *reinterpret_cast<const int*>(arow + r * RS + offd);
-#pragma unroll
-                        for (int q = 0; q < P; ++q) d.pb[q] = qb[P - 1 - q];
-#pragma unroll
-                        for (int q = 0; q + 1 < P; ++q) d.py[q] = qy[P - 2 - q];
-                        // my last label pairs with the LAST label of partner thread X-1 = the thread
-                        // lane+1 of my warp talks to; lane 31 reads it itself
-                        float yl = __shfl_down_sync(0xffffffffu, qy[P - 1], 1);
-                        int ol = __shfl_down_sync(0xffffffffu, d.ob, 1);
-                        if (lane == 31 && hasX1) { yl = stp[NP + (P == 8 ? HS : 0) - 1]; ol = sto[-1]; }
-                        d.py[P - 1] = yl;
-                        d.oy = ol;
-                    }
-                };
-                // returns true when `gq` (label occupancies, Q1.31) still has to be added to the class slots
-                auto combine_rd = [&](int r, const RowData& d, unsigned (&gq)[P], float& bsum_out) -> bool {
-                    const int u = tt0 + r - i0;
-                    const float (&aB)[P] = d.aB; const float (&aY)[P] = d.aY;
-                    const float (&pb)[P] = d.pb; const float (&py)[P] = d.py;
-                    const int off = d.off, ob = d.ob, oy = d.oy;
-                    const bool in_win = (unsigned)u < win_cons;
-                    float bsum = 0.f;
-                    bool pending = false;
-                    if (first && r == 0) {
-                        // first combined row: also yields the likelihood P = sum_s a * p~.
-                        // Exponent/mantissa form: E0 = max exponent of any term, z = sum of the
-                        // terms scaled by 2^-E0; log2 P = E0 + log2 z.
-                        float tB[P], tY[P];
-                        int eB[P], eY[P];
-#pragma unroll
-                        for (int q = 0; q < P; ++q) {
-                            tB[q] = 0.f; tY[q] = 0.f; eB[q] = kLinNone; eY[q] = kLinNone;
-                            if (in_win && vB[q] && aB[q] > 0.f && pb[q] > 0.f) {
-                                const int ea = expo(aB[q]), ep = expo(pb[q]);
-                                tB[q] = (aB[q] * pow2c(-ea)) * (pb[q] * pow2c(-ep));
-                                eB[q] = ea + ep + off + ob;
-                            }
-                            const bool okY = q + 1 < P ? true : hasX1;
-                            const int oq = q + 1 < P ? ob : oy;
-                            if (in_win && vY[q] && okY && aY[q] > 0.f && py[q] > 0.f) {
-                                const int ea = expo(aY[q]), ep = expo(py[q]);
-                                tY[q] = (aY[q] * pow2c(-ea)) * (py[q] * pow2c(-ep));
-                                eY[q] = ea + ep + off + oq;
-                            }
+        auto comb_iter = [&](int it) {
+                LPROF_BEGIN();
+                // partner rows of chunk `it` (consumed in iteration it+2); the first two consume chunks
+                // are requested at the phase break
+                if (it >= n1_i + 2 && it + kLinPDist - 2 < nch_i && wgc) {
+                    if (iss_part) issue_partner(it + kLinPDist - 2, iss_p.slot);
+                    iss_p.advance();
+                }
+                const int k = it - 2;
+                if (k >= n1_i && k < nch_i) {
+                    int tt0, rows;
+                    chunk_at(k, tt0, rows);
+                    // the chunk with the first combined row is done by group 0 alone (it yields E0 and
+                    // 1/z, which the other groups pick up from shared memory one barrier later)
+                    const bool first = k == n1_i;
+                    if (k == n1_i + 1 && cg > 0) { E0 = s_red[100]; rz = __int_as_float(s_red[101]); }
+                    const int r_begin = first ? 0 : cg, r_inc = first ? 1 : nc_i;
+                    if (!first || cg == 0) {
+                    mbar_wait(bar_part + ring_part.slot, ring_part.parity);   // TMA data landed
+                    const float* st = s_stage + (size_t)ring_part.slot * TC * RS;
+                    const float* arow = s_a + (size_t)a_buf * TC * RS + s0p;
+                    float* orow = s_occ + (size_t)o_buf * TC * ER + wc * OW;
+                    unsigned* ocl = reinterpret_cast<unsigned*>(orow);
+                    float* obl = orow + VO + lane;
+                    struct RowData { float aB[P], aY[P], pb[P], py[P]; int off, ob, oy; };
+                    auto load_rd = [&](int r, RowData& d) {
+                        // the chunk was staged in frame order: the reversed sweep walks it backwards
+                        const float* str = st + (size_t)(rev ? rows - 1 - r : r) * RS;
+                        const float* stp = str + (hasX ? X * PW : 0);        // partner thread's P blanks
+                        const int* sto = reinterpret_cast<const int*>(str + 2 * NP) + (hasX ? X : 0);
+                        {
+                            float qb[P], qy[P];
+                            load_row<P>(stp + NP, qy, HS);     // first: the shuffles below wait for these
+                            d.ob = *sto;
+                            load_row<P>(stp, qb, HS);
+                            load_row<P>(arow + r * RS, d.aB, HS);
+                            load_row<P>(arow + r * RS + NP, d.aY, HS);
+                            d.off = *reinterpret_cast<const int*>(arow + r * RS + offd);
+    #pragma unroll
+                            for (int q = 0; q < P; ++q) d.pb[q] = qb[P - 1 - q];
+    #pragma unroll
+                            for (int q = 0; q + 1 < P; ++q) d.py[q] = qy[P - 2 - q];
+                            // my last label pairs with the LAST label of partner thread X-1 = the thread
+                            // lane+1 of my warp talks to; lane 31 reads it itself
+                            float yl = __shfl_down_sync(0xffffffffu, qy[P - 1], 1);
+                            int ol = __shfl_down_sync(0xffffffffu, d.ob, 1);
+                            if (lane == 31 && hasX1) { yl = stp[NP + (P == 8 ? HS : 0) - 1]; ol = sto[-1]; }
+                            d.py[P - 1] = yl;
+                            d.oy = ol;
                         }
-                        int em = kLinNone;
-#pragma unroll
-                        for (int q = 0; q < P; ++q) em = max(em, max(eB[q], eY[q]));
-                        em = warp_max_i(em);
-                        if (R > 1) {
-                            if (lane == 0) s_red[64 + wc] = em;
-                            named_bar_sync(2, nbar);
-                            for (int i = 0; i < R; ++i) em = max(em, s_red[64 + i]);
-                            named_bar_sync(2, nbar);
-                        }
-                        const bool dead = em == kLinNone;      // no path survived (infeasible or underflow)
-                        E0 = dead ? 0 : em;
-                        float z = 0.f;
-#pragma unroll
-                        for (int q = 0; q < P; ++q) {
-                            tB[q] = eB[q] == kLinNone ? 0.f : tB[q] * pow2c(eB[q] - E0);
-                            tY[q] = eY[q] == kLinNone ? 0.f : tY[q] * pow2c(eY[q] - E0);
-                            z += tB[q] + tY[q];
-                        }
-                        z = warp_sum(z);
-                        if (R > 1) {
-                            if (lane == 0) s_red[128 + wc] = __float_as_int(z);
-                            named_bar_sync(2, nbar);
-                            z = 0.f;
-                            for (int i = 0; i < R; ++i) z += __int_as_float(s_red[128 + i]);
-                            named_bar_sync(2, nbar);
-                        }
-                        const bool bad = dead || !(z > 0.f) || !(z < 3.0e38f);
-                        rz = bad ? 0.f : 1.0f / z;
-                        if (tid == 0) {
-                            s_red[100] = E0;
-                            s_red[101] = __float_as_int(rz);
-                            if (bad) { s_flag[0] = 1; s_flag[1] = 1; }
-                            if (!rev) p.nll[b] = bad ? 0.f : (float)(-((double)E0 + (double)log2f(z)) * kLn2);
-                        }
-                        if (wgc) {
-#pragma unroll
+                    };
+                    // returns true when `gq` (label occupancies, Q1.31) still has to be added to the class slots
+                    auto combine_rd = [&](int r, const RowData& d, unsigned (&gq)[P], float& bsum_out) -> bool {
+                        const int u = tt0 + r - i0;
+                        const float (&aB)[P] = d.aB; const float (&aY)[P] = d.aY;
+                        const float (&pb)[P] = d.pb; const float (&py)[P] = d.py;
+                        const int off = d.off, ob = d.ob, oy = d.oy;
+                        const bool in_win = (unsigned)u < win_cons;
+                        float bsum = 0.f;
+                        bool pending = false;
+                        if (first && r == 0) {
+                            // first combined row: also yields the likelihood P = sum_s a * p~.
+                            // Exponent/mantissa form: E0 = max exponent of any term, z = sum of the
+                            // terms scaled by 2^-E0; log2 P = E0 + log2 z.
+                            float tB[P], tY[P];
+                            int eB[P], eY[P];
+    #pragma unroll
                             for (int q = 0; q < P; ++q) {
-                                bsum += tB[q] * rz;
-                                atomicAdd(ocl + r * ER + lab[q], __float2uint_rn(tY[q] * (rz * kQ31)));
+                                tB[q] = 0.f; tY[q] = 0.f; eB[q] = kLinNone; eY[q] = kLinNone;
+                                if (in_win && vB[q] && aB[q] > 0.f && pb[q] > 0.f) {
+                                    const int ea = expo(aB[q]), ep = expo(pb[q]);
+                                    tB[q] = (aB[q] * pow2c(-ea)) * (pb[q] * pow2c(-ep));
+                                    eB[q] = ea + ep + off + ob;
+                                }
+                                const bool okY = q + 1 < P ? true : hasX1;
+                                const int oq = q + 1 < P ? ob : oy;
+                                if (in_win && vY[q] && okY && aY[q] > 0.f && py[q] > 0.f) {
+                                    const int ea = expo(aY[q]), ep = expo(py[q]);
+                                    tY[q] = (aY[q] * pow2c(-ea)) * (py[q] * pow2c(-ep));
+                                    eY[q] = ea + ep + off + oq;
+                                }
+                            }
+                            int em = kLinNone;
+    #pragma unroll
+                            for (int q = 0; q < P; ++q) em = max(em, max(eB[q], eY[q]));
+                            em = warp_max_i(em);
+                            if (R > 1) {
+                                if (lane == 0) s_red[64 + wc] = em;
+                                named_bar_sync(2, nbar);
+                                for (int i = 0; i < R; ++i) em = max(em, s_red[64 + i]);
+                                named_bar_sync(2, nbar);
+                            }
+                            const bool dead = em == kLinNone;      // no path survived (infeasible or underflow)
+                            E0 = dead ? 0 : em;
+                            float z = 0.f;
+    #pragma unroll
+                            for (int q = 0; q < P; ++q) {
+                                tB[q] = eB[q] == kLinNone ? 0.f : tB[q] * pow2c(eB[q] - E0);
+                                tY[q] = eY[q] == kLinNone ? 0.f : tY[q] * pow2c(eY[q] - E0);
+                                z += tB[q] + tY[q];
+                            }
+                            z = warp_sum(z);
+                            if (R > 1) {
+                                if (lane == 0) s_red[128 + wc] = __float_as_int(z);
+                                named_bar_sync(2, nbar);
+                                z = 0.f;
+                                for (int i = 0; i < R; ++i) z += __int_as_float(s_red[128 + i]);
+                                named_bar_sync(2, nbar);
+                            }
+                            const bool bad = dead || !(z > 0.f) || !(z < 3.0e38f);
+                            rz = bad ? 0.f : 1.0f / z;
+                            if (tid == 0) {
+                                s_red[100] = E0;
+                                s_red[101] = __float_as_int(rz);
+                                if (bad) { s_flag[0] = 1; s_flag[1] = 1; }
+                                if (!rev) p.nll[b] = bad ? 0.f : (float)(-((double)E0 + (double)log2f(z)) * kLn2);
+                            }
+                            if (wgc) {
+    #pragma unroll
+                                for (int q = 0; q < P; ++q) {
+                                    bsum += tB[q] * rz;
+                                    atomicAdd(occ_slot(ocl + r * ER, lab[q]), __float2uint_rn(tY[q] * (rz * kQ31)));
+                                }
+                            }
+                        } else if (in_win) {
+                            // occupancy = a * p~ * 2^(off + o - E0) / z   (exact exponents); cells outside
+                            // [0, S] are exact zeros on REC's side, partner vectors are finite
+                            // (label cells directly in Q1.31 units)
+                            // The exponent h = off + o - E0 goes onto the partner cell up to kLinHmax (so that
+                            // p * 2^h cannot overflow); a larger h -- cells far below their thread's maximum on
+                            // both sides, steep lattices -- puts the rest onto the product (a factor of 1 otherwise).
+                            const int hb = off + ob - E0, hy = off + oy - E0;
+                            const int hbc = max(min(hb, kLinHmax), kLinHmin), hyc = max(min(hy, kLinHmax), kLinHmin);
+                            const float sb = pow2c(hbc) * rz;
+                            const float sq = sb * kQ31;
+                            const float sy = hasX1 ? pow2c(hyc) * (rz * kQ31) : 0.f;
+                            const float rb = pow2c(hb - hbc), ry = pow2c(hy - hyc);   // 1 unless h is outside [kLinHmin, kLinHmax]
+    #pragma unroll
+                            for (int q = 0; q < P; ++q) {
+                                bsum += (aB[q] * (pb[q] * sb)) * rb;
+                                float gy = 0.f;
+                                if (q + 1 < P) gy = (aY[q] * (py[q] * sq)) * rb;
+                                else if (hasX1) gy = (aY[q] * (py[q] * sy)) * ry;
+                                gq[q] = __float2uint_rn(gy);
+                            }
+                            pending = true;
+                        }
+                        bsum_out = bsum;
+                        return pending;
+                    };
+                    // Steady state with registers to spare (4-warp CTAs): TWO rows per pass, staged so that
+                    // at most ~48 cell registers are live: label planes of both rows -> Q1.31 occupancies;
+                    // blank planes of both rows -> blank sums; then all atomics.  Two independent dependency
+                    // chains per warp instead of one.
+                    auto combine2 = [&](int rA, int rB) {
+                        const float* strA = st + (size_t)(rev ? rows - 1 - rA : rA) * RS;
+                        const float* strB = st + (size_t)(rev ? rows - 1 - rB : rB) * RS;
+                        const float* stpA = strA + (hasX ? X * PW : 0);
+                        const float* stpB = strB + (hasX ? X * PW : 0);
+                        const int* stoA = reinterpret_cast<const int*>(strA + 2 * NP) + (hasX ? X : 0);
+                        const int* stoB = reinterpret_cast<const int*>(strB + 2 * NP) + (hasX ? X : 0);
+                        const float* arA = arow + rA * RS;
+                        const float* arB = arow + rB * RS;
+                        float qyA[P], qyB[P], aYA[P], aYB[P];
+                        load_row<P>(stpA + NP, qyA, HS);
+                        load_row<P>(stpB + NP, qyB, HS);
+                        const int obA = *stoA, obB = *stoB;
+                        const int offA = *reinterpret_cast<const int*>(arA + offd);
+                        const int offB = *reinterpret_cast<const int*>(arB + offd);
+                        load_row<P>(arA + NP, aYA, HS);
+                        load_row<P>(arB + NP, aYB, HS);
+                        float ylA = __shfl_down_sync(0xffffffffu, qyA[P - 1], 1);
+                        float ylB = __shfl_down_sync(0xffffffffu, qyB[P - 1], 1);
+                        int olA = __shfl_down_sync(0xffffffffu, obA, 1);
+                        int olB = __shfl_down_sync(0xffffffffu, obB, 1);
+                        if (lane == 31 && hasX1) {
+                            ylA = stpA[NP + (P == 8 ? HS : 0) - 1]; olA = stoA[-1];
+                            ylB = stpB[NP + (P == 8 ? HS : 0) - 1]; olB = stoB[-1];
+                        }
+                        const bool winA = (unsigned)(tt0 + rA - i0) < win_cons;
+                        const bool winB = (unsigned)(tt0 + rB - i0) < win_cons;
+                        // occupancy = a * p~ * 2^(off + o - E0) / z (see combine_rd for the exponent split)
+                        const int hbA = offA + obA - E0, hyA = offA + olA - E0;
+                        const int hbB = offB + obB - E0, hyB = offB + olB - E0;
+                        const int cbA = max(min(hbA, kLinHmax), kLinHmin), cyA = max(min(hyA, kLinHmax), kLinHmin);
+                        const int cbB = max(min(hbB, kLinHmax), kLinHmin), cyB = max(min(hyB, kLinHmax), kLinHmin);
+                        const float sbA = winA ? pow2c(cbA) * rz : 0.f, sbB = winB ? pow2c(cbB) * rz : 0.f;
+                        const float syA = (winA && hasX1) ? pow2c(cyA) * (rz * kQ31) : 0.f;
+                        const float syB = (winB && hasX1) ? pow2c(cyB) * (rz * kQ31) : 0.f;
+                        const float rbA = pow2c(hbA - cbA), ryA = pow2c(hyA - cyA);
+                        const float rbB = pow2c(hbB - cbB), ryB = pow2c(hyB - cyB);
+                        const float sqA = sbA * kQ31, sqB = sbB * kQ31;
+                        unsigned gA[P], gB[P];
+    #pragma unroll
+                        for (int q = 0; q + 1 < P; ++q) {
+                            gA[q] = __float2uint_rn((aYA[q] * (qyA[P - 2 - q] * sqA)) * rbA);
+                            gB[q] = __float2uint_rn((aYB[q] * (qyB[P - 2 - q] * sqB)) * rbB);
+                        }
+                        gA[P - 1] = __float2uint_rn((aYA[P - 1] * (ylA * syA)) * ryA);
+                        gB[P - 1] = __float2uint_rn((aYB[P - 1] * (ylB * syB)) * ryB);
+                        float bsA = 0.f, bsB = 0.f;
+                        {
+                            float qbA[P], qbB[P], aBA[P], aBB[P];
+                            load_row<P>(stpA, qbA, HS);
+                            load_row<P>(stpB, qbB, HS);
+                            load_row<P>(arA, aBA, HS);
+                            load_row<P>(arB, aBB, HS);
+    #pragma unroll
+                            for (int q = 0; q < P; ++q) {
+                                bsA += (aBA[q] * (qbA[P - 1 - q] * sbA)) * rbA;
+                                bsB += (aBB[q] * (qbB[P - 1 - q] * sbB)) * rbB;
                             }
                         }
-                    } else if (in_win) {
-                        // occupancy = a * p~ * 2^(off + o - E0) / z   (exact exponents); cells outside
-                        // [0, S] are exact zeros on REC's side, partner vectors are finite
-                        // (label cells directly in Q1.31 units)
-                        // The exponent h = off + o - E0 goes onto the partner cell up to kLinHmax (so that
-                        // p * 2^h cannot overflow); a larger h -- cells far below their thread's maximum on
-                        // both sides, steep lattices -- puts the rest onto the product (a factor of 1 otherwise).
-                        const int hb = off + ob - E0, hy = off + oy - E0;
-                        const int hbc = max(min(hb, kLinHmax), kLinHmin), hyc = max(min(hy, kLinHmax), kLinHmin);
-                        const float sb = pow2c(hbc) * rz;
-                        const float sq = sb * kQ31;
-                        const float sy = hasX1 ? pow2c(hyc) * (rz * kQ31) : 0.f;
-                        const float rb = pow2c(hb - hbc), ry = pow2c(hy - hyc);   // 1 unless h is outside [kLinHmin, kLinHmax]
-#pragma unroll
-                        for (int q = 0; q < P; ++q) {
-                            bsum += (aB[q] * (pb[q] * sb)) * rb;
-                            float gy = 0.f;
-                            if (q + 1 < P) gy = (aY[q] * (py[q] * sq)) * rb;
-                            else if (hasX1) gy = (aY[q] * (py[q] * sy)) * ry;
-                            gq[q] = __float2uint_rn(gy);
+                        if (winA) {
+    #pragma unroll
+                            for (int q = 0; q < P; ++q) atomicAdd(occ_slot(ocl + rA * ER, lab[q]), gA[q]);
                         }
-                        pending = true;
+                        if (winB) {
+    #pragma unroll
+                            for (int q = 0; q < P; ++q) atomicAdd(occ_slot(ocl + rB * ER, lab[q]), gB[q]);
+                        }
+                        // (a thread outside its window may have read lattice cells nobody wrote: whatever they held
+                        // -- NaN bit patterns of a recycled allocation included -- must not reach the blank sum)
+                        obl[rA * ER] = winA ? bsA : 0.f;
+                        obl[rB * ER] = winB ? bsB : 0.f;
+                    };
+                    int r = r_begin;
+                    if (!first && wgc && NT <= 128)
+                        for (; r + r_inc < rows; r += 2 * r_inc) combine2(r, r + r_inc);
+                    for (; r < rows; r += r_inc) {
+                        RowData d0;
+                        unsigned gq[P];
+                        float bsum;
+                        load_rd(r, d0);
+                        if (combine_rd(r, d0, gq, bsum)) {
+    #pragma unroll
+                            for (int q = 0; q < P; ++q) atomicAdd(occ_slot(ocl + r * ER, lab[q]), gq[q]);
+                        }
+                        if (wgc) obl[r * ER] = bsum;
                     }
-                    bsum_out = bsum;
-                    return pending;
-                };
-                // Steady state with registers to spare (4-warp CTAs): TWO rows per pass, staged so that
-                // at most ~48 cell registers are live: label planes of both rows -> Q1.31 occupancies;
-                // blank planes of both rows -> blank sums; then all atomics.  Two independent dependency
-                // chains per warp instead of one.
-                auto combine2 = [&](int rA, int rB) {
-                    const float* strA = st + (size_t)(rev ? rows - 1 - rA : rA) * RS;
-                    const float* strB = st + (size_t)(rev ? rows - 1 - rB : rB) * RS;
-                    const float* stpA = strA + (hasX ? X * PW : 0);
-                    const float* stpB = strB + (hasX ? X * PW : 0);
-                    const int* stoA = reinterpret_cast<const int*>(strA + 2 * NP) + (hasX ? X : 0);
-                    const int* stoB = reinterpret_cast<const int*>(strB + 2 * NP) + (hasX ? X : 0);
-                    const float* arA = arow + rA * RS;
-                    const float* arB = arow + rB * RS;
-                    float qyA[P], qyB[P], aYA[P], aYB[P];
-                    load_row<P>(stpA + NP, qyA, HS);
-                    load_row<P>(stpB + NP, qyB, HS);
-                    const int obA = *stoA, obB = *stoB;
-                    const int offA = *reinterpret_cast<const int*>(arA + offd);
-                    const int offB = *reinterpret_cast<const int*>(arB + offd);
-                    load_row<P>(arA + NP, aYA, HS);
-                    load_row<P>(arB + NP, aYB, HS);
-                    float ylA = __shfl_down_sync(0xffffffffu, qyA[P - 1], 1);
-                    float ylB = __shfl_down_sync(0xffffffffu, qyB[P - 1], 1);
-                    int olA = __shfl_down_sync(0xffffffffu, obA, 1);
-                    int olB = __shfl_down_sync(0xffffffffu, obB, 1);
-                    if (lane == 31 && hasX1) {
-                        ylA = stpA[NP + (P == 8 ? HS : 0) - 1]; olA = stoA[-1];
-                        ylB = stpB[NP + (P == 8 ? HS : 0) - 1]; olB = stoB[-1];
                     }
-                    const bool winA = (unsigned)(tt0 + rA - i0) < win_cons;
-                    const bool winB = (unsigned)(tt0 + rB - i0) < win_cons;
-                    // occupancy = a * p~ * 2^(off + o - E0) / z (see combine_rd for the exponent split)
-                    const int hbA = offA + obA - E0, hyA = offA + olA - E0;
-                    const int hbB = offB + obB - E0, hyB = offB + olB - E0;
-                    const int cbA = max(min(hbA, kLinHmax), kLinHmin), cyA = max(min(hyA, kLinHmax), kLinHmin);
-                    const int cbB = max(min(hbB, kLinHmax), kLinHmin), cyB = max(min(hyB, kLinHmax), kLinHmin);
-                    const float sbA = winA ? pow2c(cbA) * rz : 0.f, sbB = winB ? pow2c(cbB) * rz : 0.f;
-                    const float syA = (winA && hasX1) ? pow2c(cyA) * (rz * kQ31) : 0.f;
-                    const float syB = (winB && hasX1) ? pow2c(cyB) * (rz * kQ31) : 0.f;
-                    const float rbA = pow2c(hbA - cbA), ryA = pow2c(hyA - cyA);
-                    const float rbB = pow2c(hbB - cbB), ryB = pow2c(hyB - cyB);
-                    const float sqA = sbA * kQ31, sqB = sbB * kQ31;
-                    unsigned gA[P], gB[P];
-#pragma unroll
-                    for (int q = 0; q + 1 < P; ++q) {
-                        gA[q] = __float2uint_rn((aYA[q] * (qyA[P - 2 - q] * sqA)) * rbA);
-                        gB[q] = __float2uint_rn((aYB[q] * (qyB[P - 2 - q] * sqB)) * rbB);
-                    }
-                    gA[P - 1] = __float2uint_rn((aYA[P - 1] * (ylA * syA)) * ryA);
-                    gB[P - 1] = __float2uint_rn((aYB[P - 1] * (ylB * syB)) * ryB);
-                    float bsA = 0.f, bsB = 0.f;
-                    {
-                        float qbA[P], qbB[P], aBA[P], aBB[P];
-                        load_row<P>(stpA, qbA, HS);
-                        load_row<P>(stpB, qbB, HS);
-                        load_row<P>(arA, aBA, HS);
-                        load_row<P>(arB, aBB, HS);
-#pragma unroll
-                        for (int q = 0; q < P; ++q) {
-                            bsA += (aBA[q] * (qbA[P - 1 - q] * sbA)) * rbA;
-                            bsB += (aBB[q] * (qbB[P - 1 - q] * sbB)) * rbB;
+                    ring_part.advance();
+                    a_buf ^= 1;
+                    o_buf ^= 1;
+                }
+                LPROF_END(it >= n1 + 2);
+                __syncthreads();
+                if (it == n1) {
+                    // Phase break: my REC warps have stored every row the partner will consume,
+                    // and (after the cluster barrier) vice versa.
+                    cluster_sync_all();
+                    if (iss_part) {
+                        fence_proxy_async();
+                        for (int kk = n1; kk < n1 + kLinPDist; ++kk) {
+                            if (kk < nch && (want_grad || kk == n1)) issue_partner(kk, iss_p.slot);
+                            iss_p.advance();
                         }
                     }
-                    if (winA) {
-#pragma unroll
-                        for (int q = 0; q < P; ++q) atomicAdd(ocl + rA * ER + lab[q], gA[q]);
-                    }
-                    if (winB) {
-#pragma unroll
-                        for (int q = 0; q < P; ++q) atomicAdd(ocl + rB * ER + lab[q], gB[q]);
-                    }
-                    // (a thread outside its window may have read lattice cells nobody wrote: whatever they held
-                    // -- NaN bit patterns of a recycled allocation included -- must not reach the blank sum)
-                    obl[rA * ER] = winA ? bsA : 0.f;
-                    obl[rB * ER] = winB ? bsB : 0.f;
-                };
-                int r = r_begin;
-                if (!first && wgc && NT <= 128)
-                    for (; r + r_inc < rows; r += 2 * r_inc) combine2(r, r + r_inc);
-                for (; r < rows; r += r_inc) {
-                    RowData d0;
-                    unsigned gq[P];
-                    float bsum;
-                    load_rd(r, d0);
-                    if (combine_rd(r, d0, gq, bsum)) {
-#pragma unroll
-                        for (int q = 0; q < P; ++q) atomicAdd(ocl + r * ER + lab[q], gq[q]);
-                    }
-                    if (wgc) obl[r * ER] = bsum;
+                    __syncthreads();
                 }
-                }
-                ring_part.advance();
-                a_buf ^= 1;
-                o_buf ^= 1;
-            }
-            LPROF_END(it >= n1 + 2);
-            __syncthreads();
-            if (it == n1) {
-                // Phase break: my REC warps have stored every row the partner will consume,
-                // and (after the cluster barrier) vice versa.
-                cluster_sync_all();
-                if (iss_part) {
-                    fence_proxy_async();
-                    for (int kk = n1; kk < n1 + kLinPDist; ++kk) {
-                        if (kk < nch && (want_grad || kk == n1)) issue_partner(kk, iss_p.slot);
+        };
+        int it = 0;
+        if constexpr (FIX) {
+            // Steady state of the headline shape class in a loop of its own: chunks k = it - 2 in (n1, nch - 1), i.e.
+            // neither the first combined chunk nor the (possibly short) last one; full chunks of 4 rows, two
+            // combine groups (this warp takes rows cg and cg + 2).  Every shared-memory address is an immediate
+            // offset from a running 32-bit base; what only the general path needs is not live in here.
+            static_assert(!FIX || kLinPDist == 2, "the steady-state loop requests the partner rows two chunks ahead");
+            const int it_fast_end = wgc ? nch_i + 1 : 0;
+            for (; it < n_it && it < n1_i + 3; ++it) comb_iter(it);
+            if (it < it_fast_end) {
+                if (cg > 0) { E0 = s_red[100]; rz = __int_as_float(s_red[101]); }
+                unsigned uA = (unsigned)(n_store + (it - 2 - n1_i) * 4 + cg - i0);    // sweep step of row A minus my first pair
+                const unsigned bar0 = sbase + lay.bars + 8u * (unsigned)lay.NL;       // bar_part[0]
+                for (; it < it_fast_end; ++it) {
+                    LPROF_BEGIN();
+                    if (it < nch_i) {     // partner rows of chunk `it` (consumed in iteration it + 2)
+                        if (iss_part && lane == 0) {
+                            const int tt0i = n_store + (it - n1_i) * 4, rowsi = min(4, Tb - tt0i);
+                            const int t_lo = rev ? tbase - (tt0i + rowsi - 1) : tt0i;
+                            const unsigned bytes = (unsigned)rowsi * (544u * 4u), bar = bar0 + 8u * (unsigned)iss_p.slot;
+                            mbar_expect_tx_a(bar, bytes);
+                            bulk_g2s_a(sbase + lay.stage + (unsigned)iss_p.slot * (4u * 544u * 4u),
+                                       lat_b + (ptrdiff_t)t_lo * 544, bytes, bar);
+                        }
                         iss_p.advance();
                     }
+                    mbar_wait_a(bar0 + 8u * (unsigned)ring_part.slot, ring_part.parity);   // TMA data landed
+                    {
+                constexpr unsigned RSB = 544u * 4u, PLB = 256u * 4u, HSB = 128u * 4u, ERB = 112u * 4u;
+                const unsigned stb = sbase + lay.stage + (unsigned)ring_part.slot * (4u * RSB);
+                const unsigned stA = stb + fx_stA, stB = stb + fx_stB;
+                const unsigned arA = sbase + lay.a + (unsigned)a_buf * (4u * RSB) + fx_ar, arB = arA + 2u * RSB;
+                const unsigned ocA = sbase + lay.occ + (unsigned)o_buf * (4u * ERB) + (unsigned)cg * ERB, ocB = ocA + 2u * ERB;
+                float4 t0, t1;
+                float qyA[P], qyB[P], aYA[P], aYB[P];
+#define CTC_LD8(dst, addr) t0 = lds128(addr); t1 = lds128((addr) + HSB); \
+    dst[0] = t0.x; dst[1] = t0.y; dst[2] = t0.z; dst[3] = t0.w; dst[4] = t1.x; dst[5] = t1.y; dst[6] = t1.z; dst[7] = t1.w
+                CTC_LD8(qyA, stA + PLB);
+                CTC_LD8(qyB, stB + PLB);
+                const int obA = lds32i(stA + fx_e), obB = lds32i(stB + fx_e);
+                const int offA = lds32i(arA + fx_o), offB = lds32i(arB + fx_o);
+                CTC_LD8(aYA, arA + PLB);
+                CTC_LD8(aYB, arB + PLB);
+                float ylA = __shfl_down_sync(0xffffffffu, qyA[P - 1], 1);
+                float ylB = __shfl_down_sync(0xffffffffu, qyB[P - 1], 1);
+                int olA = __shfl_down_sync(0xffffffffu, obA, 1);
+                int olB = __shfl_down_sync(0xffffffffu, obB, 1);
+                if (lane == 31 && hasX1) {
+                    ylA = lds32(stA + PLB + HSB - 4u); olA = lds32i(stA + fx_e - 4u);
+                    ylB = lds32(stB + PLB + HSB - 4u); olB = lds32i(stB + fx_e - 4u);
                 }
-                __syncthreads();
+                const bool winA = uA < win_cons;
+                const bool winB = uA + 2u < win_cons;
+                const int hbA = offA + obA - E0, hyA = offA + olA - E0;
+                const int hbB = offB + obB - E0, hyB = offB + olB - E0;
+                const int cbA = max(min(hbA, kLinHmax), kLinHmin), cyA = max(min(hyA, kLinHmax), kLinHmin);
+                const int cbB = max(min(hbB, kLinHmax), kLinHmin), cyB = max(min(hyB, kLinHmax), kLinHmin);
+                const float sbA = winA ? pow2c(cbA) * rz : 0.f, sbB = winB ? pow2c(cbB) * rz : 0.f;
+                const float syA = (winA && hasX1) ? pow2c(cyA) * (rz * kQ31) : 0.f;
+                const float syB = (winB && hasX1) ? pow2c(cyB) * (rz * kQ31) : 0.f;
+                const float rbA = pow2c(hbA - cbA), ryA = pow2c(hyA - cyA);
+                const float rbB = pow2c(hbB - cbB), ryB = pow2c(hyB - cyB);
+                const float sqA = sbA * kQ31, sqB = sbB * kQ31;
+                unsigned gA[P], gB[P];
+#pragma unroll
+                for (int q = 0; q + 1 < P; ++q) {
+                    gA[q] = __float2uint_rn((aYA[q] * (qyA[P - 2 - q] * sqA)) * rbA);
+                    gB[q] = __float2uint_rn((aYB[q] * (qyB[P - 2 - q] * sqB)) * rbB);
+                }
+                gA[P - 1] = __float2uint_rn((aYA[P - 1] * (ylA * syA)) * ryA);
+                gB[P - 1] = __float2uint_rn((aYB[P - 1] * (ylB * syB)) * ryB);
+                float bsA = 0.f, bsB = 0.f;
+                {
+                    float qbA[P], qbB[P], aBA[P], aBB[P];
+                    CTC_LD8(qbA, stA);
+                    CTC_LD8(qbB, stB);
+                    CTC_LD8(aBA, arA);
+                    CTC_LD8(aBB, arB);
+#pragma unroll
+                    for (int q = 0; q < P; ++q) {
+                        bsA += (aBA[q] * (qbA[P - 1 - q] * sbA)) * rbA;
+                        bsB += (aBB[q] * (qbB[P - 1 - q] * sbB)) * rbB;
+                    }
+                }
+#undef CTC_LD8
+                if (winA) {
+#pragma unroll
+                    for (int q = 0; q < P; ++q) reds_add_u32(ocA + (unsigned)lab[q], gA[q]);
+                }
+                if (winB) {
+#pragma unroll
+                    for (int q = 0; q < P; ++q) reds_add_u32(ocB + (unsigned)lab[q], gB[q]);
+                }
+                sts32(ocA + fx_bl, winA ? bsA : 0.f);
+                sts32(ocB + fx_bl, winB ? bsB : 0.f);
+                    }
+                    uA += 4u;
+                    ring_part.advance();
+                    a_buf ^= 1;
+                    o_buf ^= 1;
+                    LPROF_END(true);
+                    __syncthreads();
+                }
             }
         }
+        for (; it < n_it; ++it) comb_iter(it);
     } else {
         // =============================================================================
         // SOFT / GRAD: logits staging + fused softmax; gradient rows
@@ -902,11 +1090,13 @@ ctc_lin_kernel(const PipeParams pp, int* __restrict__ flags) {
         const int n4 = TC * V4;
         const bool cp_groups = nA == 1 && !wide_rows;   // one softmax warp waits for its own cp.async groups
         int cp_dst[2], cp_row[2];
+        bool pf_lane[2];
         ptrdiff_t cp_src[2];
 #pragma unroll
         for (int j = 0; j < 2; ++j) {
             const int idx = lane + 32 * j, r = idx / max(V4, 1), c = idx - r * V4;
             cp_row[j] = idx < n4 ? r : 0x7fffffff;
+            pf_lane[j] = c == 0 || c == 8;   // two of a V = 48 row's lanes touch both of its 128-byte lines
             cp_dst[j] = r * Vs + 4 * c;
             cp_src[j] = r * a_inc + 4 * c;
         }
@@ -1333,7 +1523,7 @@ ctc_lin_kernel(const PipeParams pp, int* __restrict__ flags) {
                 iss_a.advance();
             }
         }
-        for (int it = 0; it < n_it; ++it) {
+        auto help_iter = [&](int it) {
             LPROF_BEGIN();
             {
                 const int ka = it + kLinYDist + 1;
@@ -1371,7 +1561,170 @@ ctc_lin_kernel(const PipeParams pp, int* __restrict__ flags) {
                 cluster_sync_all();
                 __syncthreads();
             }
+        };
+        int it = 0;
+        if constexpr (FIX) {
+            // The headline shape class in loops of their own (V = 48, one helper warp, full chunks of 4 frames, a
+            // group of 8 lanes per frame), every shared-memory address an offset from the pinned 32-bit base:
+            //   phase 1, it in [0, n1 - 1):        logits request for chunk it + 2, softmax of chunk it
+            //   phase 2, it in [n1 + 3, nch - 1):  the same plus the gradient rows of chunk it - 3, with the two
+            //                                      dependent chains (shuffle trees) interleaved level by level
+            // Everything else (short chunks, the phase break, the drain) runs through help_iter.
+            static_assert(!FIX || kLinYDist == 1, "the steady-state loops wait for cp.async group it with two groups pending");
+            constexpr unsigned YSB = 80u * 4u, YCH = 4u * YSB, ERB = 112u * 4u;
+            const unsigned gl8 = (unsigned)(lane & 7) * 8u, fr = (unsigned)(lane >> 3);
+            const unsigned y0 = sbase + lay.y + fr * YSB + gl8;          // my 3 x 8 bytes of frame fr, ring slot 0
+            const unsigned o0 = sbase + lay.occ + fr * ERB;             // occupancy row of frame fr, buffer 0
+            const unsigned fl0 = sbase + lay.flag;
+            const ptrdiff_t a_step = (ptrdiff_t)tsign * (ptrdiff_t)frame_stride;   // floats per sweep step
+            // logits of chunk ka -> ring slot: two 16-byte cp.async per lane; chunk ka + 6 is pulled into L2
+            auto issue_fast = [&](int ka) {
+                if (ka < nchh_i) {
+                    int tt0, rows;
+                    chunk_at(ka, tt0, rows);
+                    const float* src = acts_b + (ptrdiff_t)(tbase + tsign * tt0) * (ptrdiff_t)frame_stride;
+                    const unsigned dst = sbase + lay.y + (unsigned)iss_a.slot * YCH;
+                    if (cp_row[0] < rows) cp_async16_a(dst + (unsigned)cp_dst[0] * 4u, src + cp_src[0]);
+                    if (cp_row[1] < rows) cp_async16_a(dst + (unsigned)cp_dst[1] * 4u, src + cp_src[1]);
+                    const int kp = ka + 6;
+                    if (kp < nchh_i && (kp < n1h_i) == (ka < n1h_i)) {     // same half of the sweep: 24 steps further on
+                        int tp0, rowsp;
+                        chunk_at(kp, tp0, rowsp);
+                        if (cp_row[0] < rowsp && pf_lane[0]) prefetch_l2(src + 24 * a_step + cp_src[0]);
+                        if (cp_row[1] < rowsp && pf_lane[1]) prefetch_l2(src + 24 * a_step + cp_src[1]);
+                    }
+                }
+                cp_async_commit();
+            };
+            // softmax of my frame of the chunk in ring slot `ys` (+ gradient row of my frame: occupancy buffer
+            // `ob`, softmax rows in ring slot `yg`, gradient row at g2)
+            auto help_fast = [&](auto with_grad, unsigned ys, unsigned ob, unsigned yg, float2* g2) {
+                constexpr bool WG = decltype(with_grad)::value;
+                float4 bp = make_float4(0.f, 0.f, 0.f, 0.f);
+                uint2 xo[3];
+                float2 yo[3];
+                if constexpr (WG) {
+                    bp = lds128(ob + 80u * 4u + 2u * gl8);
+#pragma unroll
+                    for (int j = 0; j < 3; ++j) {
+                        xo[j] = lds64u(ob + gl8 + 64u * j);
+                        yo[j] = lds64(yg + 64u * j);
+                    }
+#pragma unroll
+                    for (int j = 0; j < 3; ++j) sts64u(ob + gl8 + 64u * j, make_uint2(0u, 0u));
+                }
+                cp_async_wait<kLinYDist + 1>();
+                __syncwarp();
+                float2 x[3];
+#pragma unroll
+                for (int j = 0; j < 3; ++j) x[j] = lds64(ys + 64u * j);
+                unsigned mk = 0u;                  // fused Hardtanh: bit 2j / 2j+1 = gradient blocked
+                if (clp.on) {
+#pragma unroll
+                    for (int j = 0; j < 3; ++j) {
+                        mk |= (clp.cmask(x[j].x) ? 1u : 0u) << (2 * j) | (clp.cmask(x[j].y) ? 1u : 0u) << (2 * j + 1);
+                        x[j].x = clp.cin(x[j].x);
+                        x[j].y = clp.cin(x[j].y);
+                    }
+                }
+                float m = fmaxf(fmaxf(fmaxf(x[0].x, x[0].y), fmaxf(x[1].x, x[1].y)), fmaxf(x[2].x, x[2].y));
+                float bs = 0.f, tot = 0.f;
+                float2 o[3];
+                if constexpr (WG) {
+                    bs = (bp.x + bp.y) + (bp.z + bp.w);
+#pragma unroll
+                    for (int j = 0; j < 3; ++j) {
+                        o[j].x = __uint2float_rn(xo[j].x) * (1.0f / kQ31);
+                        o[j].y = __uint2float_rn(xo[j].y) * (1.0f / kQ31);
+                        tot += o[j].x + o[j].y;
+                    }
+                }
+#pragma unroll
+                for (int sft = 4; sft > 0; sft >>= 1) {
+                    const float m2 = __shfl_xor_sync(0xffffffffu, m, sft);
+                    if constexpr (WG) {
+                        const float b2 = __shfl_xor_sync(0xffffffffu, bs, sft);
+                        const float t2 = __shfl_xor_sync(0xffffffffu, tot, sft);
+                        bs += b2;
+                        tot += t2;
+                    }
+                    m = fmaxf(m, m2);
+                }
+                const float mb = m * kLog2e;
+                float z = 0.f;
+#pragma unroll
+                for (int j = 0; j < 3; ++j) {
+                    x[j].x = ex2f(fmaf(x[j].x, kLog2e, -mb));
+                    x[j].y = ex2f(fmaf(x[j].y, kLog2e, -mb));
+                    z += x[j].x + x[j].y;
+                }
+                if constexpr (WG) {
+                    // the blank class sits in column (blank >> 1) of lane (blank >> 1) & 7, slot (blank >> 1) >> 3
+                    const int cb = blank >> 1, glq = lane & 7;
+                    const float addx = (blank & 1) ? 0.f : bs, addy = (blank & 1) ? bs : 0.f;
+#pragma unroll
+                    for (int j = 0; j < 3; ++j) {
+                        const bool mine = cb == glq + 8 * j;
+                        const float ox = o[j].x + (mine ? addx : 0.f), oy = o[j].y + (mine ? addy : 0.f);
+                        // (a set sign bit of y: the fused Hardtanh blocks this entry's gradient)
+                        g2[glq + 8 * j] = make_float2(__float_as_int(yo[j].x) < 0 ? 0.f : gscale * (yo[j].x - ox),
+                                                      __float_as_int(yo[j].y) < 0 ? 0.f : gscale * (yo[j].y - oy));
+                    }
+                    if (!(fabsf(tot + bs - 1.0f) <= kMassTol)) sts32(fl0, __int_as_float(1));   // NaN-safe
+#ifdef CTC_B200_MASSDEV
+                    atomicMax(&s_flag[2], __float_as_int(fabsf(tot + bs - 1.0f)));
+#endif
+                }
+                z += __shfl_xor_sync(0xffffffffu, z, 4);
+                z += __shfl_xor_sync(0xffffffffu, z, 2);
+                z += __shfl_xor_sync(0xffffffffu, z, 1);
+                float rs;
+                asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rs) : "f"(z));
+                rs = rs * (2.0f - z * rs);          // one Newton step: full fp32 accuracy
+#pragma unroll
+                for (int j = 0; j < 3; ++j) {
+                    const float a = x[j].x * rs, c = x[j].y * rs;
+                    sts64(ys + 64u * j, make_float2((mk >> (2 * j)) & 1u ? -a : a, (mk >> (2 * j + 1)) & 1u ? -c : c));
+                }
+                if ((lane & 7) == 0) sts32(ys + 48u * 4u, 0.f);     // slot V: what padding pairs gather
+            };
+            if (iss_acts && do_sm) {     // (always: one helper warp)
+                for (; it < n1h_i - 1; ++it) {
+                    LPROF_BEGIN();
+                    issue_fast(it + 2);
+                    iss_a.advance();
+                    if (it >= 3) gr_a.advance();
+                    help_fast(std::false_type{}, y0 + (unsigned)sm_a.slot * YCH, 0u, 0u, nullptr);
+                    sm_a.advance();
+                    LPROF_END(false);
+                    __syncthreads();
+                }
+                for (; it < n_it && it < n1h_i + 3; ++it) help_iter(it);
+                if (want_grad && it < nchh_i - 1) {
+                    // gradient row of my frame of chunk it - 3 (a full chunk of the second half)
+                    float* gp = grad_b + (ptrdiff_t)(tbase + tsign * (n_store + (it - 3 - n1h_i) * 4 + (int)fr)) *
+                                             (ptrdiff_t)frame_stride;
+                    for (; it < nchh_i - 1; ++it) {
+                        LPROF_BEGIN();
+                        issue_fast(it + 2);
+                        iss_a.advance();
+                        const unsigned ys = y0 + (unsigned)sm_a.slot * YCH;
+                        if (lds32i(fl0 + 4u) == 0)
+                            help_fast(std::true_type{}, ys, o0 + (unsigned)gr_o * (4u * ERB), y0 + (unsigned)gr_a.slot * YCH,
+                                      reinterpret_cast<float2*>(gp));
+                        else
+                            help_fast(std::false_type{}, ys, 0u, 0u, nullptr);
+                        gp += 4 * a_step;
+                        gr_o ^= 1;
+                        gr_a.advance();
+                        sm_a.advance();
+                        LPROF_END(true);
+                        __syncthreads();
+                    }
+                }
+            }
         }
+        for (; it < n_it; ++it) help_iter(it);
     }
 #ifdef CTC_B200_PROFILE
     if (blockIdx.x == 0 && threadIdx.x == 0) {
