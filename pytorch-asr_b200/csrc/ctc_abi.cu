@@ -294,6 +294,8 @@ int launch_fused(const float* acts, const int32_t* targets, const int32_t* tgt_o
         lp.queue = nullptr;
         lp.n_utt = utt_count;
         lp.utt_rot = 0;
+        lp.map_mode = 0;
+        lp.map_pairs = std::max(1, num_sms() / 2);
         int n_clusters = utt_count;
         // Optional (opt->persistent): with more utterances than co-resident clusters, launch only those and
         // let them pull utterances from a device-side queue, longest first.  Off by default -- the hardware
@@ -314,6 +316,7 @@ int launch_fused(const float* acts, const int32_t* targets, const int32_t* tgt_o
                           ? pairs * std::max(1, layers - 1) : 0;
             if (env().utt_rot >= 0) rot = env().utt_rot;
             lp.utt_rot = std::max(0, std::min(rot, utt_count - 1));
+            if (env().map_mode > 0 && utt_count > pairs && utt_count <= 4 * pairs) lp.map_mode = env().map_mode;
         }
         CTC_CUDA(launch_lin(lp, fl, g, n_clusters, st));
 #ifdef CTC_B200_DEV_KNOBS   // developer builds only: look at the linear kernel's own output for flagged utterances
@@ -325,6 +328,8 @@ int launch_fused(const float* acts, const int32_t* targets, const int32_t* tgt_o
         pp.f = prm;
         pp.redo = use_lin ? fl : nullptr;
         pp.utt_rot = 0;
+        pp.map_mode = 0;
+        pp.map_pairs = 0;
         pp.queue = nullptr;
         pp.n_utt = utt_count;
         pp.R = g.R;

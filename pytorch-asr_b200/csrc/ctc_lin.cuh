@@ -90,6 +90,10 @@ constexpr float kQ31 = 2147483648.0f;   // label occupancies are accumulated as 
 #ifndef CTC_LIN_PD
 #define CTC_LIN_PD 2
 #endif
+#ifndef CTC_LIN_P1RING
+#define CTC_LIN_P1RING 1  // FIX, first half: 1 = rows go through the shared-memory ring and the combine warps copy them to HBM;
+                          // 0 = the recursion warp stores them to HBM itself
+#endif
 constexpr int kLinYDist = CTC_LIN_YD;   // logits are requested kLinYDist + 1 chunks before their softmax
 constexpr int kLinPDist = CTC_LIN_PD;   // partner rows are requested kLinPDist chunks before COMB needs them
 
@@ -128,6 +132,10 @@ __device__ __forceinline__ int lds32i(unsigned a) {
     asm volatile("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(a));
     return v;
 }
+__device__ __forceinline__ void sts128(unsigned a, float x, float y, float z, float w) {
+    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(x), "f"(y), "f"(z), "f"(w) : "memory");
+}
+__device__ __forceinline__ void sts32i(unsigned a, int v) { asm volatile("st.shared.s32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
 __device__ __forceinline__ void sts32(unsigned a, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(v) : "memory"); }
 __device__ __forceinline__ void sts64(unsigned a, float2 v) {
     asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(a), "f"(v.x), "f"(v.y) : "memory");
@@ -236,6 +244,29 @@ struct LinSmem {
     }
 };
 
+// Length-balanced placement of a one-wave launch.  The batch is sorted by length, longest first
+// (dataloader.py:53), and the hardware hands cluster c of a fresh launch to SM pair c mod `pairs`, layer by
+// layer.  With n = full * pairs + rem clusters the first `rem` SM pairs host full + 1 clusters and the others
+// `full`.  mode 1: the pairs with the extra cluster take the SHORTEST (full + 1) * rem utterances, the others
+// the longest full * (pairs - rem), and inside either group consecutive layers run in opposite directions
+// (boustrophedon), so that every SM pair carries about the same number of frames.  mode 2: plain
+// boustrophedon over the layers of the launch.
+__device__ __forceinline__ int lin_map_utt(int c, int n, int pairs, int mode) {
+    if (pairs <= 0 || n <= pairs) return c;
+    const int full = n / pairs, rem = n - full * pairs;
+    const int L = c / pairs, j = c - L * pairs;
+    if (rem == 0 || mode == 2) {
+        const int width = min(pairs, n - L * pairs);
+        return L * pairs + ((L & 1) ? width - 1 - j : j);
+    }
+    const int m = pairs - rem;                 // SM pairs with `full` clusters
+    if (j >= rem) {
+        const int jj = j - rem;
+        return L * m + ((L & 1) ? m - 1 - jj : jj);
+    }
+    return full * m + L * rem + ((L & 1) ? rem - 1 - j : j);
+}
+
 // Template parameters: P pairs per thread; RC = number of recursion warps when it is known at
 // compile time (1: the common case S + P <= 32 * P, every stride becomes an immediate) or 0 for
 // "run time"; YS = floats per row of the emission ring (compile time) or 0 for "run time".
@@ -313,8 +344,12 @@ ctc_lin_kernel(const PipeParams pp, int* __restrict__ flags) {
             break;
         }
     } else {
-        b_local = (int)(blockIdx.x >> 1) + pp.utt_rot;
-        if (b_local >= (int)(gridDim.x >> 1)) b_local -= (int)(gridDim.x >> 1);
+        if (pp.map_mode != 0) {
+            b_local = lin_map_utt((int)(blockIdx.x >> 1), (int)(gridDim.x >> 1), pp.map_pairs, pp.map_mode);
+        } else {
+            b_local = (int)(blockIdx.x >> 1) + pp.utt_rot;
+            if (b_local >= (int)(gridDim.x >> 1)) b_local -= (int)(gridDim.x >> 1);
+        }
     }
     const int b = p.utt_begin + b_local;
     int Tb = p.in_lens[b], S = p.tgt_lens[b];
@@ -580,7 +615,7 @@ ctc_lin_kernel(const PipeParams pp, int* __restrict__ flags) {
         Ring ring_y(NL);                  // position of the chunk REC works on
         int a_buf = 0;
         renorm();                         // normalises the start value
-        for (int it = 0; it < n_it; ++it) {
+        auto rec_iter = [&](int it) {
             const int k = it - 1;
             LPROF_BEGIN();
             if (k >= 0 && k < nch) {
@@ -642,7 +677,119 @@ ctc_lin_kernel(const PipeParams pp, int* __restrict__ flags) {
                 cluster_sync_all();
                 __syncthreads();
             }
+        };
+        int it = 0;
+        if constexpr (FIX) {
+            // The headline shape class with a gradient, full chunks, in loops of their own.  Emissions of step
+            // r + 1 are loaded BEFORE the row of step r is stored (loads cannot be hoisted over shared-memory
+            // stores), and the first half publishes its pre-emission rows in the shared-memory ring as well: the
+            // combine warps, idle until the phase break, copy them to HBM (a recursion warp that stores to HBM
+            // itself waits for every store to have read its registers before it may overwrite them).
+            if (wg) {
+                constexpr unsigned RSB = 544u * 4u, YSB = 80u * 4u, YCH = 4u * YSB;
+                unsigned labo[P];
+#pragma unroll
+                for (int q = 0; q < P; ++q) labo[q] = (unsigned)lab[q] * 4u;
+                const unsigned blo = (unsigned)blank * 4u;
+                const unsigned ar0 = sbase + lay.a + (unsigned)lane * 16u;
+                const unsigned exo = 2048u + (unsigned)lane * 4u - (unsigned)lane * 16u;   // my exponent, from my blank cells
+                auto load_y = [&](unsigned yrow, float (&y)[P + 1]) {
+#pragma unroll
+                    for (int q = 0; q < P; ++q) y[q] = lds32(yrow + labo[q]);
+                    y[P] = lds32(yrow + blo);
+                };
+                // one recursion step with the emissions in registers (see `advance`)
+                auto advance_y = [&](const float (&y)[P + 1], float (&xs)[P], float (&ins)[P]) {
+                    const float yb = fabsf(y[P]);
+                    float v = __shfl_up_sync(0xffffffffu, aY[P - 1], 1);
+                    const int o = __shfl_up_sync(0xffffffffu, off, 1);
+                    if (lane0) v = 0.f;
+                    if (u > c_i) v = 0.f;
+                    const float am1 = v * pow2c(o - off);
+#pragma unroll
+                    for (int k = P - 1; k >= 0; --k) {
+                        const float prev = k > 0 ? aY[k > 0 ? k - 1 : 0] : am1;
+                        const float x = aB[k] + prev;
+                        const float in = fmaf(skf[k], prev, aY[k] + aB[k]);
+                        xs[k] = x;
+                        ins[k] = in;
+                        aB[k] = yb * x;
+                        aY[k] = fabsf(y[k]) * in;
+                    }
+                };
+                for (; it < n_it && it < 1; ++it) rec_iter(it);
+                int pbuf = 0;
+                for (; it < n1; ++it) {          // chunk it - 1 in [0, n1 - 1): first half, full chunk
+                    LPROF_BEGIN();
+                    const unsigned yb0 = sbase + lay.y + (unsigned)ring_y.slot * YCH;
+                    const unsigned ar = ar0 + (unsigned)pbuf * (4u * RSB);
+#if !CTC_LIN_P1RING
+                    float* grow = p.lattice + ((long long)(b - p.utt_begin) * p.lat_utt_stride +
+                                               (long long)(tbase + tsign * (it - 1) * 4) * RS + s0p);
+#endif
+                    float ya[P + 1], yn[P + 1];
+                    load_y(yb0, ya);
+#pragma unroll
+                    for (int r = 0; r < 4; ++r) {
+                        if (r < 3) load_y(yb0 + (unsigned)(r + 1) * YSB, yn);
+                        float xs[P], ins[P];
+                        advance_y(ya, xs, ins);
+#if CTC_LIN_P1RING
+                        const unsigned a = ar + (unsigned)r * RSB;
+                        sts128(a, xs[0], xs[1], xs[2], xs[3]);
+                        sts128(a + 512u, xs[4], xs[5], xs[6], xs[7]);
+                        sts128(a + 1024u, ins[0], ins[1], ins[2], ins[3]);
+                        sts128(a + 1536u, ins[4], ins[5], ins[6], ins[7]);
+                        sts32i(a + exo, off);
+#else
+                        if ((unsigned)(u + P) < win_store) {
+                            store_row<P>(grow, xs, HS);
+                            store_row<P>(grow + NP, ins, HS);
+                            *reinterpret_cast<int*>(grow + offd) = off;
+                        }
+                        grow += row_step;
+#endif
+                        ++u;
+#pragma unroll
+                        for (int q = 0; q <= P; ++q) ya[q] = yn[q];
+                    }
+                    renorm();
+                    ring_y.advance();
+                    pbuf ^= 1;
+                    LPROF_END(false);
+                    __syncthreads();
+                }
+                for (; it < n_it && it <= n1; ++it) rec_iter(it);     // last chunk of the first half, phase break
+                for (; it < nch; ++it) {         // chunk it - 1 in [n1, nch - 1): second half, full chunk
+                    LPROF_BEGIN();
+                    const unsigned yb0 = sbase + lay.y + (unsigned)ring_y.slot * YCH;
+                    const unsigned ar = ar0 + (unsigned)a_buf * (4u * RSB);
+                    float ya[P + 1], yn[P + 1];
+                    load_y(yb0, ya);
+#pragma unroll
+                    for (int r = 0; r < 4; ++r) {
+                        if (r < 3) load_y(yb0 + (unsigned)(r + 1) * YSB, yn);
+                        float xs[P], ins[P];
+                        advance_y(ya, xs, ins);
+                        const unsigned a = ar + (unsigned)r * RSB;
+                        sts128(a, aB[0], aB[1], aB[2], aB[3]);
+                        sts128(a + 512u, aB[4], aB[5], aB[6], aB[7]);
+                        sts128(a + 1024u, aY[0], aY[1], aY[2], aY[3]);
+                        sts128(a + 1536u, aY[4], aY[5], aY[6], aY[7]);
+                        sts32i(a + exo, off);
+                        ++u;
+#pragma unroll
+                        for (int q = 0; q <= P; ++q) ya[q] = yn[q];
+                    }
+                    renorm();
+                    ring_y.advance();
+                    a_buf ^= 1;
+                    LPROF_END(true);
+                    __syncthreads();
+                }
+            }
         }
+        for (; it < n_it; ++it) rec_iter(it);
     } else if (is_comb) {
         // =============================================================================
         // COMB: occupancies of the second half = REC's row x the partner's stored row
@@ -964,6 +1111,39 @@ ctc_lin_kernel(const PipeParams pp, int* __restrict__ flags) {
             // offset from a running 32-bit base; what only the general path needs is not live in here.
             static_assert(!FIX || kLinPDist == 2, "the steady-state loop requests the partner rows two chunks ahead");
             const int it_fast_end = wgc ? nch_i + 1 : 0;
+            if (wgc) {
+                // First half: the recursion warp publishes the pre-emission rows of chunk it - 1 in the
+                // shared-memory ring (full chunks 0 .. n1 - 2); this warp copies rows cg and cg + 2 of chunk
+                // it - 2 to the lattice in HBM, inside the same band of cells the recursion warp would store.
+                const unsigned win_copy = (i0 - P <= S) ? (unsigned)(C + 3 * P) : 0u;
+                const unsigned cp0 = sbase + lay.a + (unsigned)lane * 16u;
+                const unsigned exo = 2048u + (unsigned)lane * 4u - (unsigned)lane * 16u;
+                auto copy_chunk = [&](int k) {
+                    const unsigned src = cp0 + (unsigned)(k & 1) * (4u * 544u * 4u);
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        const int rr = cg + 2 * h, tt = 4 * k + rr;
+                        if ((unsigned)(tt - i0 + P) < win_copy) {
+                            const unsigned a = src + (unsigned)rr * (544u * 4u);
+                            const float4 v0 = lds128(a), v1 = lds128(a + 512u), v2 = lds128(a + 1024u), v3 = lds128(a + 1536u);
+                            const int e = lds32i(a + exo);
+                            float* dst = lat_b + (ptrdiff_t)(tbase + tsign * tt) * 544 + lane * 4;
+                            *reinterpret_cast<float4*>(dst) = v0;
+                            *reinterpret_cast<float4*>(dst + 128) = v1;
+                            *reinterpret_cast<float4*>(dst + 256) = v2;
+                            *reinterpret_cast<float4*>(dst + 384) = v3;
+                            *reinterpret_cast<int*>(dst + 512 + lane - lane * 4) = e;
+                        }
+                    }
+                };
+#if CTC_LIN_P1RING
+                for (; it < n1_i; ++it) {
+                    if (it >= 2) copy_chunk(it - 2);
+                    __syncthreads();
+                }
+                if (it == n1_i && n1_i >= 2) copy_chunk(n1_i - 2);
+#endif
+            }
             for (; it < n_it && it < n1_i + 3; ++it) comb_iter(it);
             if (it < it_fast_end) {
                 if (cg > 0) { E0 = s_red[100]; rz = __int_as_float(s_red[101]); }

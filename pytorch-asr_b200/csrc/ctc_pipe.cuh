@@ -35,6 +35,8 @@ struct PipeParams {
     int rotate;    // CTAs per launch "layer" (= #SMs): co-resident CTAs rotate their warp roles
     const int* redo;  // [2 * N] or nullptr: run only utterances the linear kernel flagged (ctc_lin.cuh)
     int utt_rot;      // linear kernel: cluster c works on utterance (c + utt_rot) mod n_utt (CTA placement)
+    int map_mode;     // linear kernel: 0 = rotation only; 1 / 2 = length-balanced placement (lin_map_utt)
+    int map_pairs;    // SM pairs of the device (clusters per launch "layer")
     int* queue;       // linear kernel, persistent launch: {next utterance, clusters that ran dry}; nullptr: one cluster per utterance
     int n_utt;        // utterances of this launch (queue mode)
 };
