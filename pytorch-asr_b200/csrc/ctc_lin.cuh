@@ -1914,7 +1914,13 @@ ctc_lin_kernel(const PipeParams pp, int* __restrict__ flags) {
 #endif
     // every CTA reports whether its half passed; the log-domain kernel redoes flagged utterances
     __syncthreads();
-#ifdef CTC_B200_MASSDEV   // developer build: report the largest posterior-mass deviation instead of the flag
+#if defined(CTC_B200_ENDTIME)   // developer build: when did this CTA finish (globaltimer, ns, low bits)
+    if (threadIdx.x == 0) {
+        unsigned long long t_;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_));
+        flags[2 * b + (rev ? 1 : 0)] = (int)(t_ & 0x3fffffffull);
+    }
+#elif defined(CTC_B200_MASSDEV)   // developer build: report the largest posterior-mass deviation instead of the flag
     if (threadIdx.x == 0) flags[2 * b + (rev ? 1 : 0)] = s_flag[1] ? 0x7f800000 : s_flag[2];
 #else
     if (threadIdx.x == 0) flags[2 * b + (rev ? 1 : 0)] = s_flag[0];

@@ -249,3 +249,55 @@ def test_persistent_queue_launch():
         torch.cuda.synchronize()
         assert np.array_equal(p2.nll.cpu().numpy(), nll[lo:hi])
         assert np.array_equal(p2.grad.cpu().numpy(), grad[:, lo:hi])
+
+
+@pytest.mark.parametrize("t_lo,t_hi,mode", [(1, 64, "plain"), (1, 64, "ntv+clamp"), (60, 200, "plain"),
+                                            (60, 200, "ntv+clamp"), (3, 40, "peaky")])
+def test_headline_instantiation_every_length(t_lo, t_hi, mode):
+    """ctc_lin_kernel<8,1,80,128,4,FIX> runs its full chunks in steady-state loops of their own and everything
+    else (short chunks, the phase break, the drain, T_b of a few frames) through the general iteration: one
+    utterance of EVERY length T_b in [t_lo, t_hi] (so that every count of first-half and second-half chunks, with
+    and without a short last chunk, occurs), targets from empty to the longest feasible, against the fp64 oracle
+    at the flat bounds; rows t >= T_b exact zeros; no utterance may need the fallback."""
+    g = torch.Generator().manual_seed(1000 + t_lo + t_hi)
+    V, T = 48, t_hi
+    il = torch.arange(t_hi, t_lo - 1, -1, dtype=torch.int32)        # sorted, longest first (dataloader.py:53)
+    B = il.numel()
+    tl = torch.minimum((torch.rand(B, generator=g) * 0.55 * il).to(torch.int32), il // 2).to(torch.int32)
+    tl[::7] = 0                                                     # empty targets
+    tg = torch.randint(1, V, (int(tl.sum()),), generator=g, dtype=torch.int32)
+    for i in range(1, tg.numel(), 5):
+        tg[i] = tg[i - 1]                                           # adjacent repeats (no-skip rule)
+    acts = torch.randn(T, B, V, generator=g)
+    if mode == "peaky":
+        acts = acts * 4.0
+        acts[:, :, 0] += 6.0
+    geo = cabi.geometry(T, B, V, int(tl.max()))
+    assert geo["variant_name"] == "ctc_lin_kernel<8,1,80,128,4,FIX>", geo
+    if mode == "ntv+clamp":
+        x, lo, hi = acts * 1.5, -3.0, 3.0
+        prob = cabi.DeviceProblem(x.transpose(0, 1).contiguous(), tg, il, tl, reduction="sum", batch_major=True,
+                                  clamp=(lo, hi))
+        ref_in, mask = x.clamp(lo, hi), ((x > lo) & (x < hi)).numpy()
+    else:
+        prob = cabi.DeviceProblem(acts, tg, il, tl, reduction="sum")
+        ref_in, mask = acts, None
+    prob.grad.fill_(float("nan"))
+    prob.run()
+    torch.cuda.synchronize()
+    prob.check_status()
+    orc = oracle.ctc_oracle_f64(ref_in.numpy(), tg.numpy(), il.numpy(), tl.numpy())
+    nll, grad = prob.nll.cpu().numpy(), prob.grad.cpu().numpy()
+    if mode == "ntv+clamp":
+        grad = grad.transpose(1, 0, 2)
+    fin = np.isfinite(orc["nll"])
+    assert (np.isfinite(nll) == fin).all()
+    rel = np.abs(nll[fin] - orc["nll"][fin]) / np.maximum(np.abs(orc["nll"][fin]), 1e-30)
+    assert rel.max() <= NLL_RTOL, rel.max()
+    want = orc["grad"] if mask is None else orc["grad"] * mask
+    assert not np.isnan(grad[:, fin]).any()
+    assert np.abs(grad[:, fin] - want[:, fin]).max() <= GRAD_ATOL
+    for b in range(B):
+        assert not grad[int(il[b]):, b].any()
+    flagged = prob.flags_view().cpu().view(-1, 2).abs().sum(1) > 0
+    assert not flagged[torch.from_numpy(fin)].any(), "feasible utterances must not need the fallback"
