@@ -63,7 +63,9 @@ typedef struct ctc_b200_options {
                                         clusters and let them pull utterances from a device-side queue (longest first).
                                         Off by default: measured on B200 the hardware CTA scheduler, which hands the
                                         next cluster of the grid to the first free slot, does exactly as well
-                                        (B = 512: 0.437 ms both ways; B = 1024: 0.865 vs 0.857 ms). */
+                                        (B = 512: 0.437 ms both ways; B = 1024: 0.865 vs 0.857 ms).  Honoured for the
+                                        headline shape class only (V = 48, targets up to 248 labels; the loop around
+                                        the utterance is a separate instantiation there) and ignored otherwise. */
 } ctc_b200_options;
 
 typedef enum ctc_b200_reduction {

@@ -301,7 +301,7 @@ int launch_fused(const float* acts, const int32_t* targets, const int32_t* tgt_o
         // let them pull utterances from a device-side queue, longest first.  Off by default -- the hardware
         // CTA scheduler already hands the next cluster of the grid to the first free slot, in the same order.
         const bool want_persist = env().persist > 0 || (env().persist < 0 && opt && opt->persistent);
-        const int resident = (want_persist && queue) ? lin_resident_clusters(g, V) : 0;
+        const int resident = (want_persist && queue && lin_supports_queue(g, V)) ? lin_resident_clusters(g, V) : 0;
         if (resident > 0 && utt_count > resident) {
             lp.queue = queue;
             n_clusters = std::min(resident, utt_count);

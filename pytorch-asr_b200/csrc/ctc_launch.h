@@ -77,6 +77,8 @@ const char* lin_variant_name(int id);
 cudaError_t launch_lin(const PipeParams& pp, int* flags, const Geometry& g, int n_clusters, cudaStream_t st);
 // co-resident clusters of the instantiation `g` selects, on the current device (0 when it cannot be queried)
 int lin_resident_clusters(const Geometry& g, int V);
+// persistent launches (utterance queue) exist for the headline shape class only
+bool lin_supports_queue(const Geometry& g, int V);
 
 int pipe_variant(const Geometry& g);
 const char* pipe_variant_name(int id);

@@ -20,6 +20,8 @@ enum LinVariant {
     kLinRn256,          // <8,0,0,256,2>       several recursion warps, run-time strides, <= 256 threads
     kLinRn512,          // <8,0,0,512,1>
     kLinRn1024,         // <8,0,0,1024,1>
+    kLinFixQueue,       // <8,1,80,128,4,FIX,QUEUE>  the headline shape class as a persistent launch (not reported as a
+                        // variant of its own: same code, wrapped in the loop over the utterance queue)
     kLinCount
 };
 
@@ -27,6 +29,7 @@ const char* const kLinNames[kLinCount] = {
     "ctc_lin_kernel<8,1,80,128,4,FIX>", "ctc_lin_kernel<8,1,80,128,4>", "ctc_lin_kernel<8,1,0,128,4>",
     "ctc_lin_kernel<8,1,0,256,2>",      "ctc_lin_kernel<8,2,80,512,1>", "ctc_lin_kernel<8,4,80,512,1>",
     "ctc_lin_kernel<8,0,0,256,2>",      "ctc_lin_kernel<8,0,0,512,1>",  "ctc_lin_kernel<8,0,0,1024,1>",
+    "ctc_lin_kernel<8,1,80,128,4,FIX,QUEUE>",
 };
 
 using LinKernel = void (*)(const PipeParams, int*);
@@ -42,6 +45,7 @@ LinKernel lin_kernel(int id) {
         case kLinRn256: return ctc_lin_kernel<8, 0, 0, 256, 2>;
         case kLinRn512: return ctc_lin_kernel<8, 0, 0, 512, 1>;
         case kLinRn1024: return ctc_lin_kernel<8, 0, 0, 1024, 1>;
+        case kLinFixQueue: return ctc_lin_kernel<8, 1, 80, 128, 4, true, true>;
     }
     return nullptr;
 }
@@ -77,8 +81,14 @@ int lin_row_stride_host(int NP, int P) { return lin_row_stride(NP, P); }
 
 const char* lin_variant_name(int id) { return id >= 0 && id < kLinCount ? kLinNames[id] : "?"; }
 
+bool lin_supports_queue(const Geometry& g, int V) { return lin_variant(g, V) == kLinFix; }
+
 cudaError_t launch_lin(const PipeParams& pp, int* flags, const Geometry& g, int n_clusters, cudaStream_t st) {
-    const int id = lin_variant(g, pp.f.V);
+    int id = lin_variant(g, pp.f.V);
+    if (pp.queue != nullptr) {
+        if (id != kLinFix) return last_cuda_error_set(cudaErrorInvalidConfiguration);   // (the caller asks lin_supports_queue)
+        id = kLinFixQueue;
+    }
     LinKernel k = lin_kernel(id);
     if (!k) return last_cuda_error_set(cudaErrorInvalidConfiguration);
     cudaError_t e = ensure_smem(reinterpret_cast<const void*>(k), g_marks[id], g.lsmem);
@@ -88,7 +98,8 @@ cudaError_t launch_lin(const PipeParams& pp, int* flags, const Geometry& g, int 
 }
 
 int lin_resident_clusters(const Geometry& g, int V) {
-    const int id = lin_variant(g, V);
+    int id = lin_variant(g, V);
+    if (id == kLinFix) id = kLinFixQueue;   // what a persistent launch would run
     LinKernel k = lin_kernel(id);
     if (!k) return 0;
     if (ensure_smem(reinterpret_cast<const void*>(k), g_marks[id], g.lsmem) != cudaSuccess) {

@@ -272,7 +272,9 @@ __device__ __forceinline__ int lin_map_utt(int c, int n, int pairs, int mode) {
 // "run time"; YS = floats per row of the emission ring (compile time) or 0 for "run time".
 // FIX: the headline shape class (V = 48, one helper warp, two combine groups, 128 threads) with all
 // of these as compile-time constants.
-template <int P, int RC, int YS, int MAXT, int MINB, bool FIX = false>
+// QUEUE: persistent launch (pp.queue; instantiated for the headline shape class only -- the loop around the
+// whole utterance costs the other instantiations 6 ... 18 % when it is merely present).
+template <int P, int RC, int YS, int MAXT, int MINB, bool FIX = false, bool QUEUE = false>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(MAXT, MINB)
 ctc_lin_kernel(const PipeParams pp, int* __restrict__ flags) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -322,11 +324,12 @@ ctc_lin_kernel(const PipeParams pp, int* __restrict__ flags) {
     // atomic queue in index order -- the batch is sorted by length, longest first, so this is the
     // longest-processing-time-first schedule and the tail of the launch is filled with the SHORT utterances.
     int& s_next = s_flag[3];
+    int* const queue_ = QUEUE ? pp.queue : nullptr;
     for (;;) {
     int b_local;
-    if (pp.queue != nullptr) {
+    if (queue_ != nullptr) {
         __syncthreads();                     // the previous utterance is done with this CTA's shared memory
-        if (threadIdx.x == 0 && (blockIdx.x & 1) == 0) s_next = atomicAdd(pp.queue, 1);
+        if (threadIdx.x == 0 && (blockIdx.x & 1) == 0) s_next = atomicAdd(queue_, 1);
         cluster_sync_all();                  // rank 0's ticket is visible to rank 1 (release / acquire)
         {
             unsigned remote;
@@ -337,9 +340,9 @@ ctc_lin_kernel(const PipeParams pp, int* __restrict__ flags) {
         if (b_local >= pp.n_utt) {
             // the last cluster to run dry re-arms the queue for the next launch on this stream
             if (threadIdx.x == 0 && (blockIdx.x & 1) == 0 &&
-                atomicAdd(pp.queue + 1, 1) == (int)(gridDim.x >> 1) - 1) {
-                pp.queue[0] = 0;
-                pp.queue[1] = 0;
+                atomicAdd(queue_ + 1, 1) == (int)(gridDim.x >> 1) - 1) {
+                queue_[0] = 0;
+                queue_[1] = 0;
             }
             break;
         }
@@ -403,7 +406,7 @@ ctc_lin_kernel(const PipeParams pp, int* __restrict__ flags) {
             flags[2 * b + (rev ? 1 : 0)] = 0;
             if (!rev) p.nll[b] = (S == 0 || p.zero_infinity) ? 0.0f : CUDART_INF_F;
         }
-        if (pp.queue != nullptr) continue;
+        if (queue_ != nullptr) continue;
         return;  // both CTAs of the cluster take this exit
     }
 
@@ -1313,7 +1316,10 @@ ctc_lin_kernel(const PipeParams pp, int* __restrict__ flags) {
         };
 
         // V = 48 with four frames per pass: straight-line code, the row stays in registers
-        auto softmax_fast = [&](float* base, int rows, const float2 (&lg)[3]) {
+        auto softmax_fast = [&](auto CL, float* base, int rows, const float2 (&lg)[3]) {
+                constexpr bool CLAMPED = decltype(CL)::value;   // compile-time copy of clp.on (uniform branch at the call)
+                const Clamp clq{CLAMPED, clp.lo, clp.hi};
+                (void)clq;
             const bool act = fA < rows;
             float* row = base + min(fA, rows - 1) * Vs;
             float2* row2 = reinterpret_cast<float2*>(row);
@@ -1321,12 +1327,12 @@ ctc_lin_kernel(const PipeParams pp, int* __restrict__ flags) {
 #pragma unroll
             for (int j = 0; j < 3; ++j) x[j] = act ? lg[j] : make_float2(0.f, 0.f);
             unsigned mk = 0u;                  // fused Hardtanh: bit 2j / 2j+1 = gradient blocked
-            if (clp.on) {
+            if (clq.on) {
 #pragma unroll
                 for (int j = 0; j < 3; ++j) {
-                    mk |= (clp.cmask(x[j].x) ? 1u : 0u) << (2 * j) | (clp.cmask(x[j].y) ? 1u : 0u) << (2 * j + 1);
-                    x[j].x = clp.cin(x[j].x);
-                    x[j].y = clp.cin(x[j].y);
+                    mk |= (clq.cmask(x[j].x) ? 1u : 0u) << (2 * j) | (clq.cmask(x[j].y) ? 1u : 0u) << (2 * j + 1);
+                    x[j].x = clq.cin(x[j].x);
+                    x[j].y = clq.cin(x[j].y);
                 }
             }
             float m = fmaxf(fmaxf(fmaxf(x[0].x, x[0].y), fmaxf(x[1].x, x[1].y)), fmaxf(x[2].x, x[2].y));
@@ -1361,7 +1367,10 @@ ctc_lin_kernel(const PipeParams pp, int* __restrict__ flags) {
         // ---- fused softmax, in place, of my F frames of a chunk (a group of G lanes per frame) ----
         // The maximum of a row comes from ONE redux.sync per group (no shuffle tree); the sum needs
         // log2 G shuffle levels.
-        auto softmax_chunk = [&](float* base, int rows) {
+        auto softmax_chunk = [&](auto CL, float* base, int rows) {
+                constexpr bool CLAMPED = decltype(CL)::value;   // compile-time copy of clp.on (uniform branch at the call)
+                const Clamp clq{CLAMPED, clp.lo, clp.hi};
+                (void)clq;
             const int G = GA, gl = glA, f = fA;
             const unsigned gmask = gmaskA;
             const bool act = f < rows;
@@ -1369,14 +1378,14 @@ ctc_lin_kernel(const PipeParams pp, int* __restrict__ flags) {
             float2* row2 = reinterpret_cast<float2*>(row);
             if (!al) {      // rows that are not 16-byte aligned in HBM (V % 4 != 0): scalar passes
                 float m = -CUDART_INF_F, z = 0.f;
-                for (int c = gl; c < V; c += G) m = fmaxf(m, clp.cin(row[c]));
+                for (int c = gl; c < V; c += G) m = fmaxf(m, clq.cin(row[c]));
                 m = group_max(m, G);
-                for (int c = gl; c < V; c += G) z += ex2f((clp.cin(row[c]) - m) * kLog2e);
+                for (int c = gl; c < V; c += G) z += ex2f((clq.cin(row[c]) - m) * kLog2e);
                 const float rs = 1.0f / group_sum(z, G);
                 if (act) {
                     for (int c = gl; c < V; c += G) {
-                        const float raw = row[c], y = ex2f((clp.cin(raw) - m) * kLog2e) * rs;
-                        row[c] = clp.cmask(raw) ? -y : y;
+                        const float raw = row[c], y = ex2f((clq.cin(raw) - m) * kLog2e) * rs;
+                        row[c] = clq.cmask(raw) ? -y : y;
                     }
                     for (int c = V + gl; c < Vs; c += G) row[c] = 0.f;   // slot V: what padding pairs gather
                 }
@@ -1386,7 +1395,7 @@ ctc_lin_kernel(const PipeParams pp, int* __restrict__ flags) {
                 float2 lg[3];
 #pragma unroll
                 for (int j = 0; j < 3; ++j) lg[j] = row2[gl + 8 * j];
-                softmax_fast(base, rows, lg);
+                softmax_fast(CL, base, rows, lg);
                 return;
             }
             if (V2 <= 4 * G) {      // at most 4 float2 per lane: the row stays in registers
@@ -1397,10 +1406,10 @@ ctc_lin_kernel(const PipeParams pp, int* __restrict__ flags) {
                 for (int j = 0; j < 4; ++j) {
                     const int c = gl + j * G;
                     x[j] = c < V2 ? row2[c] : make_float2(-CUDART_INF_F, -CUDART_INF_F);
-                    if (clp.on && c < V2) {
-                        mk |= (clp.cmask(x[j].x) ? 1u : 0u) << (2 * j) | (clp.cmask(x[j].y) ? 1u : 0u) << (2 * j + 1);
-                        x[j].x = clp.cin(x[j].x);
-                        x[j].y = clp.cin(x[j].y);
+                    if (clq.on && c < V2) {
+                        mk |= (clq.cmask(x[j].x) ? 1u : 0u) << (2 * j) | (clq.cmask(x[j].y) ? 1u : 0u) << (2 * j + 1);
+                        x[j].x = clq.cin(x[j].x);
+                        x[j].y = clq.cin(x[j].y);
                     }
                     m = fmaxf(m, fmaxf(x[j].x, x[j].y));
                 }
@@ -1436,11 +1445,11 @@ ctc_lin_kernel(const PipeParams pp, int* __restrict__ flags) {
                 for (int j = 0; j < 8; ++j) {
                     const int c = gl + j * G;
                     x[j] = c < V4 ? row4[c] : make_float4(-CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F);
-                    if (clp.on && c < V4) {
-                        mk |= ((clp.cmask(x[j].x) ? 1u : 0u) | (clp.cmask(x[j].y) ? 2u : 0u) |
-                               (clp.cmask(x[j].z) ? 4u : 0u) | (clp.cmask(x[j].w) ? 8u : 0u)) << (4 * j);
-                        x[j].x = clp.cin(x[j].x); x[j].y = clp.cin(x[j].y);
-                        x[j].z = clp.cin(x[j].z); x[j].w = clp.cin(x[j].w);
+                    if (clq.on && c < V4) {
+                        mk |= ((clq.cmask(x[j].x) ? 1u : 0u) | (clq.cmask(x[j].y) ? 2u : 0u) |
+                               (clq.cmask(x[j].z) ? 4u : 0u) | (clq.cmask(x[j].w) ? 8u : 0u)) << (4 * j);
+                        x[j].x = clq.cin(x[j].x); x[j].y = clq.cin(x[j].y);
+                        x[j].z = clq.cin(x[j].z); x[j].w = clq.cin(x[j].w);
                     }
                     m = fmaxf(m, fmaxf(fmaxf(x[j].x, x[j].y), fmaxf(x[j].z, x[j].w)));
                 }
@@ -1472,19 +1481,19 @@ ctc_lin_kernel(const PipeParams pp, int* __restrict__ flags) {
                 float m = -CUDART_INF_F, z = 0.f;
                 for (int c = gl; c < V2; c += G) {
                     const float2 x = row2[c];
-                    m = fmaxf(m, fmaxf(clp.cin(x.x), clp.cin(x.y)));
+                    m = fmaxf(m, fmaxf(clq.cin(x.x), clq.cin(x.y)));
                 }
                 asm volatile("redux.sync.max.f32 %0, %1, %2;" : "=f"(m) : "f"(m), "r"(gmask));
                 for (int c = gl; c < V2; c += G) {
                     const float2 x = row2[c];
-                    z += ex2f((clp.cin(x.x) - m) * kLog2e) + ex2f((clp.cin(x.y) - m) * kLog2e);
+                    z += ex2f((clq.cin(x.x) - m) * kLog2e) + ex2f((clq.cin(x.y) - m) * kLog2e);
                 }
                 const float rs = 1.0f / group_sum(z, G);
                 if (act)
                     for (int c = gl; c < V2; c += G) {
                         const float2 x = row2[c];
-                        const float a = ex2f((clp.cin(x.x) - m) * kLog2e) * rs, d = ex2f((clp.cin(x.y) - m) * kLog2e) * rs;
-                        row2[c] = make_float2(clp.cmask(x.x) ? -a : a, clp.cmask(x.y) ? -d : d);
+                        const float a = ex2f((clq.cin(x.x) - m) * kLog2e) * rs, d = ex2f((clq.cin(x.y) - m) * kLog2e) * rs;
+                        row2[c] = make_float2(clq.cmask(x.x) ? -a : a, clq.cmask(x.y) ? -d : d);
                     }
             }
             if (act && gl == 0) row[V] = 0.f;  // what padding pairs gather
@@ -1496,7 +1505,10 @@ ctc_lin_kernel(const PipeParams pp, int* __restrict__ flags) {
         //   The sum of ALL occupancies of a frame must be 1: the posterior-mass check.
         //   All loads are issued up front and the two reductions (blank sum, total) share their
         //   shuffle levels, so that the pass is one short dependent chain.
-        auto grad_chunk = [&](float* obase, const float* ybase, int tt0, int rows) {
+        auto grad_chunk = [&](auto CL, float* obase, const float* ybase, int tt0, int rows) {
+                constexpr bool CLAMPED = decltype(CL)::value;   // compile-time copy of clp.on (uniform branch at the call)
+                const Clamp clq{CLAMPED, clp.lo, clp.hi};
+                (void)clq;
             const int G = GB, gl = glB, f = fB;
             const bool act = f < rows;
             const int fr = min(f, rows - 1);
@@ -1535,8 +1547,8 @@ ctc_lin_kernel(const PipeParams pp, int* __restrict__ flags) {
                     const bool mine = cb == gl + 8 * j;
                     const float ox = o[j].x + (mine ? addx : 0.f), oy = o[j].y + (mine ? addy : 0.f);
                     // (a set sign bit of y: the fused Hardtanh blocks this entry's gradient)
-                    if (act) g2[gl + 8 * j] = make_float2(__float_as_int(y[j].x) < 0 ? 0.f : gscale * (y[j].x - ox),
-                                                          __float_as_int(y[j].y) < 0 ? 0.f : gscale * (y[j].y - oy));
+                    if (act) g2[gl + 8 * j] = make_float2((CLAMPED && __float_as_int(y[j].x) < 0) ? 0.f : gscale * (y[j].x - ox),
+                                                          (CLAMPED && __float_as_int(y[j].y) < 0) ? 0.f : gscale * (y[j].y - oy));
                 }
                 if (act && !(fabsf(tot + bs - 1.0f) <= kMassTol)) s_flag[0] = 1;   // NaN-safe
 #ifdef CTC_B200_MASSDEV
@@ -1574,8 +1586,8 @@ ctc_lin_kernel(const PipeParams pp, int* __restrict__ flags) {
                         const int c = gl + j * G;
                         if (c < V2) {
                             if ((blank >> 1) == c) { if (blank & 1) o[j].y += bs; else o[j].x += bs; }
-                            g2[c] = make_float2(__float_as_int(y[j].x) < 0 ? 0.f : gscale * (y[j].x - o[j].x),
-                                                __float_as_int(y[j].y) < 0 ? 0.f : gscale * (y[j].y - o[j].y));
+                            g2[c] = make_float2((CLAMPED && __float_as_int(y[j].x) < 0) ? 0.f : gscale * (y[j].x - o[j].x),
+                                                (CLAMPED && __float_as_int(y[j].y) < 0) ? 0.f : gscale * (y[j].y - o[j].y));
                         }
                     }
                     if (!(fabsf(tot + bs - 1.0f) <= kMassTol)) s_flag[0] = 1;   // NaN-safe
@@ -1626,10 +1638,10 @@ ctc_lin_kernel(const PipeParams pp, int* __restrict__ flags) {
                             o[j].y += (mine && kb == 1) ? bs : 0.f;
                             o[j].z += (mine && kb == 2) ? bs : 0.f;
                             o[j].w += (mine && kb == 3) ? bs : 0.f;
-                            g4[c] = make_float4(__float_as_int(y[j].x) < 0 ? 0.f : gscale * (y[j].x - o[j].x),
-                                                __float_as_int(y[j].y) < 0 ? 0.f : gscale * (y[j].y - o[j].y),
-                                                __float_as_int(y[j].z) < 0 ? 0.f : gscale * (y[j].z - o[j].z),
-                                                __float_as_int(y[j].w) < 0 ? 0.f : gscale * (y[j].w - o[j].w));
+                            g4[c] = make_float4((CLAMPED && __float_as_int(y[j].x) < 0) ? 0.f : gscale * (y[j].x - o[j].x),
+                                                (CLAMPED && __float_as_int(y[j].y) < 0) ? 0.f : gscale * (y[j].y - o[j].y),
+                                                (CLAMPED && __float_as_int(y[j].z) < 0) ? 0.f : gscale * (y[j].z - o[j].z),
+                                                (CLAMPED && __float_as_int(y[j].w) < 0) ? 0.f : gscale * (y[j].w - o[j].w));
                         }
                     }
                     if (!(fabsf(tot + bs - 1.0f) <= kMassTol)) s_flag[0] = 1;   // NaN-safe
@@ -1654,7 +1666,7 @@ ctc_lin_kernel(const PipeParams pp, int* __restrict__ flags) {
                     tot += o;
                     if (c == blank) o += bs;
                     const float y = y1[c];
-                    if (act) g1[c] = __float_as_int(y) < 0 ? 0.f : gscale * (y - o);
+                    if (act) g1[c] = (CLAMPED && __float_as_int(y) < 0) ? 0.f : gscale * (y - o);
                 }
                 tot = group_sum(tot, G) + bs;
                 if (act && !(fabsf(tot - 1.0f) <= kMassTol)) s_flag[0] = 1;   // NaN-safe
@@ -1677,8 +1689,8 @@ ctc_lin_kernel(const PipeParams pp, int* __restrict__ flags) {
                     if (blank & 1) o.y += bs; else o.x += bs;
                 }
                 const float2 y = y2[c];
-                if (act) g2[c] = make_float2(__float_as_int(y.x) < 0 ? 0.f : gscale * (y.x - o.x),
-                                             __float_as_int(y.y) < 0 ? 0.f : gscale * (y.y - o.y));
+                if (act) g2[c] = make_float2((CLAMPED && __float_as_int(y.x) < 0) ? 0.f : gscale * (y.x - o.x),
+                                             (CLAMPED && __float_as_int(y.y) < 0) ? 0.f : gscale * (y.y - o.y));
             }
             tot = group_sum(tot, G) + bs;
             if (act && !(fabsf(tot - 1.0f) <= kMassTol)) s_flag[0] = 1;   // NaN-safe
@@ -1719,7 +1731,8 @@ ctc_lin_kernel(const PipeParams pp, int* __restrict__ flags) {
                 if (do_gr && kg >= n1h_i && kg < nchh_i && s_flag[1] == 0) {   // gradient rows of chunk it-3
                     int tt0, rows;
                     chunk_at(kg, tt0, rows);
-                    grad_chunk(s_occ + (size_t)gr_o * TC * ER, s_y + (size_t)gr_a.slot * TC * Vs, tt0, rows);
+                    if (clp.on) grad_chunk(std::true_type{}, s_occ + (size_t)gr_o * TC * ER, s_y + (size_t)gr_a.slot * TC * Vs, tt0, rows);
+                    else grad_chunk(std::false_type{}, s_occ + (size_t)gr_o * TC * ER, s_y + (size_t)gr_a.slot * TC * Vs, tt0, rows);
                 }
                 if (kg >= n1h_i) gr_o ^= 1;
                 gr_a.advance();
@@ -1731,7 +1744,8 @@ ctc_lin_kernel(const PipeParams pp, int* __restrict__ flags) {
                 if (cp_groups) { cp_async_wait<kLinYDist + 1>(); __syncwarp(); }
                 else mbar_wait(bar_acts + sm_a.slot, sm_a.parity);
                 LPROF_SEC(12);
-                softmax_chunk(s_y + (size_t)sm_a.slot * TC * Vs, rows);
+                if (clp.on) softmax_chunk(std::true_type{}, s_y + (size_t)sm_a.slot * TC * Vs, rows);
+                else softmax_chunk(std::false_type{}, s_y + (size_t)sm_a.slot * TC * Vs, rows);
             }
             LPROF_SEC(13);
             sm_a.advance();
@@ -1778,7 +1792,10 @@ ctc_lin_kernel(const PipeParams pp, int* __restrict__ flags) {
             };
             // softmax of my frame of the chunk in ring slot `ys` (+ gradient row of my frame: occupancy buffer
             // `ob`, softmax rows in ring slot `yg`, gradient row at g2)
-            auto help_fast = [&](auto with_grad, unsigned ys, unsigned ob, unsigned yg, float2* g2) {
+            auto help_fast = [&](auto with_grad, auto CL, unsigned ys, unsigned ob, unsigned yg, float2* g2) {
+                constexpr bool CLAMPED = decltype(CL)::value;   // compile-time copy of clp.on (uniform branch at the call)
+                const Clamp clq{CLAMPED, clp.lo, clp.hi};
+                (void)clq;
                 constexpr bool WG = decltype(with_grad)::value;
                 float4 bp = make_float4(0.f, 0.f, 0.f, 0.f);
                 uint2 xo[3];
@@ -1799,12 +1816,12 @@ ctc_lin_kernel(const PipeParams pp, int* __restrict__ flags) {
 #pragma unroll
                 for (int j = 0; j < 3; ++j) x[j] = lds64(ys + 64u * j);
                 unsigned mk = 0u;                  // fused Hardtanh: bit 2j / 2j+1 = gradient blocked
-                if (clp.on) {
+                if (clq.on) {
 #pragma unroll
                     for (int j = 0; j < 3; ++j) {
-                        mk |= (clp.cmask(x[j].x) ? 1u : 0u) << (2 * j) | (clp.cmask(x[j].y) ? 1u : 0u) << (2 * j + 1);
-                        x[j].x = clp.cin(x[j].x);
-                        x[j].y = clp.cin(x[j].y);
+                        mk |= (clq.cmask(x[j].x) ? 1u : 0u) << (2 * j) | (clq.cmask(x[j].y) ? 1u : 0u) << (2 * j + 1);
+                        x[j].x = clq.cin(x[j].x);
+                        x[j].y = clq.cin(x[j].y);
                     }
                 }
                 float m = fmaxf(fmaxf(fmaxf(x[0].x, x[0].y), fmaxf(x[1].x, x[1].y)), fmaxf(x[2].x, x[2].y));
@@ -1847,8 +1864,8 @@ ctc_lin_kernel(const PipeParams pp, int* __restrict__ flags) {
                         const bool mine = cb == glq + 8 * j;
                         const float ox = o[j].x + (mine ? addx : 0.f), oy = o[j].y + (mine ? addy : 0.f);
                         // (a set sign bit of y: the fused Hardtanh blocks this entry's gradient)
-                        g2[glq + 8 * j] = make_float2(__float_as_int(yo[j].x) < 0 ? 0.f : gscale * (yo[j].x - ox),
-                                                      __float_as_int(yo[j].y) < 0 ? 0.f : gscale * (yo[j].y - oy));
+                        g2[glq + 8 * j] = make_float2((CLAMPED && __float_as_int(yo[j].x) < 0) ? 0.f : gscale * (yo[j].x - ox),
+                                                      (CLAMPED && __float_as_int(yo[j].y) < 0) ? 0.f : gscale * (yo[j].y - oy));
                     }
                     if (!(fabsf(tot + bs - 1.0f) <= kMassTol)) sts32(fl0, __int_as_float(1));   // NaN-safe
 #ifdef CTC_B200_MASSDEV
@@ -1874,7 +1891,8 @@ ctc_lin_kernel(const PipeParams pp, int* __restrict__ flags) {
                     issue_fast(it + 2);
                     iss_a.advance();
                     if (it >= 3) gr_a.advance();
-                    help_fast(std::false_type{}, y0 + (unsigned)sm_a.slot * YCH, 0u, 0u, nullptr);
+                    if (clp.on) help_fast(std::false_type{}, std::true_type{}, y0 + (unsigned)sm_a.slot * YCH, 0u, 0u, nullptr);
+                    else help_fast(std::false_type{}, std::false_type{}, y0 + (unsigned)sm_a.slot * YCH, 0u, 0u, nullptr);
                     sm_a.advance();
                     LPROF_END(false);
                     __syncthreads();
@@ -1889,11 +1907,15 @@ ctc_lin_kernel(const PipeParams pp, int* __restrict__ flags) {
                         issue_fast(it + 2);
                         iss_a.advance();
                         const unsigned ys = y0 + (unsigned)sm_a.slot * YCH;
-                        if (lds32i(fl0 + 4u) == 0)
-                            help_fast(std::true_type{}, ys, o0 + (unsigned)gr_o * (4u * ERB), y0 + (unsigned)gr_a.slot * YCH,
-                                      reinterpret_cast<float2*>(gp));
-                        else
-                            help_fast(std::false_type{}, ys, 0u, 0u, nullptr);
+                        const unsigned ob = o0 + (unsigned)gr_o * (4u * ERB), yg = y0 + (unsigned)gr_a.slot * YCH;
+                        const bool gr = lds32i(fl0 + 4u) == 0;
+                        if (clp.on) {
+                            if (gr) help_fast(std::true_type{}, std::true_type{}, ys, ob, yg, reinterpret_cast<float2*>(gp));
+                            else help_fast(std::false_type{}, std::true_type{}, ys, 0u, 0u, nullptr);
+                        } else {
+                            if (gr) help_fast(std::true_type{}, std::false_type{}, ys, ob, yg, reinterpret_cast<float2*>(gp));
+                            else help_fast(std::false_type{}, std::false_type{}, ys, 0u, 0u, nullptr);
+                        }
                         gp += 4 * a_step;
                         gr_o ^= 1;
                         gr_a.advance();
@@ -1925,7 +1947,7 @@ ctc_lin_kernel(const PipeParams pp, int* __restrict__ flags) {
 #else
     if (threadIdx.x == 0) flags[2 * b + (rev ? 1 : 0)] = s_flag[0];
 #endif
-    if (pp.queue == nullptr) break;
+    if (queue_ == nullptr) break;
     if (threadIdx.x == 0) {   // the barriers are initialised afresh for the next utterance
         for (int i = 0; i < NL + NS; ++i)
             asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(smem_u32(bar_acts + i)) : "memory");
