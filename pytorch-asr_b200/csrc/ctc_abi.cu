@@ -166,7 +166,11 @@ bool pick_lin(int T, int V, int S_max, int n_utt, Geometry* g) {
     const bool al = V % 4 == 0;
     // one helper warp (softmax, then gradient rows) when one recursion warp suffices: 4 warps per CTA
     // leave 128 registers per thread, which the two-rows-in-flight combine pass needs
-    const int H = V > 256 ? 4 : (R == 1 ? 1 : 2);
+    // helper warps: one (softmax, then gradient rows) for the narrow vocabularies; two softmax + two gradient warps
+    // for rows of more than 128 classes and for wide rows that are not 16-byte aligned (the reference's own
+    // V = 177, params.py:27: 0.82 ms with one helper, 0.57 ms with four on B = 64, T = 750)
+    int H = (V > 128 || (!al && V > 60)) ? 4 : (R == 1 ? 1 : 2);
+    if (env().helpers == 1 || env().helpers == 2 || env().helpers == 4) H = env().helpers;   // developer knob
     const int NC = R <= 4 ? 2 : 1;   // two combine groups while the CTA stays within 512 threads
     const int NT = 32 * ((1 + NC) * R + H);
     if (NT > 1024) return false;

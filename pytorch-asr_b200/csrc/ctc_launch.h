@@ -31,7 +31,7 @@ struct Geometry {
 
 // Knobs read ONCE from the environment (developer tuning; the defaults are the product).
 struct Env {
-    int chunk, dist, rotate, utt_rot, nofix, pdl, slice_streams, persist, map_mode;
+    int chunk, dist, rotate, utt_rot, nofix, pdl, slice_streams, persist, map_mode, helpers;
     char kernel;   // 'g': generic, 'p': log-domain pipe, 0: default (linear)
     static int geti(const char* name, int dflt) {
         const char* e = std::getenv(name);
@@ -43,6 +43,7 @@ struct Env {
         rotate = geti("CTC_B200_ROTATE", 1);
         utt_rot = geti("CTC_B200_UTT_ROT", -1);
         map_mode = geti("CTC_B200_MAP", 0);
+        helpers = geti("CTC_B200_HELPERS", 0);
         nofix = geti("CTC_B200_NOFIX", 0);
         pdl = geti("CTC_B200_PDL", 1);
         slice_streams = geti("CTC_B200_SLICE_STREAMS", 1);

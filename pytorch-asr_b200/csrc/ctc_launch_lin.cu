@@ -20,6 +20,8 @@ enum LinVariant {
     kLinRn256,          // <8,0,0,256,2>       several recursion warps, run-time strides, <= 256 threads
     kLinRn512,          // <8,0,0,512,1>
     kLinRn1024,         // <8,0,0,1024,1>
+    kLinR1Mid,          // <8,1,0,256,2,MID>   128 < V <= 256, or 60 < V <= 256 with rows that are not 16-byte aligned
+                        // (the reference's V = 177): four helper warps
     kLinFixQueue,       // <8,1,80,128,4,FIX,QUEUE>  the headline shape class as a persistent launch (not reported as a
                         // variant of its own: same code, wrapped in the loop over the utterance queue)
     kLinCount
@@ -29,7 +31,7 @@ const char* const kLinNames[kLinCount] = {
     "ctc_lin_kernel<8,1,80,128,4,FIX>", "ctc_lin_kernel<8,1,80,128,4>", "ctc_lin_kernel<8,1,0,128,4>",
     "ctc_lin_kernel<8,1,0,256,2>",      "ctc_lin_kernel<8,2,80,512,1>", "ctc_lin_kernel<8,4,80,512,1>",
     "ctc_lin_kernel<8,0,0,256,2>",      "ctc_lin_kernel<8,0,0,512,1>",  "ctc_lin_kernel<8,0,0,1024,1>",
-    "ctc_lin_kernel<8,1,80,128,4,FIX,QUEUE>",
+    "ctc_lin_kernel<8,1,0,256,2,MID>", "ctc_lin_kernel<8,1,80,128,4,FIX,QUEUE>",
 };
 
 using LinKernel = void (*)(const PipeParams, int*);
@@ -45,6 +47,7 @@ LinKernel lin_kernel(int id) {
         case kLinRn256: return ctc_lin_kernel<8, 0, 0, 256, 2>;
         case kLinRn512: return ctc_lin_kernel<8, 0, 0, 512, 1>;
         case kLinRn1024: return ctc_lin_kernel<8, 0, 0, 1024, 1>;
+        case kLinR1Mid: return ctc_lin_kernel<8, 1, 0, 256, 2, false, false, true>;
         case kLinFixQueue: return ctc_lin_kernel<8, 1, 80, 128, 4, true, true>;
     }
     return nullptr;
@@ -61,7 +64,7 @@ int lin_variant(const Geometry& g, int V) {
             return (g.lH == 1 && g.lD == 2 && V == 48 && !env().nofix) ? kLinFix : kLinR1Y80;
         if (g.lYS != 0) return -1;
         if (g.lNT <= 128) return kLinR1;
-        return g.lNT <= 256 ? kLinR1Wide : -1;
+        return g.lNT <= 256 ? (V > 256 ? kLinR1Wide : kLinR1Mid) : -1;
     }
     if (g.lYS == 80 && g.lNT <= 512) {
         if (g.lR == 2) return kLinR2Y80;

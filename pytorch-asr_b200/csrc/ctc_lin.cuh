@@ -153,6 +153,10 @@ __device__ __forceinline__ unsigned* occ_slot(unsigned* row, int byte_off) {
 __device__ __forceinline__ void cp_async16_a(unsigned dst, const void* src) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
 }
+// 16-byte cp.async of which only the first `bytes` (<= 16) are read from global memory; the rest is zero-filled
+__device__ __forceinline__ void cp_async16_zfill(void* smem_dst, const void* gmem_src, int bytes) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src), "r"(bytes) : "memory");
+}
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 __device__ __forceinline__ void mbar_expect_tx_a(unsigned bar, unsigned bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
@@ -224,7 +228,9 @@ struct LinSmem {
     int Vs, VO, OW, ER, NL, NS;
     __host__ __device__ static int up(int x, int a) { return (x + a - 1) / a * a; }
     __host__ __device__ LinSmem(int NP, int R, int V, int TC, int RS, int ys) {
-        Vs = ys > 0 ? ys : up(V + 1, 4);
+        // (+3: a row that is not 16-byte aligned in HBM is copied in whole 16-byte segments and lands up to 3
+        // floats into its ring row; the softmax moves it to the front)
+        Vs = ys > 0 ? ys : up(V + 1 + ((V & 3) ? 3 : 0), 4);
         VO = ys > 0 ? 80 : lin_occ_classes(V);
         OW = VO + 32;            // + 32 blank partial sums
         ER = R * OW;
@@ -274,7 +280,11 @@ __device__ __forceinline__ int lin_map_utt(int c, int n, int pairs, int mode) {
 // of these as compile-time constants.
 // QUEUE: persistent launch (pp.queue; instantiated for the headline shape class only -- the loop around the
 // whole utterance costs the other instantiations 6 ... 18 % when it is merely present).
-template <int P, int RC, int YS, int MAXT, int MINB, bool FIX = false, bool QUEUE = false>
+// MID: vocabularies of 61 ... 256 classes served by four helper warps (rows that are not 16-byte aligned --
+// the reference's own V = 177 -- included): every softmax warp copies and waits for ITS OWN frames with cp.async
+// groups, rows that start off a 16-byte line are copied in whole 16-byte segments, and the softmax / gradient
+// passes hold a frame's (at most 16 per lane) classes in registers.
+template <int P, int RC, int YS, int MAXT, int MINB, bool FIX = false, bool QUEUE = false, bool MID = false>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(MAXT, MINB)
 ctc_lin_kernel(const PipeParams pp, int* __restrict__ flags) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -285,13 +295,15 @@ ctc_lin_kernel(const PipeParams pp, int* __restrict__ flags) {
     // (S2R SR_TID / SR_CgaCtaId cost ~50 cycles each): pinned in registers in the FIX instantiation
     int lane_pin = threadIdx.x & 31;
     unsigned sbase = smem_u32(smem_raw);
-    if constexpr (FIX) asm volatile("" : "+r"(lane_pin), "+r"(sbase));
+    asm volatile("" : "+r"(lane_pin), "+r"(sbase));
     const int lane = lane_pin;
     const int shift = pp.rotate > 0 ? (int)((blockIdx.x / pp.rotate) * R) % NW : 0;
     const int w = ((int)(threadIdx.x >> 5) + NW - shift) % NW;   // role (virtual) warp id
     // which utterance this cluster works on: the batch is sorted by length (dataloader.py:53); utt_rot
     // moves the longest utterances to the clusters whose SMs end up with the fewest co-resident CTAs
-    const bool rev = (blockIdx.x & 1) != 0;
+    int rev_pin = (int)(blockIdx.x & 1);
+    asm volatile("" : "+r"(rev_pin));
+    const bool rev = rev_pin != 0;
     const int T = p.T, V = FIX ? 48 : p.V, blank = p.blank;
     // rows of acts / grad start on 16-byte boundaries (always, in the V <= 60 emission-ring variants);
     // otherwise (the reference's own V = 177, params.py:27) the helpers use 4-byte copies and scalar stores
@@ -363,7 +375,7 @@ ctc_lin_kernel(const PipeParams pp, int* __restrict__ flags) {
     }
     const int32_t* tg = p.targets + p.tgt_off[b];
     int want_grad_pin = p.grad != nullptr ? 1 : 0;
-    if constexpr (FIX) asm volatile("" : "+r"(want_grad_pin));
+    asm volatile("" : "+r"(want_grad_pin));
     const bool want_grad = want_grad_pin != 0;
     const float gscale = p.grad_scale ? p.grad_scale[b] : 1.0f;
     const size_t frame_stride = (size_t)p.frame_stride;
@@ -1258,6 +1270,12 @@ ctc_lin_kernel(const PipeParams pp, int* __restrict__ flags) {
         const int GA = 32 >> lgA, glA = lane & (GA - 1), fA = ha * FA + (lane >> (5 - lgA));
         const int GB = 32 >> lgB, glB = lane & (GB - 1), fB = hb * FB + (lane >> (5 - lgB));
         const unsigned gmaskA = (GA == 32 ? 0xffffffffu : ((1u << GA) - 1u)) << (lane & ~(GA - 1));
+        // rows that are not 16-byte aligned in HBM: 16-byte copies + register-resident passes when a lane holds at
+        // most 16 classes of its frame (V <= 256 with four helpers, V <= 128 with one)
+        const bool shifted = MID && !al && !wide_rows && (V + GA - 1) / GA <= 16;
+        auto row_mis = [&](int tt) {     // floats between the 16-byte line and the logits row of sweep step tt
+            return (int)((reinterpret_cast<uintptr_t>(acts_b + (ptrdiff_t)(tbase + tsign * tt) * (ptrdiff_t)frame_stride) >> 2) & 3);
+        };
         auto group_sum = [&](float x, int G) {
             for (int o = G >> 1; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
             return x;
@@ -1270,18 +1288,23 @@ ctc_lin_kernel(const PipeParams pp, int* __restrict__ flags) {
         // ---- logits rows of a chunk: cp.async, 16 B per lane and copy; a lane's (row, column) of
         //      its first two copies never change, so they are computed once
         const ptrdiff_t a_inc = (ptrdiff_t)tsign * (ptrdiff_t)frame_stride;
-        const int n4 = TC * V4;
-        const bool cp_groups = nA == 1 && !wide_rows;   // one softmax warp waits for its own cp.async groups
+        // MID: softmax warp ha copies its own FA frames of a chunk (rows [r_lo, r_lo + r_cnt)) and waits for them
+        // with cp.async groups; otherwise one warp copies the chunk (the mbarrier arrive that several consumers
+        // need costs the issuing warp about a microsecond on B200)
+        const bool own_rows = MID && nA > 1 && !wide_rows;
+        const int r_lo = own_rows ? ha * FA : 0, r_cnt = own_rows ? FA : TC;
+        const int n4 = r_cnt * V4;
+        const bool cp_groups = (nA == 1 || own_rows) && !wide_rows;   // a softmax warp waits for its own cp.async groups
         int cp_dst[2], cp_row[2];
         bool pf_lane[2];
         ptrdiff_t cp_src[2];
 #pragma unroll
         for (int j = 0; j < 2; ++j) {
             const int idx = lane + 32 * j, r = idx / max(V4, 1), c = idx - r * V4;
-            cp_row[j] = idx < n4 ? r : 0x7fffffff;
+            cp_row[j] = idx < n4 ? r_lo + r : 0x7fffffff;
             pf_lane[j] = c == 0 || c == 8;   // two of a V = 48 row's lanes touch both of its 128-byte lines
-            cp_dst[j] = r * Vs + 4 * c;
-            cp_src[j] = r * a_inc + 4 * c;
+            cp_dst[j] = (r_lo + r) * Vs + 4 * c;
+            cp_src[j] = (r_lo + r) * a_inc + 4 * c;
         }
         auto issue_logits = [&](int ka, int slot_a) {
             int tt0, rows;
@@ -1292,8 +1315,19 @@ ctc_lin_kernel(const PipeParams pp, int* __restrict__ flags) {
                 if (lane == 0) issue_logits_tma(ka, slot_a);
                 return;
             }
-            if (!al) {
-                for (int r = 0; r < rows; ++r)
+            if (MID && !al && shifted) {
+                // rows that start 4, 8 or 12 bytes into a 16-byte line (V % 4 != 0): whole 16-byte segments of the
+                // lines the row touches; class c lands at ring position mis + c (the bytes in front of the row
+                // belong to the previous row of the tensor, the tail of the last segment is zero-filled)
+                for (int r = r_lo; r < min(rows, r_lo + r_cnt); ++r) {
+                    const float* srow = src + r * a_inc;
+                    const int mis = (int)((reinterpret_cast<uintptr_t>(srow) >> 2) & 3);
+                    const int segs = (mis + V + 3) >> 2;
+                    for (int c = lane; c < segs; c += 32)
+                        cp_async16_zfill(dst + r * Vs + 4 * c, srow - mis + 4 * c, min(16, (mis + V - 4 * c) * 4));
+                }
+            } else if (!al) {
+                for (int r = r_lo; r < min(rows, r_lo + r_cnt); ++r)
                     for (int c = lane; c < V; c += 32) cp_async4(dst + r * Vs + c, src + r * a_inc + c);
             } else {
 #pragma unroll
@@ -1301,9 +1335,10 @@ ctc_lin_kernel(const PipeParams pp, int* __restrict__ flags) {
                 if (cp_row[j] < rows) cp_async16(dst + cp_dst[j], src + cp_src[j]);
             }
             if (al && n4 > 64) {
-                int r = 64 / V4, c = 64 - r * V4 + lane;
+                const int r_end = min(rows, r_lo + r_cnt);
+                int r = r_lo + 64 / V4, c = 64 - (64 / V4) * V4 + lane;
                 while (c >= V4) { c -= V4; ++r; }
-                while (r < rows) {
+                while (r < r_end) {
                     cp_async16(dst + r * Vs + 4 * c, src + r * a_inc + 4 * c);
                     c += 32;
                     while (c >= V4) { c -= V4; ++r; }
@@ -1367,7 +1402,7 @@ ctc_lin_kernel(const PipeParams pp, int* __restrict__ flags) {
         // ---- fused softmax, in place, of my F frames of a chunk (a group of G lanes per frame) ----
         // The maximum of a row comes from ONE redux.sync per group (no shuffle tree); the sum needs
         // log2 G shuffle levels.
-        auto softmax_chunk = [&](auto CL, float* base, int rows) {
+        auto softmax_chunk = [&](auto CL, float* base, int rows, int tt0) {
                 constexpr bool CLAMPED = decltype(CL)::value;   // compile-time copy of clp.on (uniform branch at the call)
                 const Clamp clq{CLAMPED, clp.lo, clp.hi};
                 (void)clq;
@@ -1376,6 +1411,47 @@ ctc_lin_kernel(const PipeParams pp, int* __restrict__ flags) {
             const bool act = f < rows;
             float* row = base + min(f, rows - 1) * Vs;
             float2* row2 = reinterpret_cast<float2*>(row);
+            if (MID && (V + G - 1) / G <= 16) {
+                // at most 16 classes per lane: one pass in registers (a row that is not 16-byte aligned in HBM
+                // sits `mis` floats into its ring row and is moved to the front here)
+                const float* rin = row + (shifted ? row_mis(tt0 + min(f, rows - 1)) : 0);
+                float x[16];
+                float m = -CUDART_INF_F;
+                unsigned mk = 0u;
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    const int c = gl + j * G;
+                    x[j] = -CUDART_INF_F;
+                    if (c < V) {
+                        const float raw = rin[c];
+                        mk |= (clq.cmask(raw) ? 1u : 0u) << j;
+                        x[j] = clq.cin(raw);
+                    }
+                    m = fmaxf(m, x[j]);
+                }
+                m = group_max(m, G);
+                const float mb = m * kLog2e;
+                float z = 0.f;
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    x[j] = ex2f(fmaf(x[j], kLog2e, -mb));      // (-inf for the classes beyond V: 0)
+                    z += x[j];
+                }
+                const float rs = 1.0f / group_sum(z, G);
+                __syncwarp();      // every lane has read its raw values before the row is overwritten in place
+                if (act) {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        const int c = gl + j * G;
+                        if (c < V) {
+                            const float y = x[j] * rs;
+                            row[c] = (mk >> j) & 1u ? -y : y;
+                        }
+                    }
+                    for (int c = V + gl; c < Vs; c += G) row[c] = 0.f;   // slot V: what padding pairs gather
+                }
+                return;
+            }
             if (!al) {      // rows that are not 16-byte aligned in HBM (V % 4 != 0): scalar passes
                 float m = -CUDART_INF_F, z = 0.f;
                 for (int c = gl; c < V; c += G) m = fmaxf(m, clq.cin(row[c]));
@@ -1653,6 +1729,43 @@ ctc_lin_kernel(const PipeParams pp, int* __restrict__ flags) {
             }
             bs = group_sum(bs, G);
             float tot = 0.f;
+            if (MID && R == 1 && (V + G - 1) / G <= 16) {
+                // at most 16 classes per lane: every load issued up front
+                float* g1 = reinterpret_cast<float*>(g2);
+                const float* y1 = reinterpret_cast<const float*>(y2);
+                unsigned* o1 = reinterpret_cast<unsigned*>(orow);
+                float o[16], y[16];
+                float tsum = 0.f;
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    const int c = gl + j * G;
+                    o[j] = 0.f;
+                    y[j] = 0.f;
+                    if (c < V) {
+                        const unsigned xq = o1[c];
+                        y[j] = y1[c];
+                        if (act) o1[c] = 0u;
+                        o[j] = __uint2float_rn(xq) * (1.0f / kQ31);
+                        tsum += o[j];
+                    }
+                }
+                tsum = group_sum(tsum, G);      // (bs is already the frame's blank sum)
+                if (act) {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        const int c = gl + j * G;
+                        if (c < V) {
+                            const float ov = o[j] + (c == blank ? bs : 0.f);
+                            g1[c] = (CLAMPED && __float_as_int(y[j]) < 0) ? 0.f : gscale * (y[j] - ov);
+                        }
+                    }
+                    if (!(fabsf(tsum + bs - 1.0f) <= kMassTol)) s_flag[0] = 1;   // NaN-safe
+#ifdef CTC_B200_MASSDEV
+                    atomicMax(&s_flag[2], __float_as_int(fabsf(tsum + bs - 1.0f)));
+#endif
+                }
+                return;
+            }
             if (!al) {      // gradient rows that are not 16-byte aligned in HBM: scalar loads / stores
                 float* g1 = reinterpret_cast<float*>(g2);
                 const float* y1 = reinterpret_cast<const float*>(y2);
@@ -1702,7 +1815,7 @@ ctc_lin_kernel(const PipeParams pp, int* __restrict__ flags) {
         // ---- the helper schedule -----------------------------------------------------------
         // Iteration `it`:  SOFT 0 requests the logits of chunk it + kLinYDist + 1; SOFT: softmax of
         // chunk it; GRAD: gradient rows of chunk it-3 (REC runs chunk it-1, COMB chunk it-2).
-        const bool iss_acts = isA && ha == 0;
+        const bool iss_acts = isA && (ha == 0 || own_rows);
         const bool do_sm = isA && ha * FA < TC, do_gr = isB && hb * FB < TC && want_grad;
         Ring iss_a(NL), sm_a(NL), gr_a(NL);
         int gr_o = 0;
@@ -1744,8 +1857,8 @@ ctc_lin_kernel(const PipeParams pp, int* __restrict__ flags) {
                 if (cp_groups) { cp_async_wait<kLinYDist + 1>(); __syncwarp(); }
                 else mbar_wait(bar_acts + sm_a.slot, sm_a.parity);
                 LPROF_SEC(12);
-                if (clp.on) softmax_chunk(std::true_type{}, s_y + (size_t)sm_a.slot * TC * Vs, rows);
-                else softmax_chunk(std::false_type{}, s_y + (size_t)sm_a.slot * TC * Vs, rows);
+                if (clp.on) softmax_chunk(std::true_type{}, s_y + (size_t)sm_a.slot * TC * Vs, rows, tt0);
+                else softmax_chunk(std::false_type{}, s_y + (size_t)sm_a.slot * TC * Vs, rows, tt0);
             }
             LPROF_SEC(13);
             sm_a.advance();

@@ -17,6 +17,9 @@ CONFIGS = {
     "C3": (2, 64, 4000, 48, 800, True),     # long-utterance stress
     "C4": (3, 128, 1000, 1024, 200, False), # large vocabulary
     "C5": (4, 4096, 1000, 48, 200, False),  # batch-sharded across GPUs
+    # not a BASELINE.json config: the reference's own label inventory (NUM_CTC_LABELS = 177, asr/utils/params.py:27)
+    # at a deepspeech_ctc-sized batch -- rows that are not 16-byte aligned (V % 4 != 0)
+    "R177": (5, 64, 750, 177, 100, False),
 }
 
 

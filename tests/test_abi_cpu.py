@@ -52,7 +52,7 @@ def test_geometry_and_workspace():
     assert cabi.geometry(100, 1, 48, 1500)["threads"] <= 1024
     assert cabi.geometry(100, 1, 48, 4095)["pairs_per_thread"] in (4, 8)
     g177 = cabi.geometry(750, 64, 177, 100)         # the reference's own vocabulary (params.py:27), V % 4 != 0
-    assert g177["kernel"] == 2 and g177["fallback_kernel"] == 0 and g177["variant_name"] == "ctc_lin_kernel<8,1,0,128,4>"
+    assert g177["kernel"] == 2 and g177["fallback_kernel"] == 0 and g177["variant_name"] == "ctc_lin_kernel<8,1,0,256,2,MID>"
     assert g["variant_name"] == "ctc_lin_kernel<8,1,80,128,4,FIX>" and g["fallback_kernel"] == 1
     assert g3["variant_name"] == "ctc_lin_kernel<8,4,80,512,1>"
     with pytest.raises(cabi.CtcB200Error) as e:

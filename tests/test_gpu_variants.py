@@ -48,7 +48,9 @@ LIN_CASES = [
     (5, 150, 32, 30, False, "ctc_lin_kernel<8,1,80,128,4>"),           # V <= 60, not 48
     (5, 150, 60, 30, False, "ctc_lin_kernel<8,1,80,128,4>"),
     (4, 160, 128, 30, False, "ctc_lin_kernel<8,1,0,128,4>"),           # 60 < V <= 256
-    (4, 750, 177, 100, False, "ctc_lin_kernel<8,1,0,128,4>"),          # the reference's real shape (params.py:27)
+    (4, 750, 177, 100, False, "ctc_lin_kernel<8,1,0,256,2,MID>"),          # the reference's real shape (params.py:27): four helpers
+    (4, 300, 100, 60, False, "ctc_lin_kernel<8,1,0,128,4>"),           # 60 < V <= 128, aligned rows: one helper
+    (3, 300, 200, 60, False, "ctc_lin_kernel<8,1,0,256,2,MID>"),           # 128 < V <= 256: four helpers
     (4, 120, 29, 20, False, "ctc_lin_kernel<8,1,0,128,4>"),            # characters + blank: V % 4 != 0, V < 60
     (8, 1000, 1024, 200, False, "ctc_lin_kernel<8,1,0,256,2>"),        # C4 slice at full size
     (80, 120, 1024, 20, False, "ctc_lin_kernel<8,1,0,256,2>"),         # C4's geometry: >= 75 utterances -> chunks of 2 frames

@@ -1,19 +1,23 @@
 #!/bin/bash
-# developer tool: the bench lines, launch list and ncu capture committed under profiles/ (tag = $1)
-tag=$1
+# developer tool: the bench lines, launch list, ncu captures, comparators and sweeps committed under profiles/ (tag = $1)
+cd "$GRAFT_REPO_ROOT" || exit 1
+mkdir -p gpurun_out
+tag=${1:-r02}
+timeout 1500 python -m pytest tests -m gpu -q -rs --tb=short 2>&1 | grep -v "^E    +" | tail -40 > gpurun_out/${tag}_pytest_gpu.log
 python bench.py > gpurun_out/${tag}_bench_c2.json 2> gpurun_out/${tag}_bench_c2.err
 python bench.py --impl reference > gpurun_out/${tag}_ref.json 2>/dev/null
-for w in C1 C3 C4; do python bench.py --workload $w --steps 50 --no-cpu-baseline > gpurun_out/${tag}_bench_$w.json 2>/dev/null; done
-python bench.py --peaky --steps 50 --no-cpu-baseline > gpurun_out/${tag}_bench_c2_peaky.json 2>/dev/null
-python bench.py --workload C5 --steps 20 --warmup 3 --no-cpu-baseline > gpurun_out/${tag}_bench_c5_n1.json 2>/dev/null
-python bench.py --steps 3 --warmup 3 --no-cpu-baseline > /dev/null 2>&1 && \
+for w in C1 C3 C4 R177; do python bench.py --workload $w --steps 50 --no-cpu-baseline --no-c5 --no-module > gpurun_out/${tag}_bench_$w.json 2>/dev/null; done
+python bench.py --peaky --steps 50 --no-cpu-baseline --no-c5 --no-module > gpurun_out/${tag}_bench_c2_peaky.json 2>/dev/null
+python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-c5 --no-module > /dev/null 2>&1 && \
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/${tag}_launches.csv \
-    python bench.py --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/ncu1.log 2>&1
+    python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-c5 --no-module > gpurun_out/ncu1.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:ctc_lin -s 3 -c 1 -f -o gpurun_out/prof_${tag}_c2 \
-    python bench.py --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/ncu2.log 2>&1
+    python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-c5 --no-module > gpurun_out/ncu2.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:ctc_lin -s 3 -c 1 -f -o gpurun_out/prof_${tag}_c4 \
-    python bench.py --workload C4 --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/ncu3.log 2>&1
+    python bench.py --workload C4 --steps 3 --warmup 3 --no-cpu-baseline --no-c5 --no-module > gpurun_out/ncu3.log 2>&1
 python tools/gpu_comparators.py --out gpurun_out/${tag}_comparators.json > gpurun_out/cmp.log 2>&1
+python tools/gpu_sigma_sweep.py gpurun_out/${tag}_sigma_sweep.json > gpurun_out/sigma.log 2>&1
+tail -3 gpurun_out/${tag}_pytest_gpu.log; tail -3 gpurun_out/cmp.log; tail -12 gpurun_out/sigma.log
 for f in gpurun_out/${tag}_bench_*.json; do python - "$f" <<'PY'
 import json,sys
 d=json.loads(open(sys.argv[1]).read().strip().splitlines()[-1]); r=d["roofline"]
