@@ -53,6 +53,33 @@ def torch_path(acts_d, tg, il, tl, cudnn):
     return fn
 
 
+def cudnn_variant(B, T, V, S, idx):
+    """cuDNN's CTC (cudnnCTCLoss_v8 behind torch) only takes batches with every input length = T and target
+    lengths <= 255: time it on the FIXED-LENGTH variant of the config (S capped at 255), next to this engine and
+    torch's native kernels on the same inputs.  torch picks cuDNN for CUDA int32 targets / lengths
+    (`torch._use_cudnn_ctc_loss`); whether it did is recorded, and so is any error."""
+    Sc = min(S, 255)
+    acts, tg, il, tl = synth.make_batch(B, T, V, Sc, seed=1234 + idx, fixed_lengths=True)
+    acts_d = acts.cuda()
+    out = {"variant": f"fixed lengths: every T_b = {T}, S_b = {Sc}"}
+    try:
+        prob = cabi.DeviceProblem(acts, tg, il, tl, blank=0, reduction="mean")
+        out["b200_engine"] = timed(lambda: prob.run(want_grad=True, reduce=True))
+        out["torch_native_gpu"] = timed(torch_path(acts_d, tg, il, tl, cudnn=False))
+        tg_d, il_d, tl_d = tg.cuda(), il.cuda(), tl.cuda()
+        lp = F.log_softmax(acts_d, -1)
+        with torch.backends.cudnn.flags(enabled=True, deterministic=True):
+            out["use_cudnn"] = bool(torch._use_cudnn_ctc_loss(lp, tg_d, il_d, tl_d, 0))
+        fnc = torch_path(acts_d, tg_d, il_d, tl_d, cudnn=True)
+        loss_c = float(fnc())
+        out.update(timed(fnc))
+        out["loss_cudnn_path"] = loss_c
+        out["loss_engine"] = float(prob.loss.cpu())
+    except Exception as e:  # noqa: BLE001
+        out["error"] = str(e)[:300]
+    return out
+
+
 def main():
     names = [a for a in sys.argv[1:] if a in synth.CONFIGS] or ["C1", "C2", "C3", "C4"]
     out = None
@@ -74,15 +101,7 @@ def main():
         row["torch_native_gpu"] = timed(fn)
         loss_t = float(fn())
         row["loss_engine"], row["loss_torch_native"] = loss_e, loss_t
-        try:
-            fnc = torch_path(acts_d, tg, il, tl, cudnn=True)
-            r = timed(fnc)
-            # torch silently uses the native kernels when cuDNN rejects the batch
-            # (needs all T_b == T, S_b <= 256, int32 CPU lengths): say which ran
-            r["eligible"] = bool(fixed and int(tl.max()) <= 256)
-            row["torch_cudnn_enabled"] = r
-        except Exception as e:  # noqa: BLE001
-            row["torch_cudnn_enabled"] = {"error": str(e)[:200]}
+        row["torch_cudnn_enabled"] = cudnn_variant(B, T, V, S, idx)
         for k in ("b200_engine", "torch_native_gpu", "torch_cudnn_enabled"):
             if "median_ms" in row[k]:
                 row[k]["frames_per_s"] = B * T / (row[k]["median_ms"] * 1e-3)
