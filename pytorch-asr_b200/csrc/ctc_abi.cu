@@ -185,6 +185,9 @@ bool pick_lin(int T, int V, int S_max, int n_utt, Geometry* g) {
             int TC = cand[ci];
             if (tc_env >= 1 && tc_env <= 4) TC = tc_env;   // the kernel unrolls 4 rows
             if (YS == 80 && TC != 4) continue;   // the fixed-stride variants are built for chunks of 4 frames
+            // wide aligned rows: a whole warp per frame (chunks of 2 frames with two softmax warps) keeps a row in
+            // registers; chunks of 4 would halve the lanes per frame and fall back to the looped passes
+            if (V > 256 && al && H == 4 && TC == 4 && tc_env == 0) continue;
             const int total = lin_smem_size(NP, R, V, TC, RS, YS);
             const int need = std::max(1, std::min(4, (2 * std::max(n_utt, 1) + kNumSmsHint - 1) / kNumSmsHint));
             const int limit = pass == 0 ? std::min(kMaxSmemBytes, 227 * 1024 / need - 1024) : kMaxSmemBytes;

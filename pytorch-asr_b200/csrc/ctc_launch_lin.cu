@@ -22,6 +22,7 @@ enum LinVariant {
     kLinRn1024,         // <8,0,0,1024,1>
     kLinR1Mid,          // <8,1,0,256,2,MID>   128 < V <= 256, or 60 < V <= 256 with rows that are not 16-byte aligned
                         // (the reference's V = 177): four helper warps
+    kLinR1WideAl,       // <8,1,0,256,2,WIDE>  V > 256 in 16-byte aligned rows (C4); kLinR1Wide keeps the rows that are not
     kLinFixQueue,       // <8,1,80,128,4,FIX,QUEUE>  the headline shape class as a persistent launch (not reported as a
                         // variant of its own: same code, wrapped in the loop over the utterance queue)
     kLinCount
@@ -31,7 +32,7 @@ const char* const kLinNames[kLinCount] = {
     "ctc_lin_kernel<8,1,80,128,4,FIX>", "ctc_lin_kernel<8,1,80,128,4>", "ctc_lin_kernel<8,1,0,128,4>",
     "ctc_lin_kernel<8,1,0,256,2>",      "ctc_lin_kernel<8,2,80,512,1>", "ctc_lin_kernel<8,4,80,512,1>",
     "ctc_lin_kernel<8,0,0,256,2>",      "ctc_lin_kernel<8,0,0,512,1>",  "ctc_lin_kernel<8,0,0,1024,1>",
-    "ctc_lin_kernel<8,1,0,256,2,MID>", "ctc_lin_kernel<8,1,80,128,4,FIX,QUEUE>",
+    "ctc_lin_kernel<8,1,0,256,2,MID>", "ctc_lin_kernel<8,1,0,256,2,WIDE>", "ctc_lin_kernel<8,1,80,128,4,FIX,QUEUE>",
 };
 
 using LinKernel = void (*)(const PipeParams, int*);
@@ -48,6 +49,7 @@ LinKernel lin_kernel(int id) {
         case kLinRn512: return ctc_lin_kernel<8, 0, 0, 512, 1>;
         case kLinRn1024: return ctc_lin_kernel<8, 0, 0, 1024, 1>;
         case kLinR1Mid: return ctc_lin_kernel<8, 1, 0, 256, 2, false, false, true>;
+        case kLinR1WideAl: return ctc_lin_kernel<8, 1, 0, 256, 2, false, false, false, true>;
         case kLinFixQueue: return ctc_lin_kernel<8, 1, 80, 128, 4, true, true>;
     }
     return nullptr;
@@ -64,7 +66,11 @@ int lin_variant(const Geometry& g, int V) {
             return (g.lH == 1 && g.lD == 2 && V == 48 && !env().nofix) ? kLinFix : kLinR1Y80;
         if (g.lYS != 0) return -1;
         if (g.lNT <= 128) return kLinR1;
-        return g.lNT <= 256 ? (V > 256 ? kLinR1Wide : kLinR1Mid) : -1;
+        if (g.lNT > 256) return -1;
+        // (the WIDE / MID instantiations have their CTA shape -- four helpers, 224 threads, WIDE: chunks of 2 frames --
+        // as compile-time constants; any other choice of the geometry heuristics runs the general instantiation)
+        if (V > 256) return (V % 4 == 0 && g.lH == 4 && g.lD == 2 && g.lchunk == 2) ? kLinR1WideAl : kLinR1Wide;
+        return (g.lH == 4 && g.lD == 2) ? kLinR1Mid : kLinR1Wide;
     }
     if (g.lYS == 80 && g.lNT <= 512) {
         if (g.lR == 2) return kLinR2Y80;

@@ -284,13 +284,19 @@ __device__ __forceinline__ int lin_map_utt(int c, int n, int pairs, int mode) {
 // the reference's own V = 177 -- included): every softmax warp copies and waits for ITS OWN frames with cp.async
 // groups, rows that start off a 16-byte line are copied in whole 16-byte segments, and the softmax / gradient
 // passes hold a frame's (at most 16 per lane) classes in registers.
-template <int P, int RC, int YS, int MAXT, int MINB, bool FIX = false, bool QUEUE = false, bool MID = false>
+// WIDE: more than 256 classes in 16-byte aligned rows (C4): four helper warps, a warp per frame, TMA row copies;
+// everything the narrower vocabularies need is compiled out (ncu on C4: 2.3 instruction-fetch stalls per issued
+// instruction in the 175 KB kernel that carries every path).
+template <int P, int RC, int YS, int MAXT, int MINB, bool FIX = false, bool QUEUE = false, bool MID = false,
+          bool WIDE = false>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(MAXT, MINB)
 ctc_lin_kernel(const PipeParams pp, int* __restrict__ flags) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const FusedParams& p = pp.f;
-    const int NT = FIX ? 128 : blockDim.x, NW = NT >> 5;
-    const int R = RC > 0 ? RC : pp.R, H = FIX ? 1 : pp.H, NP = RC > 0 ? 32 * P * RC : pp.NP;
+    // threads per CTA: a compile-time constant wherever the instantiation fixes the warp roles (what only other
+    // CTA shapes need -- e.g. the two-rows-in-flight combine pass of the 4-warp CTAs -- is then compiled out)
+    const int NT = (FIX || (RC == 1 && MAXT == 128)) ? 128 : ((WIDE || MID) ? 224 : blockDim.x), NW = NT >> 5;
+    const int R = RC > 0 ? RC : pp.R, H = FIX ? 1 : (WIDE ? 4 : pp.H), NP = RC > 0 ? 32 * P * RC : pp.NP;
     // loop invariants the compiler would otherwise re-derive inside the role loops at the register cap
     // (S2R SR_TID / SR_CgaCtaId cost ~50 cycles each): pinned in registers in the FIX instantiation
     int lane_pin = threadIdx.x & 31;
@@ -307,10 +313,11 @@ ctc_lin_kernel(const PipeParams pp, int* __restrict__ flags) {
     const int T = p.T, V = FIX ? 48 : p.V, blank = p.blank;
     // rows of acts / grad start on 16-byte boundaries (always, in the V <= 60 emission-ring variants);
     // otherwise (the reference's own V = 177, params.py:27) the helpers use 4-byte copies and scalar stores
-    const bool al = YS == 80 ? true : ((V & 3) == 0 && ((p.frame_stride | p.utt_stride) & 3) == 0);
+    const bool al = (YS == 80 || WIDE) ? true : ((V & 3) == 0 && ((p.frame_stride | p.utt_stride) & 3) == 0);
     const Clamp clp{p.use_clamp != 0, p.clamp_lo, p.clamp_hi};
     // the V <= 60 emission-ring variants (YS = 80) are only launched with chunks of 4 frames
-    const int RS = RC > 0 ? lin_row_stride(32 * P * RC, P) : p.row_stride, TC = (YS == 80 && CTC_LIN_TC4) ? 4 : p.chunk;
+    const int RS = RC > 0 ? lin_row_stride(32 * P * RC, P) : p.row_stride,
+              TC = (YS == 80 && CTC_LIN_TC4) ? 4 : (WIDE ? 2 : p.chunk);   // WIDE: chunks of 2 frames, a warp per frame
     const int NC = FIX ? 2 : pp.D;           // combine groups: group g takes the rows r == g (mod NC) of a chunk
     const bool is_rec = w < R, is_comb = w >= R && w < (1 + NC) * R;
     const int hw = w - (1 + NC) * R;   // helper index (>= 0 for SOFT / GRAD warps)
@@ -388,7 +395,7 @@ ctc_lin_kernel(const PipeParams pp, int* __restrict__ flags) {
     const bool isA = hw >= 0 && (H == 1 || hw < nA), isB = hw >= 0 && (H == 1 || hw >= nA);
     const int ha = hw, hb = H == 1 ? 0 : hw - nA;
     // wide vocabulary: logits rows come in by TMA bulk copies (one per row) instead of cp.async
-    const bool wide_rows = CTC_LIN_TMA_Y ? true : (YS == 0 && nA > 1 && V > 256 && al);
+    const bool wide_rows = (CTC_LIN_TMA_Y || WIDE) ? true : (YS == 0 && nA > 1 && V > 256 && al);
 
     // ---- GRAD warps: mandatory zero fill of gradient rows t >= T_b (no compute) --------
     if (want_grad && isB) {
@@ -396,10 +403,10 @@ ctc_lin_kernel(const PipeParams pp, int* __restrict__ flags) {
         const int mine = (nrows + (rev ? 0 : 1)) >> 1;  // rows Tb+rev, Tb+rev+2, ...
         float* g = grad_b + (size_t)(Tb + (rev ? 1 : 0) + 2 * hb) * frame_stride;
         const size_t ginc = 2 * (size_t)nB * frame_stride;
-        if (!al) {
+        if (!WIDE && !al) {
             for (int r = hb; r < mine; r += nB, g += ginc)
                 for (int c = lane; c < V; c += 32) g[c] = 0.f;
-        } else if (YS == 80 || V4 < 32) {
+        } else if (!WIDE && (YS == 80 || V4 < 32)) {
             // narrow rows: the 32 lanes of a store cover 32 / V4 rows (V = 48: 12 lanes per row otherwise)
             int r = hb, c = lane;
             while (c >= V4) { c -= V4; r += nB; g += ginc; }
@@ -1452,7 +1459,7 @@ ctc_lin_kernel(const PipeParams pp, int* __restrict__ flags) {
                 }
                 return;
             }
-            if (!al) {      // rows that are not 16-byte aligned in HBM (V % 4 != 0): scalar passes
+            if (!WIDE && !al) {      // rows that are not 16-byte aligned in HBM (V % 4 != 0): scalar passes
                 float m = -CUDART_INF_F, z = 0.f;
                 for (int c = gl; c < V; c += G) m = fmaxf(m, clq.cin(row[c]));
                 m = group_max(m, G);
@@ -1467,14 +1474,14 @@ ctc_lin_kernel(const PipeParams pp, int* __restrict__ flags) {
                 }
                 return;
             }
-            if (G == 8 && V2 == 24) {      // V = 48, four frames per pass: straight-line code, no guards
+            if (!WIDE && G == 8 && V2 == 24) {      // V = 48, four frames per pass: straight-line code, no guards
                 float2 lg[3];
 #pragma unroll
                 for (int j = 0; j < 3; ++j) lg[j] = row2[gl + 8 * j];
                 softmax_fast(CL, base, rows, lg);
                 return;
             }
-            if (V2 <= 4 * G) {      // at most 4 float2 per lane: the row stays in registers
+            if (!WIDE && V2 <= 4 * G) {      // at most 4 float2 per lane: the row stays in registers
                 float2 x[4];
                 float m = -CUDART_INF_F;
                 unsigned mk = 0u;
@@ -1591,7 +1598,7 @@ ctc_lin_kernel(const PipeParams pp, int* __restrict__ flags) {
             float* orow = obase + fr * ER;
             const float2* y2 = reinterpret_cast<const float2*>(ybase + fr * Vs);
             float2* g2 = reinterpret_cast<float2*>(grad_b + (size_t)(tbase + tsign * (tt0 + fr)) * frame_stride);
-            if (RC == 1 && G == 8 && V2 == 24) {   // V = 48, four frames per pass: straight-line code
+            if (!WIDE && RC == 1 && G == 8 && V2 == 24) {   // V = 48, four frames per pass: straight-line code
                 const float4 bp = *reinterpret_cast<const float4*>(orow + VO + 4 * gl);
                 uint2 x[3];
                 float2 y[3];
@@ -1632,9 +1639,78 @@ ctc_lin_kernel(const PipeParams pp, int* __restrict__ flags) {
 #endif
                 return;
             }
+            if constexpr (RC > 1 && YS == 80) {
+                // several recursion warps (C3: four), V <= 60, a group of 8 lanes per frame: the RC occupancy rows
+                // of the frame with every load issued up front (the looped path below pays one shared-memory
+                // latency per load: 28 in a row for RC = 4), the two reductions sharing their shuffle levels
+                if (G == 8) {
+                    float4 bp[RC];
+                    uint2 x[RC][4];
+                    float2 y[4];
+#pragma unroll
+                    for (int rw = 0; rw < RC; ++rw) bp[rw] = *reinterpret_cast<const float4*>(orow + rw * OW + VO + 4 * gl);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const int c = gl + 8 * j;
+                        y[j] = make_float2(0.f, 0.f);
+#pragma unroll
+                        for (int rw = 0; rw < RC; ++rw) x[rw][j] = make_uint2(0u, 0u);
+                        if (c < V2) {
+#pragma unroll
+                            for (int rw = 0; rw < RC; ++rw) x[rw][j] = (reinterpret_cast<const uint2*>(orow + rw * OW))[c];
+                            y[j] = y2[c];
+                        }
+                    }
+                    if (act) {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const int c = gl + 8 * j;
+                            if (c < V2) {
+#pragma unroll
+                                for (int rw = 0; rw < RC; ++rw) (reinterpret_cast<uint2*>(orow + rw * OW))[c] = make_uint2(0u, 0u);
+                            }
+                        }
+                    }
+                    float bs = 0.f, tot = 0.f;
+#pragma unroll
+                    for (int rw = 0; rw < RC; ++rw) bs += (bp[rw].x + bp[rw].y) + (bp[rw].z + bp[rw].w);
+                    float2 o[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        o[j] = make_float2(0.f, 0.f);
+#pragma unroll
+                        for (int rw = 0; rw < RC; ++rw) {
+                            o[j].x += __uint2float_rn(x[rw][j].x) * (1.0f / kQ31);
+                            o[j].y += __uint2float_rn(x[rw][j].y) * (1.0f / kQ31);
+                        }
+                        tot += o[j].x + o[j].y;
+                    }
+#pragma unroll
+                    for (int sft = 4; sft > 0; sft >>= 1) {
+                        bs += __shfl_xor_sync(0xffffffffu, bs, sft);
+                        tot += __shfl_xor_sync(0xffffffffu, tot, sft);
+                    }
+                    if (act) {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const int c = gl + 8 * j;
+                            if (c < V2) {
+                                if ((blank >> 1) == c) { if (blank & 1) o[j].y += bs; else o[j].x += bs; }
+                                g2[c] = make_float2((CLAMPED && __float_as_int(y[j].x) < 0) ? 0.f : gscale * (y[j].x - o[j].x),
+                                                    (CLAMPED && __float_as_int(y[j].y) < 0) ? 0.f : gscale * (y[j].y - o[j].y));
+                            }
+                        }
+                        if (!(fabsf(tot + bs - 1.0f) <= kMassTol)) s_flag[0] = 1;   // NaN-safe
+#ifdef CTC_B200_MASSDEV
+                        atomicMax(&s_flag[2], __float_as_int(fabsf(tot + bs - 1.0f)));
+#endif
+                    }
+                    return;
+                }
+            }
             float bs = 0.f;
             for (int i = gl; i < 32 * R; i += G) bs += orow[(i >> 5) * OW + VO + (i & 31)];
-            if (al && R == 1 && V2 <= 4 * G) {     // at most 4 float2 per lane: everything stays in registers
+            if (!WIDE && al && R == 1 && V2 <= 4 * G) {     // at most 4 float2 per lane: everything stays in registers
                 float2 o[4], y[4];
                 float tot = 0.f;
 #pragma unroll
@@ -1766,7 +1842,7 @@ ctc_lin_kernel(const PipeParams pp, int* __restrict__ flags) {
                 }
                 return;
             }
-            if (!al) {      // gradient rows that are not 16-byte aligned in HBM: scalar loads / stores
+            if (!WIDE && !al) {      // gradient rows that are not 16-byte aligned in HBM: scalar loads / stores
                 float* g1 = reinterpret_cast<float*>(g2);
                 const float* y1 = reinterpret_cast<const float*>(y2);
                 for (int c = gl; c < V; c += G) {

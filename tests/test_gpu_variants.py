@@ -51,9 +51,10 @@ LIN_CASES = [
     (4, 750, 177, 100, False, "ctc_lin_kernel<8,1,0,256,2,MID>"),          # the reference's real shape (params.py:27): four helpers
     (4, 300, 100, 60, False, "ctc_lin_kernel<8,1,0,128,4>"),           # 60 < V <= 128, aligned rows: one helper
     (3, 300, 200, 60, False, "ctc_lin_kernel<8,1,0,256,2,MID>"),           # 128 < V <= 256: four helpers
+    (3, 200, 1001, 30, False, "ctc_lin_kernel<8,1,0,256,2>"),             # wide rows that are not 16-byte aligned
     (4, 120, 29, 20, False, "ctc_lin_kernel<8,1,0,128,4>"),            # characters + blank: V % 4 != 0, V < 60
-    (8, 1000, 1024, 200, False, "ctc_lin_kernel<8,1,0,256,2>"),        # C4 slice at full size
-    (80, 120, 1024, 20, False, "ctc_lin_kernel<8,1,0,256,2>"),         # C4's geometry: >= 75 utterances -> chunks of 2 frames
+    (8, 1000, 1024, 200, False, "ctc_lin_kernel<8,1,0,256,2,WIDE>"),        # C4 slice at full size
+    (80, 120, 1024, 20, False, "ctc_lin_kernel<8,1,0,256,2,WIDE>"),         # C4's geometry: >= 75 utterances -> chunks of 2 frames
     (4, 700, 48, 300, False, "ctc_lin_kernel<8,2,80,512,1>"),          # two recursion warps
     (4, 4000, 48, 800, True, "ctc_lin_kernel<8,4,80,512,1>"),          # C3 slice: B=4 of T=4000, S=800
     (3, 700, 128, 300, False, "ctc_lin_kernel<8,0,0,256,2>"),          # run-time strides, R = 2
