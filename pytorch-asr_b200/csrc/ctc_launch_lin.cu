@@ -70,16 +70,14 @@ int lin_variant(const Geometry& g, int V) {
         // (the WIDE / MID instantiations have their CTA shape -- four helpers, 224 threads, WIDE: chunks of 2 frames --
         // as compile-time constants; any other choice of the geometry heuristics runs the general instantiation)
         if (V > 256) return (V % 4 == 0 && g.lH == 4 && g.lD == 2 && g.lchunk == 2) ? kLinR1WideAl : kLinR1Wide;
-        return (g.lH == 4 && g.lD == 2) ? kLinR1Mid : kLinR1Wide;
+        // MID keeps a frame's classes in registers, at most 16 per lane: at least 16 lanes per frame
+        return (g.lH == 4 && g.lD == 2 && V <= 256 && g.lchunk <= 4) ? kLinR1Mid : kLinR1Wide;
     }
-    if (g.lYS == 80 && g.lNT <= 512) {
+    if (g.lYS == 80 && g.lNT <= 512 && g.lH == 2 && g.lD == 2) {   // (their CTA shape is a compile-time constant)
         if (g.lR == 2) return kLinR2Y80;
         if (g.lR == 4) return kLinR4Y80;
     }
-    if (g.lYS != 0 && !(g.lYS == 80 && (g.lR == 2 || g.lR == 4))) {
-        // (pick_lin only asks for the fixed emission-ring stride where an instantiation exists)
-        return -1;
-    }
+    if (g.lYS != 0) return -1;   // (pick_lin only asks for the fixed emission-ring stride where an instantiation exists)
     if (g.lNT <= 256) return kLinRn256;
     if (g.lNT <= 512) return kLinRn512;
     return g.lNT <= 1024 ? kLinRn1024 : -1;

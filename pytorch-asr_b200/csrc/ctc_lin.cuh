@@ -295,8 +295,9 @@ ctc_lin_kernel(const PipeParams pp, int* __restrict__ flags) {
     const FusedParams& p = pp.f;
     // threads per CTA: a compile-time constant wherever the instantiation fixes the warp roles (what only other
     // CTA shapes need -- e.g. the two-rows-in-flight combine pass of the 4-warp CTAs -- is then compiled out)
+    // (measured and rejected: the same for the several-recursion-warp instantiations -- C3 1.186 -> 1.220 ms)
     const int NT = (FIX || (RC == 1 && MAXT == 128)) ? 128 : ((WIDE || MID) ? 224 : blockDim.x), NW = NT >> 5;
-    const int R = RC > 0 ? RC : pp.R, H = FIX ? 1 : (WIDE ? 4 : pp.H), NP = RC > 0 ? 32 * P * RC : pp.NP;
+    const int R = RC > 0 ? RC : pp.R, H = FIX ? 1 : ((WIDE || MID) ? 4 : pp.H), NP = RC > 0 ? 32 * P * RC : pp.NP;
     // loop invariants the compiler would otherwise re-derive inside the role loops at the register cap
     // (S2R SR_TID / SR_CgaCtaId cost ~50 cycles each): pinned in registers in the FIX instantiation
     int lane_pin = threadIdx.x & 31;
@@ -318,7 +319,8 @@ ctc_lin_kernel(const PipeParams pp, int* __restrict__ flags) {
     // the V <= 60 emission-ring variants (YS = 80) are only launched with chunks of 4 frames
     const int RS = RC > 0 ? lin_row_stride(32 * P * RC, P) : p.row_stride,
               TC = (YS == 80 && CTC_LIN_TC4) ? 4 : (WIDE ? 2 : p.chunk);   // WIDE: chunks of 2 frames, a warp per frame
-    const int NC = FIX ? 2 : pp.D;           // combine groups: group g takes the rows r == g (mod NC) of a chunk
+    // combine groups: group g takes the rows r == g (mod NC) of a chunk
+    const int NC = (FIX || WIDE || MID) ? 2 : pp.D;
     const bool is_rec = w < R, is_comb = w >= R && w < (1 + NC) * R;
     const int hw = w - (1 + NC) * R;   // helper index (>= 0 for SOFT / GRAD warps)
     const int cg = is_comb ? (w - R) / R : 0;
@@ -858,6 +860,15 @@ ctc_lin_kernel(const PipeParams pp, int* __restrict__ flags) {
             }
         };
         Ring ring_part(NS), iss_p(NS);
+        Ring iss_y(NL);                  // WIDE: this warp also requests the logits rows (TMA), kLinYDist + 1 chunks ahead
+        if constexpr (WIDE) {
+            if (iss_part) {
+                for (int k = 0; k <= kLinYDist; ++k) {
+                    if (k < nch && lane == 0) issue_logits_tma(k, iss_y.slot);
+                    iss_y.advance();
+                }
+            }
+        }
         int a_buf = 0, o_buf = 0;
         // loop-invariant kernel parameters live in registers (each re-read from the constant bank
         // would be an exposed latency in front of a branch)
@@ -866,6 +877,12 @@ ctc_lin_kernel(const PipeParams pp, int* __restrict__ flags) {
         const bool wgc = wgc_i != 0;
         auto comb_iter = [&](int it) {
                 LPROF_BEGIN();
+                if constexpr (WIDE) {
+                    if (iss_part) {
+                        if (it + kLinYDist + 1 < nch && lane == 0) issue_logits_tma(it + kLinYDist + 1, iss_y.slot);
+                        iss_y.advance();
+                    }
+                }
                 // partner rows of chunk `it` (consumed in iteration it+2); the first two consume chunks
                 // are requested at the phase break
                 if (it >= n1_i + 2 && it + kLinPDist - 2 < nch_i && wgc) {
@@ -1279,7 +1296,7 @@ ctc_lin_kernel(const PipeParams pp, int* __restrict__ flags) {
         const unsigned gmaskA = (GA == 32 ? 0xffffffffu : ((1u << GA) - 1u)) << (lane & ~(GA - 1));
         // rows that are not 16-byte aligned in HBM: 16-byte copies + register-resident passes when a lane holds at
         // most 16 classes of its frame (V <= 256 with four helpers, V <= 128 with one)
-        const bool shifted = MID && !al && !wide_rows && (V + GA - 1) / GA <= 16;
+        const bool shifted = MID && !al;
         auto row_mis = [&](int tt) {     // floats between the 16-byte line and the logits row of sweep step tt
             return (int)((reinterpret_cast<uintptr_t>(acts_b + (ptrdiff_t)(tbase + tsign * tt) * (ptrdiff_t)frame_stride) >> 2) & 3);
         };
@@ -1418,8 +1435,8 @@ ctc_lin_kernel(const PipeParams pp, int* __restrict__ flags) {
             const bool act = f < rows;
             float* row = base + min(f, rows - 1) * Vs;
             float2* row2 = reinterpret_cast<float2*>(row);
-            if (MID && (V + G - 1) / G <= 16) {
-                // at most 16 classes per lane: one pass in registers (a row that is not 16-byte aligned in HBM
+            if constexpr (MID) {
+                // at most 16 classes per lane (V <= 256, at least 16 lanes per frame): one pass in registers (a row that is not 16-byte aligned in HBM
                 // sits `mis` floats into its ring row and is moved to the front here)
                 const float* rin = row + (shifted ? row_mis(tt0 + min(f, rows - 1)) : 0);
                 float x[16];
@@ -1805,7 +1822,7 @@ ctc_lin_kernel(const PipeParams pp, int* __restrict__ flags) {
             }
             bs = group_sum(bs, G);
             float tot = 0.f;
-            if (MID && R == 1 && (V + G - 1) / G <= 16) {
+            if constexpr (MID) {
                 // at most 16 classes per lane: every load issued up front
                 float* g1 = reinterpret_cast<float*>(g2);
                 const float* y1 = reinterpret_cast<const float*>(y2);
@@ -1891,7 +1908,9 @@ ctc_lin_kernel(const PipeParams pp, int* __restrict__ flags) {
         // ---- the helper schedule -----------------------------------------------------------
         // Iteration `it`:  SOFT 0 requests the logits of chunk it + kLinYDist + 1; SOFT: softmax of
         // chunk it; GRAD: gradient rows of chunk it-3 (REC runs chunk it-1, COMB chunk it-2).
-        const bool iss_acts = isA && (ha == 0 || own_rows);
+        // (WIDE: the logits rows are requested by the first combine warp, which has the most slack -- the first
+        // softmax warp spent 536 of its 2756 cycles per chunk issuing two TMA copies)
+        const bool iss_acts = !WIDE && isA && (ha == 0 || own_rows);
         const bool do_sm = isA && ha * FA < TC, do_gr = isB && hb * FB < TC && want_grad;
         Ring iss_a(NL), sm_a(NL), gr_a(NL);
         int gr_o = 0;
