@@ -43,8 +43,24 @@
 // chunk it, REC on chunk it-1, COMB on chunk it-2, GRAD on chunk it-3.  C2 (B=256, T=1000, V=48):
 // 4 warps per CTA (REC, 2 x COMB, helper), 4 CTAs per SM, 128 registers; this shape class (V = 48, one
 // helper, two combine groups, chunks of 4 frames) has its own instantiation with all of these as
-// compile-time constants (FIX).  Wide vocabularies (V > 256): two SOFT and two GRAD warps, a warp per
-// frame, logits rows by ONE TMA bulk copy per row, softmax / gradient rows held in registers.
+// compile-time constants (FIX).
+//
+// FIX runs its FULL chunks in steady-state loops of their own, one per role and half (rec_iter / comb_iter /
+// help_iter keep the general iteration for short chunks, the phase break and the drain): shared memory by
+// explicit 32-bit addresses off one register-resident base, REC loads the emissions of step r + 1 before it
+// stores the row of step r and publishes its rows in the shared-memory ring in BOTH halves (the combine
+// warps, idle in the first half, copy them to the lattice in HBM), the helper interleaves the gradient and
+// softmax chains and pulls the logits into L2 six chunks ahead.  Why: at the 128-register cap the general loop
+// re-derived shared-memory bases from S2R SR_CgaCtaId, kernel parameters from the constant bank and the chunk
+// geometry in every iteration (39 % of the combine warp's active samples; profiles/r02_ncu_summary.md).
+//
+// Other instantiations prune at compile time what their shape class never runs (the kernels are
+// instruction-fetch bound as soon as the hot path is scattered over the whole template):
+//   WIDE (V > 256, aligned rows; C4): two SOFT and two GRAD warps, a warp per frame, chunks of 2 frames, logits
+//        rows by ONE TMA bulk copy per row (requested by the first combine warp), rows held in registers;
+//   MID  (61 ... 256 classes, the reference's V = 177 included): four helpers, every softmax warp copies and waits
+//        for its own frames, rows that are not 16-byte aligned in HBM arrive in whole 16-byte segments;
+//   QUEUE (FIX only): the loop over a device-side utterance queue (persistent launch).
 //
 // Which utterance a cluster works on: (blockIdx.x / 2 + utt_rot) mod n_utt.  The host rotates the
 // (length-sorted) batch by whole launch layers so that the longest utterances land on the SM pairs that
@@ -1203,73 +1219,73 @@ ctc_lin_kernel(const PipeParams pp, int* __restrict__ flags) {
                     }
                     mbar_wait_a(bar0 + 8u * (unsigned)ring_part.slot, ring_part.parity);   // TMA data landed
                     {
-                constexpr unsigned RSB = 544u * 4u, PLB = 256u * 4u, HSB = 128u * 4u, ERB = 112u * 4u;
-                const unsigned stb = sbase + lay.stage + (unsigned)ring_part.slot * (4u * RSB);
-                const unsigned stA = stb + fx_stA, stB = stb + fx_stB;
-                const unsigned arA = sbase + lay.a + (unsigned)a_buf * (4u * RSB) + fx_ar, arB = arA + 2u * RSB;
-                const unsigned ocA = sbase + lay.occ + (unsigned)o_buf * (4u * ERB) + (unsigned)cg * ERB, ocB = ocA + 2u * ERB;
-                float4 t0, t1;
-                float qyA[P], qyB[P], aYA[P], aYB[P];
+                        constexpr unsigned RSB = 544u * 4u, PLB = 256u * 4u, HSB = 128u * 4u, ERB = 112u * 4u;
+                        const unsigned stb = sbase + lay.stage + (unsigned)ring_part.slot * (4u * RSB);
+                        const unsigned stA = stb + fx_stA, stB = stb + fx_stB;
+                        const unsigned arA = sbase + lay.a + (unsigned)a_buf * (4u * RSB) + fx_ar, arB = arA + 2u * RSB;
+                        const unsigned ocA = sbase + lay.occ + (unsigned)o_buf * (4u * ERB) + (unsigned)cg * ERB, ocB = ocA + 2u * ERB;
+                        float4 t0, t1;
+                        float qyA[P], qyB[P], aYA[P], aYB[P];
 #define CTC_LD8(dst, addr) t0 = lds128(addr); t1 = lds128((addr) + HSB); \
     dst[0] = t0.x; dst[1] = t0.y; dst[2] = t0.z; dst[3] = t0.w; dst[4] = t1.x; dst[5] = t1.y; dst[6] = t1.z; dst[7] = t1.w
-                CTC_LD8(qyA, stA + PLB);
-                CTC_LD8(qyB, stB + PLB);
-                const int obA = lds32i(stA + fx_e), obB = lds32i(stB + fx_e);
-                const int offA = lds32i(arA + fx_o), offB = lds32i(arB + fx_o);
-                CTC_LD8(aYA, arA + PLB);
-                CTC_LD8(aYB, arB + PLB);
-                float ylA = __shfl_down_sync(0xffffffffu, qyA[P - 1], 1);
-                float ylB = __shfl_down_sync(0xffffffffu, qyB[P - 1], 1);
-                int olA = __shfl_down_sync(0xffffffffu, obA, 1);
-                int olB = __shfl_down_sync(0xffffffffu, obB, 1);
-                if (lane == 31 && hasX1) {
-                    ylA = lds32(stA + PLB + HSB - 4u); olA = lds32i(stA + fx_e - 4u);
-                    ylB = lds32(stB + PLB + HSB - 4u); olB = lds32i(stB + fx_e - 4u);
-                }
-                const bool winA = uA < win_cons;
-                const bool winB = uA + 2u < win_cons;
-                const int hbA = offA + obA - E0, hyA = offA + olA - E0;
-                const int hbB = offB + obB - E0, hyB = offB + olB - E0;
-                const int cbA = max(min(hbA, kLinHmax), kLinHmin), cyA = max(min(hyA, kLinHmax), kLinHmin);
-                const int cbB = max(min(hbB, kLinHmax), kLinHmin), cyB = max(min(hyB, kLinHmax), kLinHmin);
-                const float sbA = winA ? pow2c(cbA) * rz : 0.f, sbB = winB ? pow2c(cbB) * rz : 0.f;
-                const float syA = (winA && hasX1) ? pow2c(cyA) * (rz * kQ31) : 0.f;
-                const float syB = (winB && hasX1) ? pow2c(cyB) * (rz * kQ31) : 0.f;
-                const float rbA = pow2c(hbA - cbA), ryA = pow2c(hyA - cyA);
-                const float rbB = pow2c(hbB - cbB), ryB = pow2c(hyB - cyB);
-                const float sqA = sbA * kQ31, sqB = sbB * kQ31;
-                unsigned gA[P], gB[P];
+                        CTC_LD8(qyA, stA + PLB);
+                        CTC_LD8(qyB, stB + PLB);
+                        const int obA = lds32i(stA + fx_e), obB = lds32i(stB + fx_e);
+                        const int offA = lds32i(arA + fx_o), offB = lds32i(arB + fx_o);
+                        CTC_LD8(aYA, arA + PLB);
+                        CTC_LD8(aYB, arB + PLB);
+                        float ylA = __shfl_down_sync(0xffffffffu, qyA[P - 1], 1);
+                        float ylB = __shfl_down_sync(0xffffffffu, qyB[P - 1], 1);
+                        int olA = __shfl_down_sync(0xffffffffu, obA, 1);
+                        int olB = __shfl_down_sync(0xffffffffu, obB, 1);
+                        if (lane == 31 && hasX1) {
+                            ylA = lds32(stA + PLB + HSB - 4u); olA = lds32i(stA + fx_e - 4u);
+                            ylB = lds32(stB + PLB + HSB - 4u); olB = lds32i(stB + fx_e - 4u);
+                        }
+                        const bool winA = uA < win_cons;
+                        const bool winB = uA + 2u < win_cons;
+                        const int hbA = offA + obA - E0, hyA = offA + olA - E0;
+                        const int hbB = offB + obB - E0, hyB = offB + olB - E0;
+                        const int cbA = max(min(hbA, kLinHmax), kLinHmin), cyA = max(min(hyA, kLinHmax), kLinHmin);
+                        const int cbB = max(min(hbB, kLinHmax), kLinHmin), cyB = max(min(hyB, kLinHmax), kLinHmin);
+                        const float sbA = winA ? pow2c(cbA) * rz : 0.f, sbB = winB ? pow2c(cbB) * rz : 0.f;
+                        const float syA = (winA && hasX1) ? pow2c(cyA) * (rz * kQ31) : 0.f;
+                        const float syB = (winB && hasX1) ? pow2c(cyB) * (rz * kQ31) : 0.f;
+                        const float rbA = pow2c(hbA - cbA), ryA = pow2c(hyA - cyA);
+                        const float rbB = pow2c(hbB - cbB), ryB = pow2c(hyB - cyB);
+                        const float sqA = sbA * kQ31, sqB = sbB * kQ31;
+                        unsigned gA[P], gB[P];
 #pragma unroll
-                for (int q = 0; q + 1 < P; ++q) {
-                    gA[q] = __float2uint_rn((aYA[q] * (qyA[P - 2 - q] * sqA)) * rbA);
-                    gB[q] = __float2uint_rn((aYB[q] * (qyB[P - 2 - q] * sqB)) * rbB);
-                }
-                gA[P - 1] = __float2uint_rn((aYA[P - 1] * (ylA * syA)) * ryA);
-                gB[P - 1] = __float2uint_rn((aYB[P - 1] * (ylB * syB)) * ryB);
-                float bsA = 0.f, bsB = 0.f;
-                {
-                    float qbA[P], qbB[P], aBA[P], aBB[P];
-                    CTC_LD8(qbA, stA);
-                    CTC_LD8(qbB, stB);
-                    CTC_LD8(aBA, arA);
-                    CTC_LD8(aBB, arB);
+                        for (int q = 0; q + 1 < P; ++q) {
+                            gA[q] = __float2uint_rn((aYA[q] * (qyA[P - 2 - q] * sqA)) * rbA);
+                            gB[q] = __float2uint_rn((aYB[q] * (qyB[P - 2 - q] * sqB)) * rbB);
+                        }
+                        gA[P - 1] = __float2uint_rn((aYA[P - 1] * (ylA * syA)) * ryA);
+                        gB[P - 1] = __float2uint_rn((aYB[P - 1] * (ylB * syB)) * ryB);
+                        float bsA = 0.f, bsB = 0.f;
+                        {
+                            float qbA[P], qbB[P], aBA[P], aBB[P];
+                            CTC_LD8(qbA, stA);
+                            CTC_LD8(qbB, stB);
+                            CTC_LD8(aBA, arA);
+                            CTC_LD8(aBB, arB);
 #pragma unroll
-                    for (int q = 0; q < P; ++q) {
-                        bsA += (aBA[q] * (qbA[P - 1 - q] * sbA)) * rbA;
-                        bsB += (aBB[q] * (qbB[P - 1 - q] * sbB)) * rbB;
-                    }
-                }
+                            for (int q = 0; q < P; ++q) {
+                                bsA += (aBA[q] * (qbA[P - 1 - q] * sbA)) * rbA;
+                                bsB += (aBB[q] * (qbB[P - 1 - q] * sbB)) * rbB;
+                            }
+                        }
 #undef CTC_LD8
-                if (winA) {
+                        if (winA) {
 #pragma unroll
-                    for (int q = 0; q < P; ++q) reds_add_u32(ocA + (unsigned)lab[q], gA[q]);
-                }
-                if (winB) {
+                            for (int q = 0; q < P; ++q) reds_add_u32(ocA + (unsigned)lab[q], gA[q]);
+                        }
+                        if (winB) {
 #pragma unroll
-                    for (int q = 0; q < P; ++q) reds_add_u32(ocB + (unsigned)lab[q], gB[q]);
-                }
-                sts32(ocA + fx_bl, winA ? bsA : 0.f);
-                sts32(ocB + fx_bl, winB ? bsB : 0.f);
+                            for (int q = 0; q < P; ++q) reds_add_u32(ocB + (unsigned)lab[q], gB[q]);
+                        }
+                        sts32(ocA + fx_bl, winA ? bsA : 0.f);
+                        sts32(ocB + fx_bl, winB ? bsB : 0.f);
                     }
                     uA += 4u;
                     ring_part.advance();
