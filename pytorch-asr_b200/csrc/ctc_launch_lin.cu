@@ -71,7 +71,7 @@ int lin_variant(const Geometry& g, int V) {
         // as compile-time constants; any other choice of the geometry heuristics runs the general instantiation)
         if (V > 256) return (V % 4 == 0 && g.lH == 4 && g.lD == 2 && g.lchunk == 2) ? kLinR1WideAl : kLinR1Wide;
         // MID keeps a frame's classes in registers, at most 16 per lane: at least 16 lanes per frame
-        return (g.lH == 4 && g.lD == 2 && V <= 256 && g.lchunk <= 4) ? kLinR1Mid : kLinR1Wide;
+        return (g.lH == 4 && g.lD == 2 && V <= 256 && g.lchunk == 4) ? kLinR1Mid : kLinR1Wide;
     }
     if (g.lYS == 80 && g.lNT <= 512 && g.lH == 2 && g.lD == 2) {   // (their CTA shape is a compile-time constant)
         if (g.lR == 2) return kLinR2Y80;

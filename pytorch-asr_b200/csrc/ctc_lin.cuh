@@ -334,7 +334,7 @@ ctc_lin_kernel(const PipeParams pp, int* __restrict__ flags) {
     const Clamp clp{p.use_clamp != 0, p.clamp_lo, p.clamp_hi};
     // the V <= 60 emission-ring variants (YS = 80) are only launched with chunks of 4 frames
     const int RS = RC > 0 ? lin_row_stride(32 * P * RC, P) : p.row_stride,
-              TC = (YS == 80 && CTC_LIN_TC4) ? 4 : (WIDE ? 2 : p.chunk);   // WIDE: chunks of 2 frames, a warp per frame
+              TC = ((YS == 80 && CTC_LIN_TC4) || MID) ? 4 : (WIDE ? 2 : p.chunk);   // WIDE: chunks of 2 frames, a warp per frame
     // combine groups: group g takes the rows r == g (mod NC) of a chunk
     const int NC = (FIX || WIDE || MID) ? 2 : pp.D;
     const bool is_rec = w < R, is_comb = w >= R && w < (1 + NC) * R;
@@ -1452,44 +1452,53 @@ ctc_lin_kernel(const PipeParams pp, int* __restrict__ flags) {
             float* row = base + min(f, rows - 1) * Vs;
             float2* row2 = reinterpret_cast<float2*>(row);
             if constexpr (MID) {
-                // at most 16 classes per lane (V <= 256, at least 16 lanes per frame): one pass in registers (a row that is not 16-byte aligned in HBM
-                // sits `mis` floats into its ring row and is moved to the front here)
-                const float* rin = row + (shifted ? row_mis(tt0 + min(f, rows - 1)) : 0);
-                float x[16];
-                float m = -CUDART_INF_F;
-                unsigned mk = 0u;
+                // MID: chunks of 4 frames, two softmax warps, 16 lanes per frame: lane gl holds classes gl, gl + 16, ...
+                // (at most NV = 12 of them up to V = 192, 16 up to 256) in registers, loaded by immediate offsets.  A row
+                // that is not 16-byte aligned in HBM sits `mis` floats into its ring row and is moved to the front here.
+                auto body = [&](auto NVC) {
+                    constexpr int NV = decltype(NVC)::value;
+                    const float* rin = row + (shifted ? row_mis(tt0 + min(f, rows - 1)) : 0) + gl;
+                    const int nv = (V - gl + 15) >> 4;      // classes this lane holds
+                    float x[NV];
+                    float m = -CUDART_INF_F;
+                    unsigned mk = 0u;
 #pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                    const int c = gl + j * G;
-                    x[j] = -CUDART_INF_F;
-                    if (c < V) {
-                        const float raw = rin[c];
-                        mk |= (clq.cmask(raw) ? 1u : 0u) << j;
-                        x[j] = clq.cin(raw);
-                    }
-                    m = fmaxf(m, x[j]);
-                }
-                m = group_max(m, G);
-                const float mb = m * kLog2e;
-                float z = 0.f;
-#pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                    x[j] = ex2f(fmaf(x[j], kLog2e, -mb));      // (-inf for the classes beyond V: 0)
-                    z += x[j];
-                }
-                const float rs = 1.0f / group_sum(z, G);
-                __syncwarp();      // every lane has read its raw values before the row is overwritten in place
-                if (act) {
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) {
-                        const int c = gl + j * G;
-                        if (c < V) {
-                            const float y = x[j] * rs;
-                            row[c] = (mk >> j) & 1u ? -y : y;
+                    for (int j = 0; j < NV; ++j) {
+                        x[j] = -CUDART_INF_F;
+                        if (j < nv) {
+                            const float raw = rin[16 * j];
+                            mk |= (clq.cmask(raw) ? 1u : 0u) << j;
+                            x[j] = clq.cin(raw);
                         }
+                        m = fmaxf(m, x[j]);
                     }
-                    for (int c = V + gl; c < Vs; c += G) row[c] = 0.f;   // slot V: what padding pairs gather
-                }
+#pragma unroll
+                    for (int o = 8; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+                    const float mb = m * kLog2e;
+                    float z = 0.f;
+#pragma unroll
+                    for (int j = 0; j < NV; ++j) {
+                        x[j] = ex2f(fmaf(x[j], kLog2e, -mb));      // (-inf for the classes beyond V: 0)
+                        z += x[j];
+                    }
+#pragma unroll
+                    for (int o = 8; o > 0; o >>= 1) z += __shfl_xor_sync(0xffffffffu, z, o);
+                    const float rs = 1.0f / z;
+                    __syncwarp();      // every lane has read its raw values before the row is overwritten in place
+                    if (act) {
+                        float* rout = row + gl;
+#pragma unroll
+                        for (int j = 0; j < NV; ++j) {
+                            if (j < nv) {
+                                const float y = x[j] * rs;
+                                rout[16 * j] = (mk >> j) & 1u ? -y : y;
+                            }
+                        }
+                        if (gl < Vs - V) row[V + gl] = 0.f;   // slot V (and the padding behind it): what padding pairs gather
+                    }
+                };
+                if (V <= 192) body(std::integral_constant<int, 12>{});
+                else body(std::integral_constant<int, 16>{});
                 return;
             }
             if (!WIDE && !al) {      // rows that are not 16-byte aligned in HBM (V % 4 != 0): scalar passes
@@ -1743,7 +1752,7 @@ ctc_lin_kernel(const PipeParams pp, int* __restrict__ flags) {
             }
             float bs = 0.f;
             for (int i = gl; i < 32 * R; i += G) bs += orow[(i >> 5) * OW + VO + (i & 31)];
-            if (!WIDE && al && R == 1 && V2 <= 4 * G) {     // at most 4 float2 per lane: everything stays in registers
+            if (!WIDE && !MID && al && R == 1 && V2 <= 4 * G) {     // at most 4 float2 per lane: everything stays in registers
                 float2 o[4], y[4];
                 float tot = 0.f;
 #pragma unroll
@@ -1779,7 +1788,7 @@ ctc_lin_kernel(const PipeParams pp, int* __restrict__ flags) {
                 }
                 return;
             }
-            if (al && YS == 0 && R == 1 && V4 <= 8 * G) {     // wide vocabulary: at most 8 x 128 bit per lane, all loads up front
+            if (!MID && al && YS == 0 && R == 1 && V4 <= 8 * G) {     // wide vocabulary: at most 8 x 128 bit per lane, all loads up front
                 uint4* o4 = reinterpret_cast<uint4*>(orow);
                 const float4* y4 = reinterpret_cast<const float4*>(y2);
                 float4* g4 = reinterpret_cast<float4*>(g2);
@@ -1839,40 +1848,46 @@ ctc_lin_kernel(const PipeParams pp, int* __restrict__ flags) {
             bs = group_sum(bs, G);
             float tot = 0.f;
             if constexpr (MID) {
-                // at most 16 classes per lane: every load issued up front
-                float* g1 = reinterpret_cast<float*>(g2);
-                const float* y1 = reinterpret_cast<const float*>(y2);
-                unsigned* o1 = reinterpret_cast<unsigned*>(orow);
-                float o[16], y[16];
-                float tsum = 0.f;
+                // lane gl holds classes gl, gl + 16, ... of its frame: every load issued up front, immediate offsets
+                auto body = [&](auto NVC) {
+                    constexpr int NV = decltype(NVC)::value;
+                    float* g1 = reinterpret_cast<float*>(g2) + gl;
+                    const float* y1 = reinterpret_cast<const float*>(y2) + gl;
+                    unsigned* o1 = reinterpret_cast<unsigned*>(orow) + gl;
+                    const int nv = (V - gl + 15) >> 4;
+                    const int jb = ((blank - gl) & 15) == 0 ? (blank - gl) >> 4 : -1;   // which of my classes is the blank
+                    float o[NV], y[NV];
+                    float tsum = 0.f;
 #pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                    const int c = gl + j * G;
-                    o[j] = 0.f;
-                    y[j] = 0.f;
-                    if (c < V) {
-                        const unsigned xq = o1[c];
-                        y[j] = y1[c];
-                        if (act) o1[c] = 0u;
-                        o[j] = __uint2float_rn(xq) * (1.0f / kQ31);
-                        tsum += o[j];
-                    }
-                }
-                tsum = group_sum(tsum, G);      // (bs is already the frame's blank sum)
-                if (act) {
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) {
-                        const int c = gl + j * G;
-                        if (c < V) {
-                            const float ov = o[j] + (c == blank ? bs : 0.f);
-                            g1[c] = (CLAMPED && __float_as_int(y[j]) < 0) ? 0.f : gscale * (y[j] - ov);
+                    for (int j = 0; j < NV; ++j) {
+                        o[j] = 0.f;
+                        y[j] = 0.f;
+                        if (j < nv) {
+                            const unsigned xq = o1[16 * j];
+                            y[j] = y1[16 * j];
+                            if (act) o1[16 * j] = 0u;
+                            o[j] = __uint2float_rn(xq) * (1.0f / kQ31);
+                            tsum += o[j];
                         }
                     }
-                    if (!(fabsf(tsum + bs - 1.0f) <= kMassTol)) s_flag[0] = 1;   // NaN-safe
+#pragma unroll
+                    for (int sft = 8; sft > 0; sft >>= 1) tsum += __shfl_xor_sync(0xffffffffu, tsum, sft);   // (bs is reduced already)
+                    if (act) {
+#pragma unroll
+                        for (int j = 0; j < NV; ++j) {
+                            if (j < nv) {
+                                const float ov = o[j] + (j == jb ? bs : 0.f);
+                                g1[16 * j] = (CLAMPED && __float_as_int(y[j]) < 0) ? 0.f : gscale * (y[j] - ov);
+                            }
+                        }
+                        if (!(fabsf(tsum + bs - 1.0f) <= kMassTol)) s_flag[0] = 1;   // NaN-safe
 #ifdef CTC_B200_MASSDEV
-                    atomicMax(&s_flag[2], __float_as_int(fabsf(tsum + bs - 1.0f)));
+                        atomicMax(&s_flag[2], __float_as_int(fabsf(tsum + bs - 1.0f)));
 #endif
-                }
+                    }
+                };
+                if (V <= 192) body(std::integral_constant<int, 12>{});
+                else body(std::integral_constant<int, 16>{});
                 return;
             }
             if (!WIDE && !al) {      // gradient rows that are not 16-byte aligned in HBM: scalar loads / stores
