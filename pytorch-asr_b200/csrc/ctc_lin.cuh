@@ -1313,9 +1313,10 @@ ctc_lin_kernel(const PipeParams pp, int* __restrict__ flags) {
         // rows that are not 16-byte aligned in HBM: 16-byte copies + register-resident passes when a lane holds at
         // most 16 classes of its frame (V <= 256 with four helpers, V <= 128 with one)
         const bool shifted = MID && !al;
-        auto row_mis = [&](int tt) {     // floats between the 16-byte line and the logits row of sweep step tt
-            return (int)((reinterpret_cast<uintptr_t>(acts_b + (ptrdiff_t)(tbase + tsign * tt) * (ptrdiff_t)frame_stride) >> 2) & 3);
-        };
+        // floats between the 16-byte line and the logits row of sweep step tt: (mis0 + tt * mis_step) & 3
+        const int mis0 = (int)(((reinterpret_cast<uintptr_t>(acts_b) >> 2) + (uintptr_t)tbase * (uintptr_t)frame_stride) & 3);
+        const int mis_step = (int)((uintptr_t)((ptrdiff_t)tsign * (ptrdiff_t)frame_stride) & 3);
+        auto row_mis = [&](int tt) { return (mis0 + tt * mis_step) & 3; };
         auto group_sum = [&](float x, int G) {
             for (int o = G >> 1; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
             return x;
@@ -1358,13 +1359,20 @@ ctc_lin_kernel(const PipeParams pp, int* __restrict__ flags) {
             if (MID && !al && shifted) {
                 // rows that start 4, 8 or 12 bytes into a 16-byte line (V % 4 != 0): whole 16-byte segments of the
                 // lines the row touches; class c lands at ring position mis + c (the bytes in front of the row
-                // belong to the previous row of the tensor, the tail of the last segment is zero-filled)
-                for (int r = r_lo; r < min(rows, r_lo + r_cnt); ++r) {
-                    const float* srow = src + r * a_inc;
-                    const int mis = (int)((reinterpret_cast<uintptr_t>(srow) >> 2) & 3);
-                    const int segs = (mis + V + 3) >> 2;
-                    for (int c = lane; c < segs; c += 32)
-                        cp_async16_zfill(dst + r * Vs + 4 * c, srow - mis + 4 * c, min(16, (mis + V - 4 * c) * 4));
+                // belong to the previous row of the tensor, the tail of the last segment is zero-filled).  At most
+                // 65 segments per row (V <= 256): three predicated copies per lane and row, straight-line.
+#pragma unroll
+                for (int rr = 0; rr < 2; ++rr) {      // MID: this warp's two frames of the chunk
+                    const int r = r_lo + rr;
+                    if (r < rows) {
+                        const int mis = (mis0 + (tt0 + r) * mis_step) & 3;
+                        const float* s16 = src + r * a_inc - mis + 4 * lane;      // 16-byte aligned
+                        float* d16 = dst + r * Vs + 4 * lane;
+                        const int left = (mis + V) * 4 - 16 * lane;             // bytes of the row from my first segment on
+#pragma unroll
+                        for (int q = 0; q < 3; ++q)
+                            if (left - 512 * q > 0) cp_async16_zfill(d16 + 128 * q, s16 + 128 * q, min(16, left - 512 * q));
+                    }
                 }
             } else if (!al) {
                 for (int r = r_lo; r < min(rows, r_lo + r_cnt); ++r)
