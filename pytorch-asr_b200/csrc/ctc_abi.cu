@@ -167,9 +167,10 @@ bool pick_lin(int T, int V, int S_max, int n_utt, Geometry* g) {
     // one helper warp (softmax, then gradient rows) when one recursion warp suffices: 4 warps per CTA
     // leave 128 registers per thread, which the two-rows-in-flight combine pass needs
     // helper warps: one (softmax, then gradient rows) for the narrow vocabularies; two softmax + two gradient warps
-    // for rows of more than 128 classes and for wide rows that are not 16-byte aligned (the reference's own
-    // V = 177, params.py:27: 0.82 ms with one helper, 0.57 ms with four on B = 64, T = 750)
-    int H = (V > 128 || (!al && V > 60)) ? 4 : (R == 1 ? 1 : 2);
+    // for rows of more than 64 classes (one helper keeps at most 4 x 64 bit of a frame per lane in registers) and
+    // for wide rows that are not 16-byte aligned (the reference's own V = 177, params.py:27: 0.82 ms with one
+    // helper and the looped passes, 0.26 ms with four and the MID instantiation on B = 64, T = 750)
+    int H = R == 1 ? ((V > 64 || (!al && V > 60)) ? 4 : 1) : (V > 256 ? 4 : 2);
     if (env().helpers == 1 || env().helpers == 2 || env().helpers == 4) H = env().helpers;   // developer knob
     const int NC = R <= 4 ? 2 : 1;   // two combine groups while the CTA stays within 512 threads
     const int NT = 32 * ((1 + NC) * R + H);

@@ -47,9 +47,10 @@ LIN_CASES = [
     (4, 1000, 48, 200, False, "ctc_lin_kernel<8,1,80,128,4,FIX>"),     # C2 slice at full length
     (5, 150, 32, 30, False, "ctc_lin_kernel<8,1,80,128,4>"),           # V <= 60, not 48
     (5, 150, 60, 30, False, "ctc_lin_kernel<8,1,80,128,4>"),
-    (4, 160, 128, 30, False, "ctc_lin_kernel<8,1,0,128,4>"),           # 60 < V <= 256
+    (4, 160, 64, 30, False, "ctc_lin_kernel<8,1,0,128,4>"),            # 60 < V <= 64: one helper, a frame's row in registers
+    (4, 160, 128, 30, False, "ctc_lin_kernel<8,1,0,256,2,MID>"),       # 64 < V <= 256: four helpers
     (4, 750, 177, 100, False, "ctc_lin_kernel<8,1,0,256,2,MID>"),          # the reference's real shape (params.py:27): four helpers
-    (4, 300, 100, 60, False, "ctc_lin_kernel<8,1,0,128,4>"),           # 60 < V <= 128, aligned rows: one helper
+    (4, 300, 100, 60, False, "ctc_lin_kernel<8,1,0,256,2,MID>"),       # aligned rows of 100 classes
     (3, 300, 200, 60, False, "ctc_lin_kernel<8,1,0,256,2,MID>"),           # 128 < V <= 256: four helpers
     (3, 200, 1001, 30, False, "ctc_lin_kernel<8,1,0,256,2>"),             # wide rows that are not 16-byte aligned
     (4, 120, 29, 20, False, "ctc_lin_kernel<8,1,0,128,4>"),            # characters + blank: V % 4 != 0, V < 60
