@@ -449,12 +449,12 @@ def main():
         e2e_loss = ses.run(pinned, tg, il, tl, reduction="mean")
     e2e_s = time.perf_counter() - t0
     e2e_launches = ses.last_launches()
+    h2d = ses.last_h2d_bytes()     # what the session actually copied (logits rows up to each slice's longest utterance)
     t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
     if dist is not None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_s = float(t[0])
     e2e_value = world * B * T * K2 / e2e_s
-    h2d = acts.numel() * 4 + int(tg.numel()) * 4 + 16 * B   # logits + labels + 4 int32/f32 per utterance
     ses.close()
     assert abs(e2e_loss - r["local_loss"]) <= 2e-6 * abs(r["local_loss"]), (e2e_loss, r["local_loss"])
 
@@ -492,7 +492,9 @@ def main():
         "roofline": roofline_block(r, peak, peak_src, workload),
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
                 "d2h_bytes_per_step": 16, "steps": K2, "ms_per_step": e2e_s / K2 * 1e3,
-                "api": "ctc_b200_session_run_host_f32 (pinned host logits, sliced H2D overlapped with compute)",
+                "api": "ctc_b200_session_run_host_f32 (pinned host logits, sliced H2D overlapped with compute; "
+                       "frames t >= T_b are never read and not copied)",
+                "padded_logits_bytes": int(acts.numel() * 4),
                 "result": "the 16 bytes read back are the step's result as the trainer consumes it (loss, status); "
                           "the gradient (same size as the logits) stays on the device by design: its consumer is the "
                           "network's backward pass on the same GPU (trainer.py:438)",

@@ -292,7 +292,7 @@ int ctc_b200_session_create(int T, int N, int V, int S_max, int max_targets, int
 int ctc_b200_session_destroy(ctc_b200_session* s);
 
 /*
- *  acts_host     host [T,N,V] fp32 (pinned for full speed)
+ *  acts_host     host [T,N,V] fp32 (pinned for full speed); rows t >= max T_b of a batch slice are not read
  *  targets_host  host int32 [n_targets] concatenated; in_lens/tgt_lens host int32 [N]
  *  loss_host     host fp32 [1] out (reduced per `reduction`; for NONE: sum)
  *  nll_host      host fp32 [N] out or NULL
@@ -308,6 +308,9 @@ int ctc_b200_session_run_host_f32(ctc_b200_session* s, const float* acts_host,
 float* ctc_b200_session_grad_device(ctc_b200_session* s);
 /* number of kernels the last run() launched */
 int ctc_b200_session_last_launches(const ctc_b200_session* s);
+/* bytes the last run() copied host -> device: the packed targets / lengths block plus, per batch slice, the logits
+ * rows up to the slice's longest utterance (frames t >= T_b are never read, so they are not moved) */
+long long ctc_b200_session_last_h2d_bytes(const ctc_b200_session* s);
 
 #ifdef __cplusplus
 }

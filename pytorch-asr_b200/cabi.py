@@ -58,6 +58,7 @@ SYMBOLS = {
     "ctc_b200_session_run_host_f32": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp]),
     "ctc_b200_session_grad_device": (_vp, [_vp]),
     "ctc_b200_session_last_launches": (_i, [_vp]),
+    "ctc_b200_session_last_h2d_bytes": (C.c_longlong, [_vp]),
 }
 
 _lib = None
@@ -272,6 +273,9 @@ class HostSession:
 
     def last_launches(self):
         return self.lib.ctc_b200_session_last_launches(self.h)
+
+    def last_h2d_bytes(self):
+        return int(self.lib.ctc_b200_session_last_h2d_bytes(self.h))
 
     def grad_device_ptr(self):
         return self.lib.ctc_b200_session_grad_device(self.h)

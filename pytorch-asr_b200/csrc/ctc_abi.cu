@@ -615,6 +615,7 @@ struct ctc_b200_session {
     std::vector<cudaStream_t> s_slice;
     std::vector<cudaEvent_t> ev_done;
     int last_launches = 0;
+    long long last_h2d_bytes = 0;
 };
 
 static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
@@ -681,6 +682,7 @@ int ctc_b200_session_destroy(ctc_b200_session* s) {
 
 float* ctc_b200_session_grad_device(ctc_b200_session* s) { return s ? s->d_grad : nullptr; }
 int ctc_b200_session_last_launches(const ctc_b200_session* s) { return s ? s->last_launches : 0; }
+long long ctc_b200_session_last_h2d_bytes(const ctc_b200_session* s) { return s ? s->last_h2d_bytes : 0; }
 
 int ctc_b200_session_run_host_f32(ctc_b200_session* s, const float* acts_host,
                                   const int32_t* targets_host, int n_targets,
@@ -730,14 +732,22 @@ int ctc_b200_session_run_host_f32(ctc_b200_session* s, const float* acts_host,
 
     // ---- slice pipeline: H2D of slice k+1 overlaps the kernel of slice k -------
     int launches = 0;
+    long long h2d = (long long)s->small_bytes;
     const size_t pitch = (size_t)N * V * sizeof(float);
     for (int k = 0; k < s->n_slices; ++k) {
         const int b0 = (int)((long long)N * k / s->n_slices);
         const int b1 = (int)((long long)N * (k + 1) / s->n_slices);
         if (b1 == b0) continue;
-        CTC_CUDA(cudaMemcpy2DAsync(s->d_acts + (size_t)b0 * V, pitch, acts_host + (size_t)b0 * V,
-                                   pitch, (size_t)(b1 - b0) * V * sizeof(float), (size_t)T,
-                                   cudaMemcpyHostToDevice, s->s_copy));
+        // variable-length masking needs no padding: frames t >= T_b are never read, so a slice's copy stops at
+        // its longest utterance (the reference's batches are sorted by length, dataloader.py:53: the slices of
+        // short utterances move correspondingly fewer rows)
+        int rows = 0;
+        for (int b = b0; b < b1; ++b) rows = std::max(rows, in_lens_host[b]);
+        if (rows > 0)
+            CTC_CUDA(cudaMemcpy2DAsync(s->d_acts + (size_t)b0 * V, pitch, acts_host + (size_t)b0 * V,
+                                       pitch, (size_t)(b1 - b0) * V * sizeof(float), (size_t)rows,
+                                       cudaMemcpyHostToDevice, s->s_copy));
+        h2d += (long long)rows * (b1 - b0) * V * (long long)sizeof(float);
         CTC_CUDA(cudaEventRecord(s->ev[k], s->s_copy));
         cudaStream_t sk = env().slice_streams ? s->s_slice[k] : s->s_comp;
         CTC_CUDA(cudaStreamWaitEvent(sk, s->ev[s->n_slices], 0));   // targets / lengths / cleared status
@@ -765,6 +775,7 @@ int ctc_b200_session_run_host_f32(ctc_b200_session* s, const float* acts_host,
                                  cudaMemcpyDeviceToHost, s->s_comp));
     CTC_CUDA(cudaStreamSynchronize(s->s_comp));
     s->last_launches = launches;
+    s->last_h2d_bytes = h2d;
 
     const float* h_out2 = reinterpret_cast<const float*>(s->h_res);
     const int bits = *reinterpret_cast<const int*>(s->h_res + 8);
