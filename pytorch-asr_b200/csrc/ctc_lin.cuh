@@ -1126,7 +1126,8 @@ ctc_lin_kernel(const PipeParams pp, int* __restrict__ flags) {
                     int r = r_begin;
                     // (two rows in flight need ~128 registers per thread: the 4-warp CTAs, and every instantiation whose
                     // launch bounds leave them -- MAXT * MINB <= 512)
-                    if (!first && wgc && (NT <= 128 || MAXT * MINB <= 512))
+                    // (WIDE: chunks of 2 frames, one row per combine warp)
+                    if (!WIDE && !first && wgc && (NT <= 128 || MAXT * MINB <= 512))
                         for (; r + r_inc < rows; r += 2 * r_inc) combine2(r, r + r_inc);
                     for (; r < rows; r += r_inc) {
                         RowData d0;
