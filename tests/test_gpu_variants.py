@@ -53,6 +53,8 @@ LIN_CASES = [
     (4, 300, 100, 60, False, "ctc_lin_kernel<8,1,0,256,2,MID>"),       # aligned rows of 100 classes
     (3, 300, 200, 60, False, "ctc_lin_kernel<8,1,0,256,2,MID>"),           # 128 < V <= 256: four helpers
     (3, 200, 1001, 30, False, "ctc_lin_kernel<8,1,0,256,2>"),             # wide rows that are not 16-byte aligned
+    (3, 120, 2048, 24, False, "ctc_lin_kernel<8,1,0,256,2,WIDE>"),        # more than 8 x 128 bit per lane: the looped passes
+    (3, 120, 260, 24, False, "ctc_lin_kernel<8,1,0,256,2,WIDE>"),         # just above the MID range
     (4, 120, 29, 20, False, "ctc_lin_kernel<8,1,0,128,4>"),            # characters + blank: V % 4 != 0, V < 60
     (8, 1000, 1024, 200, False, "ctc_lin_kernel<8,1,0,256,2,WIDE>"),        # C4 slice at full size
     (80, 120, 1024, 20, False, "ctc_lin_kernel<8,1,0,256,2,WIDE>"),         # C4's geometry: >= 75 utterances -> chunks of 2 frames
