@@ -371,6 +371,56 @@ def time_module_path(torch, r, steps):
     out["what"] = ("CTCLoss()(acts_cuda, targets_cpu_i32, in_lens_cpu, tgt_lens_cpu) + .item() + .backward() + "
                    "synchronize, host wall clock; torch_native_gpu: F.log_softmax + torch.nn.CTCLoss (cuDNN off) "
                    "on the same tensors")
+
+    # ---- from the network's own output [N,T,V]: what the rows around the loss call cost ----
+    # the reference: FC -> Hardtanh(-50, 50) -> LogSoftmax (network.py:370,375), transpose(0,1).contiguous() (trainer.py:418),
+    # loss, backward through all of it; here: the same with the B200 loss, and with layout + head folded into the kernel
+    z = acts.transpose(0, 1).contiguous().cuda().requires_grad_(True)        # raw FC outputs, batch-major
+    crit_bm = CTCLoss(blank=0, reduction="mean", batch_major=True)
+    crit_fused = CTCLoss(blank=0, reduction="mean", batch_major=True, clamp=(-50.0, 50.0))
+
+    def flow(head, transpose, loss_fn):
+        def fn():
+            z.grad = None
+            y = z
+            if head:
+                y = F.log_softmax(F.hardtanh(y, -50.0, 50.0), -1)
+            if transpose:
+                y = y.transpose(0, 1).contiguous()
+            loss = loss_fn(y)
+            v = loss.item()
+            loss.backward()
+            torch.cuda.synchronize()
+            return v
+        return fn
+
+    def torch_loss(y):
+        with torch.backends.cudnn.flags(enabled=False):
+            return ref(y, tg, il, tl)
+
+    flows = {
+        "torch_head_transpose_torch_ctc": flow(True, True, torch_loss),               # the reference today
+        "torch_head_transpose_b200": flow(True, True, lambda y: crit(y, tg, il, tl)),  # drop-in only
+        "transpose_b200": flow(False, True, lambda y: crit(y, tg, il, tl)),            # raw logits: the model drops its LogSoftmax
+        "batch_major_b200": flow(False, False, lambda y: crit_bm(y, tg, il, tl)),      # + transpose folded (raw logits)
+        "batch_major_fused_head_b200": flow(False, False, lambda y: crit_fused(y, tg, il, tl)),   # + Hardtanh folded
+    }
+    net = {}
+    for name, fn in flows.items():
+        try:
+            for _ in range(3):
+                v = fn()
+            t0 = time.perf_counter()
+            for _ in range(steps):
+                v = fn()
+            net[name] = {"ms_per_iter": (time.perf_counter() - t0) / steps * 1e3, "loss": v}
+        except Exception as e:  # noqa: BLE001
+            net[name] = {"error": f"{type(e).__name__}: {str(e)[:160]}"}
+    net["what"] = ("from raw FC outputs z[N,T,V] (leaf) to z.grad, .item() and synchronize included: "
+                   "torch_head = F.hardtanh(-50,50) + F.log_softmax in torch (network.py:370,375); transpose = "
+                   "transpose(0,1).contiguous() (trainer.py:418); 'transpose_b200' feeds raw logits (the fused log_softmax "
+                   "makes the model's own redundant); batch_major / fused_head fold the transpose / the Hardtanh into the kernel")
+    out["from_network_output"] = net
     return out
 
 
