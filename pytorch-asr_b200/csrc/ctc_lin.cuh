@@ -173,7 +173,17 @@ __device__ __forceinline__ void cp_async16_a(unsigned dst, const void* src) {
 __device__ __forceinline__ void cp_async16_zfill(void* smem_dst, const void* gmem_src, int bytes) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src), "r"(bytes) : "memory");
 }
+#ifndef CTC_LIN_PF
+#define CTC_LIN_PF 1      // FIX: how the logits of chunk ka + CTC_LIN_PFD reach L2 ahead of their cp.async: 0 = not at all,
+                          // 1 = prefetch.global.L2 of the two lines of a row, 2 = one cp.async.bulk.prefetch.L2 per row
+#endif
+#ifndef CTC_LIN_PFD
+#define CTC_LIN_PFD 6
+#endif
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+__device__ __forceinline__ void bulk_prefetch_l2(const void* p, unsigned bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
 __device__ __forceinline__ void mbar_expect_tx_a(unsigned bar, unsigned bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
@@ -2030,13 +2040,19 @@ ctc_lin_kernel(const PipeParams pp, int* __restrict__ flags) {
                     const unsigned dst = sbase + lay.y + (unsigned)iss_a.slot * YCH;
                     if (cp_row[0] < rows) cp_async16_a(dst + (unsigned)cp_dst[0] * 4u, src + cp_src[0]);
                     if (cp_row[1] < rows) cp_async16_a(dst + (unsigned)cp_dst[1] * 4u, src + cp_src[1]);
-                    const int kp = ka + 6;
-                    if (kp < nchh_i && (kp < n1h_i) == (ka < n1h_i)) {     // same half of the sweep: 24 steps further on
+#if CTC_LIN_PF
+                    const int kp = ka + CTC_LIN_PFD;
+                    if (kp < nchh_i && (kp < n1h_i) == (ka < n1h_i)) {     // same half of the sweep: 4 * CTC_LIN_PFD steps further on
                         int tp0, rowsp;
                         chunk_at(kp, tp0, rowsp);
-                        if (cp_row[0] < rowsp && pf_lane[0]) prefetch_l2(src + 24 * a_step + cp_src[0]);
-                        if (cp_row[1] < rowsp && pf_lane[1]) prefetch_l2(src + 24 * a_step + cp_src[1]);
+#if CTC_LIN_PF == 1
+                        if (cp_row[0] < rowsp && pf_lane[0]) prefetch_l2(src + 4 * CTC_LIN_PFD * a_step + cp_src[0]);
+                        if (cp_row[1] < rowsp && pf_lane[1]) prefetch_l2(src + 4 * CTC_LIN_PFD * a_step + cp_src[1]);
+#else
+                        if (lane < rowsp) bulk_prefetch_l2(src + (4 * CTC_LIN_PFD + lane) * a_step, 192u);
+#endif
                     }
+#endif
                 }
                 cp_async_commit();
             };
