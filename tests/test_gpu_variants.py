@@ -257,6 +257,17 @@ def test_persistent_queue_launch():
         assert np.array_equal(p2.grad.cpu().numpy(), grad[:, lo:hi])
 
 
+@pytest.mark.parametrize("V,variant,t_lo,t_hi,mode", [
+    (177, "ctc_lin_kernel<8,1,0,256,2,MID>", 1, 64, "plain"), (177, "ctc_lin_kernel<8,1,0,256,2,MID>", 1, 64, "ntv+clamp"),
+    (100, "ctc_lin_kernel<8,1,0,256,2,MID>", 30, 90, "plain"), (320, "ctc_lin_kernel<8,1,0,256,2,WIDE>", 1, 48, "plain"),
+    (320, "ctc_lin_kernel<8,1,0,256,2,WIDE>", 20, 60, "ntv+clamp")])
+def test_mid_and_wide_instantiations_every_length(V, variant, t_lo, t_hi, mode):
+    """The MID / WIDE instantiations (compile-time CTA shape, their own softmax / gradient / copy paths) on one
+    utterance of every length in [t_lo, t_hi], empty targets and adjacent repeats included: every count of chunks in
+    both halves, short last chunks, T_b of a few frames; rows that are not 16-byte aligned in both layouts (V = 177)."""
+    _every_length_case(V, variant, t_lo, t_hi, mode)
+
+
 @pytest.mark.parametrize("t_lo,t_hi,mode", [(1, 64, "plain"), (1, 64, "ntv+clamp"), (60, 200, "plain"),
                                             (60, 200, "ntv+clamp"), (3, 40, "peaky")])
 def test_headline_instantiation_every_length(t_lo, t_hi, mode):
@@ -265,8 +276,12 @@ def test_headline_instantiation_every_length(t_lo, t_hi, mode):
     utterance of EVERY length T_b in [t_lo, t_hi] (so that every count of first-half and second-half chunks, with
     and without a short last chunk, occurs), targets from empty to the longest feasible, against the fp64 oracle
     at the flat bounds; rows t >= T_b exact zeros; no utterance may need the fallback."""
-    g = torch.Generator().manual_seed(1000 + t_lo + t_hi)
-    V, T = 48, t_hi
+    _every_length_case(48, "ctc_lin_kernel<8,1,80,128,4,FIX>", t_lo, t_hi, mode)
+
+
+def _every_length_case(V, variant, t_lo, t_hi, mode):
+    g = torch.Generator().manual_seed(1000 + t_lo + t_hi + V)
+    T = t_hi
     il = torch.arange(t_hi, t_lo - 1, -1, dtype=torch.int32)        # sorted, longest first (dataloader.py:53)
     B = il.numel()
     tl = torch.minimum((torch.rand(B, generator=g) * 0.55 * il).to(torch.int32), il // 2).to(torch.int32)
@@ -279,7 +294,7 @@ def test_headline_instantiation_every_length(t_lo, t_hi, mode):
         acts = acts * 4.0
         acts[:, :, 0] += 6.0
     geo = cabi.geometry(T, B, V, int(tl.max()))
-    assert geo["variant_name"] == "ctc_lin_kernel<8,1,80,128,4,FIX>", geo
+    assert geo["variant_name"] == variant, geo
     if mode == "ntv+clamp":
         x, lo, hi = acts * 1.5, -3.0, 3.0
         prob = cabi.DeviceProblem(x.transpose(0, 1).contiguous(), tg, il, tl, reduction="sum", batch_major=True,
