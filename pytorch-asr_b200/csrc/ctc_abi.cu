@@ -171,7 +171,12 @@ bool pick_lin(int T, int V, int S_max, int n_utt, Geometry* g) {
     // for wide rows that are not 16-byte aligned (the reference's own V = 177, params.py:27: 0.82 ms with one
     // helper and the looped passes, 0.26 ms with four and the MID instantiation on B = 64, T = 750)
     int H = R == 1 ? ((V > 64 || (!al && V > 60)) ? 4 : 1) : (V > 256 ? 4 : 2);
-    if (env().helpers == 1 || env().helpers == 2 || env().helpers == 4) H = env().helpers;   // developer knob
+    // the MID vocabularies (60 < V <= 256) in a launch that leaves every CTA an SM of its own -- at most 74 utterances: the
+    // reference trains with batches of 32 / 64 (deepspeech_ctc/train.py:75-100) at V = 177 -- get EIGHT helper warps,
+    // a warp per frame of a chunk: with 7 warps on an SM the helpers' dependent chains bound every iteration
+    // (B = 64, T = 750, V = 177: SOFT 2177 / GRAD 2827 busy cycles per chunk against REC 1181 / COMB 1665)
+    if (R == 1 && H == 4 && V <= 256 && 2 * std::max(n_utt, 1) <= kNumSmsHint) H = 8;
+    if (env().helpers == 1 || env().helpers == 2 || env().helpers == 4 || env().helpers == 8) H = env().helpers;   // developer knob
     const int NC = R <= 4 ? 2 : 1;   // two combine groups while the CTA stays within 512 threads
     const int NT = 32 * ((1 + NC) * R + H);
     if (NT > 1024) return false;

@@ -173,6 +173,9 @@ __device__ __forceinline__ void cp_async16_a(unsigned dst, const void* src) {
 __device__ __forceinline__ void cp_async16_zfill(void* smem_dst, const void* gmem_src, int bytes) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src), "r"(bytes) : "memory");
 }
+__device__ __forceinline__ void cp_async16_zfill_a(unsigned dst, const void* gmem_src, int bytes) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(gmem_src), "r"(bytes) : "memory");
+}
 #ifndef CTC_LIN_PF
 #define CTC_LIN_PF 1      // FIX: how the logits of chunk ka + CTC_LIN_PFD reach L2 ahead of their cp.async: 0 = not at all,
                           // 1 = prefetch.global.L2 of the two lines of a row, 2 = one cp.async.bulk.prefetch.L2 per row
@@ -322,8 +325,13 @@ ctc_lin_kernel(const PipeParams pp, int* __restrict__ flags) {
     // threads per CTA: a compile-time constant wherever the instantiation fixes the warp roles (what only other
     // CTA shapes need -- e.g. the two-rows-in-flight combine pass of the 4-warp CTAs -- is then compiled out)
     // (measured and rejected: the same for the several-recursion-warp instantiations -- C3 1.186 -> 1.220 ms)
-    const int NT = (FIX || (RC == 1 && MAXT == 128)) ? 128 : ((WIDE || MID) ? 224 : blockDim.x), NW = NT >> 5;
-    const int R = RC > 0 ? RC : pp.R, H = FIX ? 1 : ((WIDE || MID) ? 4 : pp.H), NP = RC > 0 ? 32 * P * RC : pp.NP;
+    // MID with launch bounds of 384 threads: EIGHT helper warps (a warp per frame of a chunk, 32 lanes per frame), for
+    // launches that leave every CTA an SM of its own (at most 74 utterances: the reference's batches of 32 / 64,
+    // deepspeech_ctc/train.py:75-100): with one CTA per SM the helpers' chains bound the iteration, not their number
+    constexpr bool MID8 = MID && MAXT == 384;
+    constexpr int MG = MID8 ? 32 : 16;      // MID: lanes per frame in the softmax / gradient passes
+    const int NT = (FIX || (RC == 1 && MAXT == 128)) ? 128 : (MID8 ? 352 : ((WIDE || MID) ? 224 : blockDim.x)), NW = NT >> 5;
+    const int R = RC > 0 ? RC : pp.R, H = FIX ? 1 : (MID8 ? 8 : ((WIDE || MID) ? 4 : pp.H)), NP = RC > 0 ? 32 * P * RC : pp.NP;
     // loop invariants the compiler would otherwise re-derive inside the role loops at the register cap
     // (S2R SR_TID / SR_CgaCtaId cost ~50 cycles each): pinned in registers in the FIX instantiation
     int lane_pin = threadIdx.x & 31;
@@ -1375,16 +1383,20 @@ ctc_lin_kernel(const PipeParams pp, int* __restrict__ flags) {
                 // belong to the previous row of the tensor, the tail of the last segment is zero-filled).  At most
                 // 65 segments per row (V <= 256): three predicated copies per lane and row, straight-line.
 #pragma unroll
-                for (int rr = 0; rr < 2; ++rr) {      // MID: this warp's two frames of the chunk
+                // (shared memory by explicit 32-bit addresses off the pinned base: a generic pointer costs an
+                // S2R SR_CgaCtaId + LEA per use in a kernel with cluster dimensions)
+                const unsigned dst_a = sbase + (unsigned)lay.y + (unsigned)(slot_a * TC * Vs + 4 * lane) * 4u;
+#pragma unroll
+                for (int rr = 0; rr < (MID8 ? 1 : 2); ++rr) {      // MID: this warp's two frames of the chunk (MID8: its frame)
                     const int r = r_lo + rr;
                     if (r < rows) {
                         const int mis = (mis0 + (tt0 + r) * mis_step) & 3;
                         const float* s16 = src + r * a_inc - mis + 4 * lane;      // 16-byte aligned
-                        float* d16 = dst + r * Vs + 4 * lane;
+                        const unsigned d16 = dst_a + (unsigned)(r * Vs) * 4u;
                         const int left = (mis + V) * 4 - 16 * lane;             // bytes of the row from my first segment on
 #pragma unroll
                         for (int q = 0; q < 3; ++q)
-                            if (left - 512 * q > 0) cp_async16_zfill(d16 + 128 * q, s16 + 128 * q, min(16, left - 512 * q));
+                            if (left - 512 * q > 0) cp_async16_zfill_a(d16 + 512u * q, s16 + 128 * q, min(16, left - 512 * q));
                     }
                 }
             } else if (!al) {
@@ -1478,8 +1490,10 @@ ctc_lin_kernel(const PipeParams pp, int* __restrict__ flags) {
                 // that is not 16-byte aligned in HBM sits `mis` floats into its ring row and is moved to the front here.
                 auto body = [&](auto NVC) {
                     constexpr int NV = decltype(NVC)::value;
-                    const float* rin = row + (shifted ? row_mis(tt0 + min(f, rows - 1)) : 0) + gl;
-                    const int nv = (V - gl + 15) >> 4;      // classes this lane holds
+                    // (explicit 32-bit shared-memory addresses, as in the FIX loops)
+                    const unsigned ra = sbase + (unsigned)lay.y + (unsigned)((int)(base - s_y) + min(f, rows - 1) * Vs + gl) * 4u;
+                    const unsigned rin = ra + (unsigned)(shifted ? row_mis(tt0 + min(f, rows - 1)) : 0) * 4u;
+                    const int nv = (V - gl + MG - 1) / MG;      // classes this lane holds
                     float x[NV];
                     float m = -CUDART_INF_F;
                     unsigned mk = 0u;
@@ -1487,14 +1501,14 @@ ctc_lin_kernel(const PipeParams pp, int* __restrict__ flags) {
                     for (int j = 0; j < NV; ++j) {
                         x[j] = -CUDART_INF_F;
                         if (j < nv) {
-                            const float raw = rin[16 * j];
+                            const float raw = lds32(rin + (unsigned)(MG * 4 * j));
                             mk |= (clq.cmask(raw) ? 1u : 0u) << j;
                             x[j] = clq.cin(raw);
                         }
                         m = fmaxf(m, x[j]);
                     }
 #pragma unroll
-                    for (int o = 8; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+                    for (int o = MG / 2; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
                     const float mb = m * kLog2e;
                     float z = 0.f;
 #pragma unroll
@@ -1503,23 +1517,24 @@ ctc_lin_kernel(const PipeParams pp, int* __restrict__ flags) {
                         z += x[j];
                     }
 #pragma unroll
-                    for (int o = 8; o > 0; o >>= 1) z += __shfl_xor_sync(0xffffffffu, z, o);
-                    const float rs = 1.0f / z;
+                    for (int o = MG / 2; o > 0; o >>= 1) z += __shfl_xor_sync(0xffffffffu, z, o);
+                    float rs;
+                    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rs) : "f"(z));
+                    rs = rs * (2.0f - z * rs);          // one Newton step: full fp32 accuracy (1 <= z <= V)
                     __syncwarp();      // every lane has read its raw values before the row is overwritten in place
                     if (act) {
-                        float* rout = row + gl;
 #pragma unroll
                         for (int j = 0; j < NV; ++j) {
                             if (j < nv) {
                                 const float y = x[j] * rs;
-                                rout[16 * j] = (mk >> j) & 1u ? -y : y;
+                                sts32(ra + (unsigned)(MG * 4 * j), (mk >> j) & 1u ? -y : y);
                             }
                         }
-                        if (gl < Vs - V) row[V + gl] = 0.f;   // slot V (and the padding behind it): what padding pairs gather
+                        if (gl < Vs - V) sts32(ra + (unsigned)V * 4u, 0.f);   // slot V (and the padding behind it): what padding pairs gather
                     }
                 };
-                if (V <= 192) body(std::integral_constant<int, 12>{});
-                else body(std::integral_constant<int, 16>{});
+                if (V <= 192) body(std::integral_constant<int, 192 / MG>{});
+                else body(std::integral_constant<int, 256 / MG>{});
                 return;
             }
             if (!WIDE && !al) {      // rows that are not 16-byte aligned in HBM (V % 4 != 0): scalar passes
@@ -1873,10 +1888,11 @@ ctc_lin_kernel(const PipeParams pp, int* __restrict__ flags) {
                 auto body = [&](auto NVC) {
                     constexpr int NV = decltype(NVC)::value;
                     float* g1 = reinterpret_cast<float*>(g2) + gl;
-                    const float* y1 = reinterpret_cast<const float*>(y2) + gl;
-                    unsigned* o1 = reinterpret_cast<unsigned*>(orow) + gl;
-                    const int nv = (V - gl + 15) >> 4;
-                    const int jb = ((blank - gl) & 15) == 0 ? (blank - gl) >> 4 : -1;   // which of my classes is the blank
+                    // (explicit 32-bit shared-memory addresses, as in the FIX loops)
+                    const unsigned ya = sbase + (unsigned)lay.y + (unsigned)((int)(ybase - s_y) + fr * Vs + gl) * 4u;
+                    const unsigned oa = sbase + (unsigned)lay.occ + (unsigned)((int)(obase - s_occ) + fr * ER + gl) * 4u;
+                    const int nv = (V - gl + MG - 1) / MG;
+                    const int jb = ((blank - gl) & (MG - 1)) == 0 ? (blank - gl) / MG : -1;   // which of my classes is the blank
                     float o[NV], y[NV];
                     float tsum = 0.f;
 #pragma unroll
@@ -1884,21 +1900,21 @@ ctc_lin_kernel(const PipeParams pp, int* __restrict__ flags) {
                         o[j] = 0.f;
                         y[j] = 0.f;
                         if (j < nv) {
-                            const unsigned xq = o1[16 * j];
-                            y[j] = y1[16 * j];
-                            if (act) o1[16 * j] = 0u;
+                            const unsigned xq = (unsigned)lds32i(oa + (unsigned)(MG * 4 * j));
+                            y[j] = lds32(ya + (unsigned)(MG * 4 * j));
+                            if (act) sts32i(oa + (unsigned)(MG * 4 * j), 0);
                             o[j] = __uint2float_rn(xq) * (1.0f / kQ31);
                             tsum += o[j];
                         }
                     }
 #pragma unroll
-                    for (int sft = 8; sft > 0; sft >>= 1) tsum += __shfl_xor_sync(0xffffffffu, tsum, sft);   // (bs is reduced already)
+                    for (int sft = MG / 2; sft > 0; sft >>= 1) tsum += __shfl_xor_sync(0xffffffffu, tsum, sft);   // (bs is reduced already)
                     if (act) {
 #pragma unroll
                         for (int j = 0; j < NV; ++j) {
                             if (j < nv) {
                                 const float ov = o[j] + (j == jb ? bs : 0.f);
-                                g1[16 * j] = (CLAMPED && __float_as_int(y[j]) < 0) ? 0.f : gscale * (y[j] - ov);
+                                g1[MG * j] = (CLAMPED && __float_as_int(y[j]) < 0) ? 0.f : gscale * (y[j] - ov);
                             }
                         }
                         if (!(fabsf(tsum + bs - 1.0f) <= kMassTol)) s_flag[0] = 1;   // NaN-safe
@@ -1907,8 +1923,8 @@ ctc_lin_kernel(const PipeParams pp, int* __restrict__ flags) {
 #endif
                     }
                 };
-                if (V <= 192) body(std::integral_constant<int, 12>{});
-                else body(std::integral_constant<int, 16>{});
+                if (V <= 192) body(std::integral_constant<int, 192 / MG>{});
+                else body(std::integral_constant<int, 256 / MG>{});
                 return;
             }
             if (!WIDE && !al) {      // gradient rows that are not 16-byte aligned in HBM: scalar loads / stores
