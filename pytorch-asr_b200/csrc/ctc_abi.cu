@@ -178,7 +178,7 @@ bool pick_lin(int T, int V, int S_max, int n_utt, Geometry* g) {
     if (R == 1 && H == 4 && V <= 256 && 2 * std::max(n_utt, 1) <= kNumSmsHint) H = 8;
     if (env().helpers == 1 || env().helpers == 2 || env().helpers == 4 || env().helpers == 8) H = env().helpers;   // developer knob
     const int NC = R <= 4 ? 2 : 1;   // two combine groups while the CTA stays within 512 threads
-    const int NT = 32 * ((1 + NC) * R + H);
+    const int NT = 32 * ((1 + NC) * R + H + (H == 8 ? 4 : 0));   // (eight helpers come with four copy warps: ctc_lin.cuh, MIDC)
     if (NT > 1024) return false;
     const int NP = 32 * P * R;
     const int RS = lin_row_stride_host(NP, P);

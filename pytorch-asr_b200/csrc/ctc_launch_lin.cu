@@ -25,8 +25,8 @@ enum LinVariant {
     kLinR1WideAl,       // <8,1,0,256,2,WIDE>  V > 256 in 16-byte aligned rows (C4); kLinR1Wide keeps the rows that are not
     kLinFixQueue,       // <8,1,80,128,4,FIX,QUEUE>  the headline shape class as a persistent launch (not reported as a
                         // variant of its own: same code, wrapped in the loop over the utterance queue)
-    kLinR1Mid8,         // <8,1,0,384,1,MID>   the MID vocabularies in launches of at most one CTA per SM (the reference's
-                        // batches of 32 / 64 at V = 177): eight helper warps, a warp per frame
+    kLinR1Mid8,         // <8,1,0,512,1,MID>   the MID vocabularies in launches of at most one CTA per SM (the reference's
+                        // batches of 32 / 64 at V = 177): eight helper warps, a warp per frame, and four copy warps
     kLinCount
 };
 
@@ -35,7 +35,7 @@ const char* const kLinNames[kLinCount] = {
     "ctc_lin_kernel<8,1,0,256,2>",      "ctc_lin_kernel<8,2,80,512,1>", "ctc_lin_kernel<8,4,80,512,1>",
     "ctc_lin_kernel<8,0,0,256,2>",      "ctc_lin_kernel<8,0,0,512,1>",  "ctc_lin_kernel<8,0,0,1024,1>",
     "ctc_lin_kernel<8,1,0,256,2,MID>", "ctc_lin_kernel<8,1,0,256,2,WIDE>", "ctc_lin_kernel<8,1,80,128,4,FIX,QUEUE>",
-    "ctc_lin_kernel<8,1,0,384,1,MID>",
+    "ctc_lin_kernel<8,1,0,512,1,MID>",
 };
 
 using LinKernel = void (*)(const PipeParams, int*);
@@ -54,7 +54,7 @@ LinKernel lin_kernel(int id) {
         case kLinR1Mid: return ctc_lin_kernel<8, 1, 0, 256, 2, false, false, true>;
         case kLinR1WideAl: return ctc_lin_kernel<8, 1, 0, 256, 2, false, false, false, true>;
         case kLinFixQueue: return ctc_lin_kernel<8, 1, 80, 128, 4, true, true>;
-        case kLinR1Mid8: return ctc_lin_kernel<8, 1, 0, 384, 1, false, false, true>;
+        case kLinR1Mid8: return ctc_lin_kernel<8, 1, 0, 512, 1, false, false, true>;
     }
     return nullptr;
 }
@@ -70,8 +70,8 @@ int lin_variant(const Geometry& g, int V) {
             return (g.lH == 1 && g.lD == 2 && V == 48 && !env().nofix) ? kLinFix : kLinR1Y80;
         if (g.lYS != 0) return -1;
         if (g.lNT <= 128) return kLinR1;
-        // eight helpers, 352 threads: the MID vocabularies when every CTA has an SM of its own (pick_lin)
-        if (g.lNT == 352) return (g.lH == 8 && g.lD == 2 && V > 60 && V <= 256 && g.lchunk == 4) ? kLinR1Mid8 : -1;
+        // eight helpers + four copy warps, 480 threads: the MID vocabularies when every CTA has an SM of its own (pick_lin)
+        if (g.lNT == 480) return (g.lH == 8 && g.lD == 2 && V > 60 && V <= 256 && g.lchunk == 4) ? kLinR1Mid8 : -1;
         if (g.lNT > 256) return -1;
         // (the WIDE / MID instantiations have their CTA shape -- four helpers, 224 threads, WIDE: chunks of 2 frames --
         // as compile-time constants; any other choice of the geometry heuristics runs the general instantiation)

@@ -328,9 +328,13 @@ ctc_lin_kernel(const PipeParams pp, int* __restrict__ flags) {
     // MID with launch bounds of 384 threads: EIGHT helper warps (a warp per frame of a chunk, 32 lanes per frame), for
     // launches that leave every CTA an SM of its own (at most 74 utterances: the reference's batches of 32 / 64,
     // deepspeech_ctc/train.py:75-100): with one CTA per SM the helpers' chains bound the iteration, not their number
-    constexpr bool MID8 = MID && MAXT == 384;
+    // MIDC (launch bounds of 512 threads): plus FOUR copy warps that do nothing but request the logits rows (a warp per
+    // frame), wait for them and publish them through the chunk barrier -- copy + wait were 730 of a softmax warp's 1760
+    // busy cycles per chunk, and the softmax warps bound the iteration
+    constexpr bool MIDC = MID && MAXT == 512;
+    constexpr bool MID8 = MID && (MAXT == 384 || MIDC);
     constexpr int MG = MID8 ? 32 : 16;      // MID: lanes per frame in the softmax / gradient passes
-    const int NT = (FIX || (RC == 1 && MAXT == 128)) ? 128 : (MID8 ? 352 : ((WIDE || MID) ? 224 : blockDim.x)), NW = NT >> 5;
+    const int NT = (FIX || (RC == 1 && MAXT == 128)) ? 128 : (MIDC ? 480 : (MID8 ? 352 : ((WIDE || MID) ? 224 : blockDim.x))), NW = NT >> 5;
     const int R = RC > 0 ? RC : pp.R, H = FIX ? 1 : (MID8 ? 8 : ((WIDE || MID) ? 4 : pp.H)), NP = RC > 0 ? 32 * P * RC : pp.NP;
     // loop invariants the compiler would otherwise re-derive inside the role loops at the register cap
     // (S2R SR_TID / SR_CgaCtaId cost ~50 cycles each): pinned in registers in the FIX instantiation
@@ -428,8 +432,9 @@ ctc_lin_kernel(const PipeParams pp, int* __restrict__ flags) {
 
     // helper roles: SOFT warps [0, nA), GRAD warps [nA, H); a single helper does both
     const int nA = H >= 2 ? H / 2 : 1, nB = H >= 2 ? H - nA : 1;
-    const bool isA = hw >= 0 && (H == 1 || hw < nA), isB = hw >= 0 && (H == 1 || hw >= nA);
-    const int ha = hw, hb = H == 1 ? 0 : hw - nA;
+    const bool is_copy = MIDC && hw >= H;     // copy warp hw - H requests frame hw - H of every chunk
+    const bool isA = hw >= 0 && (H == 1 || hw < nA), isB = hw >= 0 && (H == 1 || hw >= nA) && !is_copy;
+    const int ha = is_copy ? hw - H : hw, hb = H == 1 ? 0 : hw - nA;
     // wide vocabulary: logits rows come in by TMA bulk copies (one per row) instead of cp.async
     const bool wide_rows = (CTC_LIN_TMA_Y || WIDE) ? true : (YS == 0 && nA > 1 && V > 256 && al);
 
@@ -1978,7 +1983,7 @@ ctc_lin_kernel(const PipeParams pp, int* __restrict__ flags) {
         // chunk it; GRAD: gradient rows of chunk it-3 (REC runs chunk it-1, COMB chunk it-2).
         // (WIDE: the logits rows are requested by the first combine warp, which has the most slack -- the first
         // softmax warp spent 536 of its 2756 cycles per chunk issuing two TMA copies)
-        const bool iss_acts = !WIDE && isA && (ha == 0 || own_rows);
+        const bool iss_acts = !WIDE && ((isA && (ha == 0 || own_rows)) || is_copy);
         const bool do_sm = isA && ha * FA < TC, do_gr = isB && hb * FB < TC && want_grad;
         Ring iss_a(NL), sm_a(NL), gr_a(NL);
         int gr_o = 0;
@@ -1986,8 +1991,11 @@ ctc_lin_kernel(const PipeParams pp, int* __restrict__ flags) {
         asm volatile("" : "+r"(n1h_i), "+r"(nchh_i));
         if (iss_acts) {
             for (int k = 0; k <= kLinYDist; ++k) {    // prologue: logits of chunks 0..kLinYDist
-                if (k < nch) issue_logits(k, iss_a.slot);
-                else if (cp_groups) cp_async_commit();
+                // (MIDC: a softmax warp copies its frame of chunk 0 itself -- no CTA barrier lies between the prologue
+                // and its first softmax -- and the copy warps start with chunk 1)
+                const bool mine = !MIDC || (is_copy ? k > 0 : k == 0);
+                if (k < nch && mine) issue_logits(k, iss_a.slot);
+                else if (cp_groups && mine) cp_async_commit();
                 iss_a.advance();
             }
         }
@@ -1995,7 +2003,7 @@ ctc_lin_kernel(const PipeParams pp, int* __restrict__ flags) {
             LPROF_BEGIN();
             {
                 const int ka = it + kLinYDist + 1;
-                if (iss_acts) {
+                if (iss_acts && (!MIDC || is_copy)) {
                     if (ka < nch) issue_logits(ka, iss_a.slot);
                     else if (cp_groups) cp_async_commit();   // keep one group per iteration
                 }
@@ -2017,7 +2025,8 @@ ctc_lin_kernel(const PipeParams pp, int* __restrict__ flags) {
             if (do_sm && it < nchh_i) {               // softmax of chunk `it`
                 int tt0, rows;
                 chunk_at(it, tt0, rows);
-                if (cp_groups) { cp_async_wait<kLinYDist + 1>(); __syncwarp(); }
+                if (MIDC) { if (it == 0) { cp_async_wait<0>(); __syncwarp(); } }   // (later chunks: the copy warps waited)
+                else if (cp_groups) { cp_async_wait<kLinYDist + 1>(); __syncwarp(); }
                 else mbar_wait(bar_acts + sm_a.slot, sm_a.parity);
                 LPROF_SEC(12);
                 if (clp.on) softmax_chunk(std::true_type{}, s_y + (size_t)sm_a.slot * TC * Vs, rows, tt0);
@@ -2025,6 +2034,8 @@ ctc_lin_kernel(const PipeParams pp, int* __restrict__ flags) {
             }
             LPROF_SEC(13);
             sm_a.advance();
+            // MIDC: the rows of chunk it + 1 have landed before this warp arrives at the barrier that hands them over
+            if (is_copy) cp_async_wait<kLinYDist>();
             LPROF_END(it >= n1 + 1);
             __syncthreads();
             if (it == n1) {

@@ -50,12 +50,12 @@ LIN_CASES = [
     (4, 160, 64, 30, False, "ctc_lin_kernel<8,1,0,128,4>"),            # 60 < V <= 64: one helper, a frame's row in registers
     # 64 < V <= 256 (and 60 < V with rows that are not 16-byte aligned).  At most 74 utterances -- every CTA has an SM of
     # its own; the reference's batches of 32 / 64 (deepspeech_ctc/train.py:75-100) -- run EIGHT helper warps, a warp per frame:
-    (4, 160, 128, 30, False, "ctc_lin_kernel<8,1,0,384,1,MID>"),
-    (4, 750, 177, 100, False, "ctc_lin_kernel<8,1,0,384,1,MID>"),      # the reference's real label inventory (params.py:27)
-    (64, 200, 177, 40, False, "ctc_lin_kernel<8,1,0,384,1,MID>"),      # ... at its real batch size
-    (4, 300, 100, 60, False, "ctc_lin_kernel<8,1,0,384,1,MID>"),       # aligned rows of 100 classes
-    (3, 300, 200, 60, False, "ctc_lin_kernel<8,1,0,384,1,MID>"),       # 192 < V <= 256: 8 classes per lane
-    (3, 200, 255, 40, False, "ctc_lin_kernel<8,1,0,384,1,MID>"),
+    (4, 160, 128, 30, False, "ctc_lin_kernel<8,1,0,512,1,MID>"),
+    (4, 750, 177, 100, False, "ctc_lin_kernel<8,1,0,512,1,MID>"),      # the reference's real label inventory (params.py:27)
+    (64, 200, 177, 40, False, "ctc_lin_kernel<8,1,0,512,1,MID>"),      # ... at its real batch size
+    (4, 300, 100, 60, False, "ctc_lin_kernel<8,1,0,512,1,MID>"),       # aligned rows of 100 classes
+    (3, 300, 200, 60, False, "ctc_lin_kernel<8,1,0,512,1,MID>"),       # 192 < V <= 256: 8 classes per lane
+    (3, 200, 255, 40, False, "ctc_lin_kernel<8,1,0,512,1,MID>"),
     # more utterances than SM pairs: four helper warps, two CTAs per SM
     (76, 160, 128, 30, False, "ctc_lin_kernel<8,1,0,256,2,MID>"),
     (76, 300, 177, 60, False, "ctc_lin_kernel<8,1,0,256,2,MID>"),
@@ -267,8 +267,8 @@ def test_persistent_queue_launch():
 
 
 @pytest.mark.parametrize("V,variant,t_lo,t_hi,mode", [
-    (177, "ctc_lin_kernel<8,1,0,384,1,MID>", 1, 64, "plain"), (177, "ctc_lin_kernel<8,1,0,384,1,MID>", 1, 64, "ntv+clamp"),
-    (100, "ctc_lin_kernel<8,1,0,384,1,MID>", 30, 90, "plain"), (200, "ctc_lin_kernel<8,1,0,384,1,MID>", 1, 40, "ntv+clamp"),
+    (177, "ctc_lin_kernel<8,1,0,512,1,MID>", 1, 64, "plain"), (177, "ctc_lin_kernel<8,1,0,512,1,MID>", 1, 64, "ntv+clamp"),
+    (100, "ctc_lin_kernel<8,1,0,512,1,MID>", 30, 90, "plain"), (200, "ctc_lin_kernel<8,1,0,512,1,MID>", 1, 40, "ntv+clamp"),
     (177, "ctc_lin_kernel<8,1,0,256,2,MID>", 1, 80, "plain"), (177, "ctc_lin_kernel<8,1,0,256,2,MID>", 1, 80, "ntv+clamp"),
     (100, "ctc_lin_kernel<8,1,0,256,2,MID>", 20, 100, "plain"), (320, "ctc_lin_kernel<8,1,0,256,2,WIDE>", 1, 48, "plain"),
     (320, "ctc_lin_kernel<8,1,0,256,2,WIDE>", 20, 60, "ntv+clamp")])
