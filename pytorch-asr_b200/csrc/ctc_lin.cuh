@@ -334,6 +334,10 @@ ctc_lin_kernel(const PipeParams pp, int* __restrict__ flags) {
     constexpr bool MIDC = MID && MAXT == 512;
     constexpr bool MID8 = MID && (MAXT == 384 || MIDC);
     constexpr int MG = MID8 ? 32 : 16;      // MID: lanes per frame in the softmax / gradient passes
+    // the steady-state loops of the recursion and combine warps (written for FIX) also serve MID8: the same CTA shape on
+    // their side (one recursion warp, two combine groups, chunks of 4 frames); only the row strides of the emission ring
+    // and of the occupancy rows are run-time values there (FIX: 80 and 112 floats, immediates)
+    constexpr bool RCL = FIX || MID8;
     const int NT = (FIX || (RC == 1 && MAXT == 128)) ? 128 : (MIDC ? 480 : (MID8 ? 352 : ((WIDE || MID) ? 224 : blockDim.x))), NW = NT >> 5;
     const int R = RC > 0 ? RC : pp.R, H = FIX ? 1 : (MID8 ? 8 : ((WIDE || MID) ? 4 : pp.H)), NP = RC > 0 ? 32 * P * RC : pp.NP;
     // loop invariants the compiler would otherwise re-derive inside the role loops at the register cap
@@ -742,14 +746,15 @@ ctc_lin_kernel(const PipeParams pp, int* __restrict__ flags) {
             }
         };
         int it = 0;
-        if constexpr (FIX) {
+        if constexpr (RCL) {
             // The headline shape class with a gradient, full chunks, in loops of their own.  Emissions of step
             // r + 1 are loaded BEFORE the row of step r is stored (loads cannot be hoisted over shared-memory
             // stores), and the first half publishes its pre-emission rows in the shared-memory ring as well: the
             // combine warps, idle until the phase break, copy them to HBM (a recursion warp that stores to HBM
             // itself waits for every store to have read its registers before it may overwrite them).
             if (wg) {
-                constexpr unsigned RSB = 544u * 4u, YSB = 80u * 4u, YCH = 4u * YSB;
+                constexpr unsigned RSB = 544u * 4u;
+                const unsigned YSB = FIX ? 80u * 4u : (unsigned)Vs * 4u, YCH = 4u * YSB;
                 unsigned labo[P];
 #pragma unroll
                 for (int q = 0; q < P; ++q) labo[q] = (unsigned)lab[q] * 4u;
@@ -883,7 +888,7 @@ ctc_lin_kernel(const PipeParams pp, int* __restrict__ flags) {
         const unsigned fx_e = 2048u + (hasX ? (unsigned)X * 4u : 0u) - fx_x;    // its exponent, from its blank cells
         const unsigned fx_ar = (unsigned)cg * (544u * 4u) + (unsigned)lane * 16u;  // my cells in REC's row cg
         const unsigned fx_o = 2048u + (unsigned)lane * 4u - (unsigned)lane * 16u;  // my exponent, from my blank cells
-        const unsigned fx_bl = (80u + (unsigned)lane) * 4u;                      // my blank partial sum in an occupancy row
+        const unsigned fx_bl = ((FIX ? 80u : (unsigned)VO) + (unsigned)lane) * 4u;   // my blank partial sum in an occupancy row
         int E0 = 0;                      // integer part of log2 P(labels | logits)
         float rz = 0.f;                  // 1 / mantissa sum: occupancy = a * p~ * 2^(off+o-E0) * rz
         const bool iss_part = cg == 0 && wc == 0;   // this warp also requests the partner's rows (TMA)
@@ -1185,12 +1190,12 @@ ctc_lin_kernel(const PipeParams pp, int* __restrict__ flags) {
                 }
         };
         int it = 0;
-        if constexpr (FIX) {
+        if constexpr (RCL) {
             // Steady state of the headline shape class in a loop of its own: chunks k = it - 2 in (n1, nch - 1), i.e.
             // neither the first combined chunk nor the (possibly short) last one; full chunks of 4 rows, two
             // combine groups (this warp takes rows cg and cg + 2).  Every shared-memory address is an immediate
             // offset from a running 32-bit base; what only the general path needs is not live in here.
-            static_assert(!FIX || kLinPDist == 2, "the steady-state loop requests the partner rows two chunks ahead");
+            static_assert(!RCL || kLinPDist == 2, "the steady-state loop requests the partner rows two chunks ahead");
             const int it_fast_end = wgc ? nch_i + 1 : 0;
             if (wgc) {
                 // First half: the recursion warp publishes the pre-emission rows of chunk it - 1 in the
@@ -1245,7 +1250,8 @@ ctc_lin_kernel(const PipeParams pp, int* __restrict__ flags) {
                     }
                     mbar_wait_a(bar0 + 8u * (unsigned)ring_part.slot, ring_part.parity);   // TMA data landed
                     {
-                        constexpr unsigned RSB = 544u * 4u, PLB = 256u * 4u, HSB = 128u * 4u, ERB = 112u * 4u;
+                        constexpr unsigned RSB = 544u * 4u, PLB = 256u * 4u, HSB = 128u * 4u;
+                        const unsigned ERB = FIX ? 112u * 4u : (unsigned)OW * 4u;
                         const unsigned stb = sbase + lay.stage + (unsigned)ring_part.slot * (4u * RSB);
                         const unsigned stA = stb + fx_stA, stB = stb + fx_stB;
                         const unsigned arA = sbase + lay.a + (unsigned)a_buf * (4u * RSB) + fx_ar, arB = arA + 2u * RSB;
