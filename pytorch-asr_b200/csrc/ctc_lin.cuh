@@ -106,6 +106,9 @@ constexpr float kQ31 = 2147483648.0f;   // label occupancies are accumulated as 
 #ifndef CTC_LIN_PD
 #define CTC_LIN_PD 2
 #endif
+#ifndef CTC_LIN_REDUX
+#define CTC_LIN_REDUX 1    // MID with a warp per frame: row maximum by redux.sync.max.f32
+#endif
 #ifndef CTC_LIN_P1RING
 #define CTC_LIN_P1RING 1  // FIX, first half: 1 = rows go through the shared-memory ring and the combine warps copy them to HBM;
                           // 0 = the recursion warp stores them to HBM itself
@@ -172,6 +175,16 @@ __device__ __forceinline__ void cp_async16_a(unsigned dst, const void* src) {
 // 16-byte cp.async of which only the first `bytes` (<= 16) are read from global memory; the rest is zero-filled
 __device__ __forceinline__ void cp_async16_zfill(void* smem_dst, const void* gmem_src, int bytes) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src), "r"(bytes) : "memory");
+}
+// predicated stores (MID passes: a lane's last class may lie beyond V; a branch per element would diverge)
+__device__ __forceinline__ void sts32_if(unsigned a, float v, bool on) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.s32 p, %2, 0;\n\t@p st.shared.f32 [%0], %1;\n\t}" ::"r"(a), "f"(v), "r"((int)on) : "memory");
+}
+__device__ __forceinline__ void sts32i_if(unsigned a, int v, bool on) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.s32 p, %2, 0;\n\t@p st.shared.s32 [%0], %1;\n\t}" ::"r"(a), "r"(v), "r"((int)on) : "memory");
+}
+__device__ __forceinline__ void stg32_if(float* p, float v, bool on) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.s32 p, %2, 0;\n\t@p st.global.f32 [%0], %1;\n\t}" ::"l"(p), "f"(v), "r"((int)on) : "memory");
 }
 __device__ __forceinline__ void cp_async16_zfill_a(unsigned dst, const void* gmem_src, int bytes) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(gmem_src), "r"(bytes) : "memory");
@@ -1510,16 +1523,19 @@ ctc_lin_kernel(const PipeParams pp, int* __restrict__ flags) {
                     unsigned mk = 0u;
 #pragma unroll
                     for (int j = 0; j < NV; ++j) {
-                        x[j] = -CUDART_INF_F;
-                        if (j < nv) {
-                            const float raw = lds32(rin + (unsigned)(MG * 4 * j));
-                            mk |= (clq.cmask(raw) ? 1u : 0u) << j;
-                            x[j] = clq.cin(raw);
-                        }
+                        // (branch-free: every lane loads NV values -- beyond V whatever the ring holds there -- and selects)
+                        const float raw = lds32(rin + (unsigned)(MG * 4 * j));
+                        const bool on = j < nv;
+                        mk |= ((on && clq.cmask(raw)) ? 1u : 0u) << j;
+                        x[j] = on ? clq.cin(raw) : -CUDART_INF_F;
                         m = fmaxf(m, x[j]);
                     }
+                    if constexpr (MG == 32 && CTC_LIN_REDUX) {      // a warp per frame: one REDUX (five shuffle levels otherwise)
+                        asm volatile("redux.sync.max.f32 %0, %1, 0xffffffff;" : "=f"(m) : "f"(m));
+                    } else {
 #pragma unroll
-                    for (int o = MG / 2; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+                        for (int o = MG / 2; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+                    }
                     const float mb = m * kLog2e;
                     float z = 0.f;
 #pragma unroll
@@ -1533,16 +1549,12 @@ ctc_lin_kernel(const PipeParams pp, int* __restrict__ flags) {
                     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rs) : "f"(z));
                     rs = rs * (2.0f - z * rs);          // one Newton step: full fp32 accuracy (1 <= z <= V)
                     __syncwarp();      // every lane has read its raw values before the row is overwritten in place
-                    if (act) {
 #pragma unroll
-                        for (int j = 0; j < NV; ++j) {
-                            if (j < nv) {
-                                const float y = x[j] * rs;
-                                sts32(ra + (unsigned)(MG * 4 * j), (mk >> j) & 1u ? -y : y);
-                            }
-                        }
-                        if (gl < Vs - V) sts32(ra + (unsigned)V * 4u, 0.f);   // slot V (and the padding behind it): what padding pairs gather
+                    for (int j = 0; j < NV; ++j) {
+                        const float y = x[j] * rs;
+                        sts32_if(ra + (unsigned)(MG * 4 * j), (mk >> j) & 1u ? -y : y, act && j < nv);
                     }
+                    sts32_if(ra + (unsigned)V * 4u, 0.f, act && gl < Vs - V);   // slot V (and the padding behind it): what padding pairs gather
                 };
                 if (V <= 192) body(std::integral_constant<int, 192 / MG>{});
                 else body(std::integral_constant<int, 256 / MG>{});
@@ -1892,7 +1904,7 @@ ctc_lin_kernel(const PipeParams pp, int* __restrict__ flags) {
                 }
                 return;
             }
-            bs = group_sum(bs, G);
+            if (!MID) bs = group_sum(bs, G);      // (MID: reduced together with the class sum, below)
             float tot = 0.f;
             if constexpr (MID) {
                 // lane gl holds classes gl, gl + 16, ... of its frame: every load issued up front, immediate offsets
@@ -1908,26 +1920,27 @@ ctc_lin_kernel(const PipeParams pp, int* __restrict__ flags) {
                     float tsum = 0.f;
 #pragma unroll
                     for (int j = 0; j < NV; ++j) {
-                        o[j] = 0.f;
-                        y[j] = 0.f;
-                        if (j < nv) {
-                            const unsigned xq = (unsigned)lds32i(oa + (unsigned)(MG * 4 * j));
-                            y[j] = lds32(ya + (unsigned)(MG * 4 * j));
-                            if (act) sts32i(oa + (unsigned)(MG * 4 * j), 0);
-                            o[j] = __uint2float_rn(xq) * (1.0f / kQ31);
-                            tsum += o[j];
-                        }
+                        // (branch-free: unconditional loads, a predicated store, selects)
+                        const unsigned xq = (unsigned)lds32i(oa + (unsigned)(MG * 4 * j));
+                        y[j] = lds32(ya + (unsigned)(MG * 4 * j));
+                        sts32i_if(oa + (unsigned)(MG * 4 * j), 0, act && j < nv);
+                        o[j] = j < nv ? __uint2float_rn(xq) * (1.0f / kQ31) : 0.f;
+                        tsum += o[j];
                     }
+                    float bsum = bs;      // the two reductions share their shuffle levels
 #pragma unroll
-                    for (int sft = MG / 2; sft > 0; sft >>= 1) tsum += __shfl_xor_sync(0xffffffffu, tsum, sft);   // (bs is reduced already)
+                    for (int sft = MG / 2; sft > 0; sft >>= 1) {
+                        const float t2 = __shfl_xor_sync(0xffffffffu, tsum, sft), b2 = __shfl_xor_sync(0xffffffffu, bsum, sft);
+                        tsum += t2;
+                        bsum += b2;
+                    }
+                    const float bs = bsum;
+#pragma unroll
+                    for (int j = 0; j < NV; ++j) {
+                        const float ov = o[j] + (j == jb ? bs : 0.f);
+                        stg32_if(g1 + MG * j, (CLAMPED && __float_as_int(y[j]) < 0) ? 0.f : gscale * (y[j] - ov), act && j < nv);
+                    }
                     if (act) {
-#pragma unroll
-                        for (int j = 0; j < NV; ++j) {
-                            if (j < nv) {
-                                const float ov = o[j] + (j == jb ? bs : 0.f);
-                                g1[MG * j] = (CLAMPED && __float_as_int(y[j]) < 0) ? 0.f : gscale * (y[j] - ov);
-                            }
-                        }
                         if (!(fabsf(tsum + bs - 1.0f) <= kMassTol)) s_flag[0] = 1;   // NaN-safe
 #ifdef CTC_B200_MASSDEV
                         atomicMax(&s_flag[2], __float_as_int(fabsf(tsum + bs - 1.0f)));
