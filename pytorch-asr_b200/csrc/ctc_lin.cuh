@@ -1208,7 +1208,7 @@ ctc_lin_kernel(const PipeParams pp, int* __restrict__ flags) {
             // neither the first combined chunk nor the (possibly short) last one; full chunks of 4 rows, two
             // combine groups (this warp takes rows cg and cg + 2).  Every shared-memory address is an immediate
             // offset from a running 32-bit base; what only the general path needs is not live in here.
-            static_assert(!RCL || kLinPDist == 2, "the steady-state loop requests the partner rows two chunks ahead");
+            static_assert(!RCL || kLinPDist >= 2, "the steady-state loop requests the partner rows kLinPDist chunks ahead");
             const int it_fast_end = wgc ? nch_i + 1 : 0;
             if (wgc) {
                 // First half: the recursion warp publishes the pre-emission rows of chunk it - 1 in the
@@ -1250,9 +1250,9 @@ ctc_lin_kernel(const PipeParams pp, int* __restrict__ flags) {
                 const unsigned bar0 = sbase + lay.bars + 8u * (unsigned)lay.NL;       // bar_part[0]
                 for (; it < it_fast_end; ++it) {
                     LPROF_BEGIN();
-                    if (it < nch_i) {     // partner rows of chunk `it` (consumed in iteration it + 2)
+                    if (it + kLinPDist - 2 < nch_i) {     // partner rows of chunk it + kLinPDist - 2 (consumed in iteration it + kLinPDist)
                         if (iss_part && lane == 0) {
-                            const int tt0i = n_store + (it - n1_i) * 4, rowsi = min(4, Tb - tt0i);
+                            const int tt0i = n_store + (it + kLinPDist - 2 - n1_i) * 4, rowsi = min(4, Tb - tt0i);
                             const int t_lo = rev ? tbase - (tt0i + rowsi - 1) : tt0i;
                             const unsigned bytes = (unsigned)rowsi * (544u * 4u), bar = bar0 + 8u * (unsigned)iss_p.slot;
                             mbar_expect_tx_a(bar, bytes);
