@@ -106,6 +106,9 @@ constexpr float kQ31 = 2147483648.0f;   // label occupancies are accumulated as 
 #ifndef CTC_LIN_PD
 #define CTC_LIN_PD 2
 #endif
+#ifndef CTC_LIN_WIDE_FAST
+#define CTC_LIN_WIDE_FAST 1   // WIDE: branch-free softmax / gradient passes by explicit shared addresses (see softmax_chunk)
+#endif
 #ifndef CTC_LIN_REDUX
 #define CTC_LIN_REDUX 1    // MID with a warp per frame: row maximum by redux.sync.max.f32
 #endif
@@ -185,6 +188,28 @@ __device__ __forceinline__ void sts32i_if(unsigned a, int v, bool on) {
 }
 __device__ __forceinline__ void stg32_if(float* p, float v, bool on) {
     asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.s32 p, %2, 0;\n\t@p st.global.f32 [%0], %1;\n\t}" ::"l"(p), "f"(v), "r"((int)on) : "memory");
+}
+__device__ __forceinline__ uint4 lds128u(unsigned a) {
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
+    return v;
+}
+// (lanes with `on` clear keep what the registers held: initialise them)
+__device__ __forceinline__ void lds128u_if(unsigned a, uint4& v, bool on) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.s32 p, %5, 0;\n\t@p ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];\n\t}"
+                 : "+r"(v.x), "+r"(v.y), "+r"(v.z), "+r"(v.w) : "r"(a), "r"((int)on) : "memory");
+}
+__device__ __forceinline__ void sts128_if(unsigned a, float x, float y, float z, float w, bool on) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.s32 p, %5, 0;\n\t@p st.shared.v4.f32 [%0], {%1, %2, %3, %4};\n\t}"
+                 ::"r"(a), "f"(x), "f"(y), "f"(z), "f"(w), "r"((int)on) : "memory");
+}
+__device__ __forceinline__ void sts128u_if(unsigned a, unsigned x, unsigned y, unsigned z, unsigned w, bool on) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.s32 p, %5, 0;\n\t@p st.shared.v4.u32 [%0], {%1, %2, %3, %4};\n\t}"
+                 ::"r"(a), "r"(x), "r"(y), "r"(z), "r"(w), "r"((int)on) : "memory");
+}
+__device__ __forceinline__ void stg128_if(float* p, float x, float y, float z, float w, bool on) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.s32 p, %5, 0;\n\t@p st.global.v4.f32 [%0], {%1, %2, %3, %4};\n\t}"
+                 ::"l"(p), "f"(x), "f"(y), "f"(z), "f"(w), "r"((int)on) : "memory");
 }
 __device__ __forceinline__ void cp_async16_zfill_a(unsigned dst, const void* gmem_src, int bytes) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(gmem_src), "r"(bytes) : "memory");
@@ -1617,6 +1642,49 @@ ctc_lin_kernel(const PipeParams pp, int* __restrict__ flags) {
                         }
                     }
                 }
+            } else if (WIDE && CTC_LIN_WIDE_FAST && V4 <= 8 * 32) {
+                // WIDE, a warp per frame, at most 8 x 128 bit per lane (C4): as the branch below, but branch-free and by
+                // explicit 32-bit shared addresses (every lane loads 8 x 128 bit -- beyond V whatever the ring holds there --
+                // and selects; predicated stores), row maximum by ONE redux.sync.max.f32, rcp + Newton step
+                const unsigned ra = sbase + (unsigned)lay.y + (unsigned)((int)(base - s_y) + min(f, rows - 1) * Vs) * 4u + (unsigned)gl * 16u;
+                float4 x[8];
+                float m = -CUDART_INF_F;
+                unsigned mk = 0u;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const bool on = gl + j * 32 < V4;
+                    const float4 raw = lds128(ra + (unsigned)(j * 512));
+                    if (clq.on)
+                        mk |= ((clq.cmask(raw.x) ? 1u : 0u) | (clq.cmask(raw.y) ? 2u : 0u) |
+                               (clq.cmask(raw.z) ? 4u : 0u) | (clq.cmask(raw.w) ? 8u : 0u)) << (4 * j);
+                    x[j].x = on ? clq.cin(raw.x) : -CUDART_INF_F; x[j].y = on ? clq.cin(raw.y) : -CUDART_INF_F;
+                    x[j].z = on ? clq.cin(raw.z) : -CUDART_INF_F; x[j].w = on ? clq.cin(raw.w) : -CUDART_INF_F;
+                    m = fmaxf(m, fmaxf(fmaxf(x[j].x, x[j].y), fmaxf(x[j].z, x[j].w)));
+                }
+                asm volatile("redux.sync.max.f32 %0, %1, 0xffffffff;" : "=f"(m) : "f"(m));
+                const float mb = m * kLog2e;
+                float z0 = 0.f, z1 = 0.f;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    x[j].x = ex2f(fmaf(x[j].x, kLog2e, -mb));
+                    x[j].y = ex2f(fmaf(x[j].y, kLog2e, -mb));
+                    x[j].z = ex2f(fmaf(x[j].z, kLog2e, -mb));
+                    x[j].w = ex2f(fmaf(x[j].w, kLog2e, -mb));
+                    z0 += x[j].x + x[j].y;
+                    z1 += x[j].z + x[j].w;
+                }
+                const float z = group_sum(z0 + z1, 32);
+                float rs;
+                asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rs) : "f"(z));
+                rs = rs * (2.0f - z * rs);          // one Newton step: full fp32 accuracy (1 <= z <= V)
+                __syncwarp();
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const unsigned q = mk >> (4 * j);
+                    const float a = x[j].x * rs, d = x[j].y * rs, e = x[j].z * rs, h = x[j].w * rs;
+                    sts128_if(ra + (unsigned)(j * 512), q & 1u ? -a : a, q & 2u ? -d : d, q & 4u ? -e : e, q & 8u ? -h : h,
+                              act && gl + j * 32 < V4);
+                }
             } else if (YS == 0 && V4 <= 8 * G) {
                 // wide vocabulary (V = 1024 with a warp per frame): at most 8 float4 per lane, the row
                 // stays in registers and every load is issued before the first use (the looped path
@@ -1844,6 +1912,60 @@ ctc_lin_kernel(const PipeParams pp, int* __restrict__ flags) {
                         }
                     }
                     if (!(fabsf(tot + bs - 1.0f) <= kMassTol)) s_flag[0] = 1;   // NaN-safe
+                }
+                return;
+            }
+            if (WIDE && CTC_LIN_WIDE_FAST && V4 <= 8 * 32) {
+                // WIDE, a warp per frame (C4): branch-free, explicit 32-bit shared addresses, predicated stores
+                const unsigned ya = sbase + (unsigned)lay.y + (unsigned)((int)(ybase - s_y) + fr * Vs) * 4u + (unsigned)gl * 16u;
+                const unsigned oa = sbase + (unsigned)lay.occ + (unsigned)((int)(obase - s_occ) + fr * ER) * 4u + (unsigned)gl * 16u;
+                float* g4 = reinterpret_cast<float*>(g2) + 4 * gl;
+                uint4 x[8];
+                float4 y[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    // (the occupancy rows are the last big region of the CTA's shared memory: no loads beyond the row)
+                    x[j] = make_uint4(0u, 0u, 0u, 0u);
+                    lds128u_if(oa + (unsigned)(j * 512), x[j], gl + j * 32 < V4);
+                    y[j] = lds128(ya + (unsigned)(j * 512));
+                    sts128u_if(oa + (unsigned)(j * 512), 0u, 0u, 0u, 0u, act && gl + j * 32 < V4);
+                }
+                float4 o[8];
+                float t0 = 0.f, t1 = 0.f;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    o[j].x = __uint2float_rn(x[j].x) * (1.0f / kQ31);      // (0 beyond V)
+                    o[j].y = __uint2float_rn(x[j].y) * (1.0f / kQ31);
+                    o[j].z = __uint2float_rn(x[j].z) * (1.0f / kQ31);
+                    o[j].w = __uint2float_rn(x[j].w) * (1.0f / kQ31);
+                    t0 += o[j].x + o[j].y;
+                    t1 += o[j].z + o[j].w;
+                }
+                float tot = t0 + t1;
+#pragma unroll
+                for (int sft = 16; sft > 0; sft >>= 1) {
+                    const float b2 = __shfl_xor_sync(0xffffffffu, bs, sft), t2 = __shfl_xor_sync(0xffffffffu, tot, sft);
+                    bs += b2;
+                    tot += t2;
+                }
+                const int cb = blank >> 2, kb = blank & 3;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const bool mine = cb == gl + j * 32;
+                    o[j].x += (mine && kb == 0) ? bs : 0.f;
+                    o[j].y += (mine && kb == 1) ? bs : 0.f;
+                    o[j].z += (mine && kb == 2) ? bs : 0.f;
+                    o[j].w += (mine && kb == 3) ? bs : 0.f;
+                    stg128_if(g4 + j * 128, (CLAMPED && __float_as_int(y[j].x) < 0) ? 0.f : gscale * (y[j].x - o[j].x),
+                              (CLAMPED && __float_as_int(y[j].y) < 0) ? 0.f : gscale * (y[j].y - o[j].y),
+                              (CLAMPED && __float_as_int(y[j].z) < 0) ? 0.f : gscale * (y[j].z - o[j].z),
+                              (CLAMPED && __float_as_int(y[j].w) < 0) ? 0.f : gscale * (y[j].w - o[j].w), act && gl + j * 32 < V4);
+                }
+                if (act) {
+                    if (!(fabsf(tot + bs - 1.0f) <= kMassTol)) s_flag[0] = 1;   // NaN-safe
+#ifdef CTC_B200_MASSDEV
+                    atomicMax(&s_flag[2], __float_as_int(fabsf(tot + bs - 1.0f)));
+#endif
                 }
                 return;
             }
