@@ -59,7 +59,12 @@
 //   WIDE (V > 256, aligned rows; C4): two SOFT and two GRAD warps, a warp per frame, chunks of 2 frames, logits
 //        rows by ONE TMA bulk copy per row (requested by the first combine warp), rows held in registers;
 //   MID  (61 ... 256 classes, the reference's V = 177 included): four helpers, every softmax warp copies and waits
-//        for its own frames, rows that are not 16-byte aligned in HBM arrive in whole 16-byte segments;
+//        for its own frames, rows that are not 16-byte aligned in HBM arrive in whole 16-byte segments; softmax /
+//        gradient passes branch-free by explicit shared addresses;
+//   MID with launch bounds of 512 threads (launches of at most one CTA per SM: the reference's batches of 32 / 64):
+//        15 warps -- four softmax + four gradient warps (a warp per frame) and four COPY warps that request the logits
+//        rows, wait for them and publish them through the chunk barrier; the recursion / combine warps run the
+//        steady-state loops of the headline class (RCL);
 //   QUEUE (FIX only): the loop over a device-side utterance queue (persistent launch).
 //
 // Which utterance a cluster works on: (blockIdx.x / 2 + utt_rot) mod n_utt.  The host rotates the
