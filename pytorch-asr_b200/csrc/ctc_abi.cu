@@ -195,7 +195,12 @@ bool pick_lin(int T, int V, int S_max, int n_utt, Geometry* g) {
             // registers; chunks of 4 would halve the lanes per frame and fall back to the looped passes
             if (V > 256 && al && H == 4 && TC == 4 && tc_env == 0) continue;
             const int total = lin_smem_size(NP, R, V, TC, RS, YS);
-            const int need = std::max(1, std::min(4, (2 * std::max(n_utt, 1) + kNumSmsHint - 1) / kNumSmsHint));
+            // co-resident CTAs per SM a one-wave launch would need -- but never more than the register file holds (every
+            // instantiation is built for 128 registers per thread): a 224-thread CTA sits two to an SM whatever its shared
+            // memory, so asking it to fit four only pushed the 61 ... 256-class vocabularies off their instantiation (chunks
+            // of 2 frames, the general code) from 223 utterances on (V = 177, T = 750: B = 222 0.37 ms, B = 256 1.26 ms)
+            const int by_regs = std::max(1, 65536 / (NT * 128));
+            const int need = std::max(1, std::min(std::min(4, by_regs), (2 * std::max(n_utt, 1) + kNumSmsHint - 1) / kNumSmsHint));
             const int limit = pass == 0 ? std::min(kMaxSmemBytes, 227 * 1024 / need - 1024) : kMaxSmemBytes;
             if (total > limit) continue;
             g->lP = P; g->lNT = NT; g->lNP = NP; g->lchunk = TC; g->lRS = RS; g->lsmem = total;

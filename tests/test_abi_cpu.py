@@ -55,6 +55,8 @@ def test_geometry_and_workspace():
     # (a batch of 64: every CTA has an SM of its own -> eight helper warps; from 75 utterances on four, two CTAs per SM)
     assert g177["kernel"] == 2 and g177["fallback_kernel"] == 0 and g177["variant_name"] == "ctc_lin_kernel<8,1,0,512,1,MID>"
     assert g177["threads"] == 480 and g177["grad_warps"] == 8
+    for n in (256, 4096):                          # ... whatever the batch: two 224-thread CTAs per SM by their registers
+        assert cabi.geometry(750, n, 177, 100)["variant_name"] == "ctc_lin_kernel<8,1,0,256,2,MID>"
     g177b = cabi.geometry(750, 96, 177, 100)
     assert g177b["variant_name"] == "ctc_lin_kernel<8,1,0,256,2,MID>" and g177b["threads"] == 224 and g177b["grad_warps"] == 4
     assert g["variant_name"] == "ctc_lin_kernel<8,1,80,128,4,FIX>" and g["fallback_kernel"] == 1

@@ -61,6 +61,8 @@ LIN_CASES = [
     (76, 300, 177, 60, False, "ctc_lin_kernel<8,1,0,256,2,MID>"),
     (75, 200, 100, 40, False, "ctc_lin_kernel<8,1,0,256,2,MID>"),
     (75, 200, 200, 40, False, "ctc_lin_kernel<8,1,0,256,2,MID>"),
+    # (a 224-thread CTA sits two to an SM by its registers: the shared-memory budget asks for no more, whatever the batch)
+    (300, 100, 177, 20, False, "ctc_lin_kernel<8,1,0,256,2,MID>"),
     (3, 200, 1001, 30, False, "ctc_lin_kernel<8,1,0,256,2>"),             # wide rows that are not 16-byte aligned
     (3, 120, 2048, 24, False, "ctc_lin_kernel<8,1,0,256,2,WIDE>"),        # more than 8 x 128 bit per lane: the looped passes
     (3, 120, 260, 24, False, "ctc_lin_kernel<8,1,0,256,2,WIDE>"),         # just above the MID range
