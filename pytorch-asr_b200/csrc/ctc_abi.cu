@@ -162,20 +162,29 @@ bool pick_pipe(int T, int V, int pairs, int n_utt, Geometry* g) {
 // params.py:27) use the run-time-stride variants with 4-byte copies.
 bool pick_lin(int T, int V, int S_max, int n_utt, Geometry* g) {
     const int P = 8;   // one recursion warp covers 248 labels; also the fastest choice for short targets
-    const int R = (S_max + P + 32 * P - 1) / (32 * P);
+    int R = (S_max + P + 32 * P - 1) / (32 * P);
     const bool al = V % 4 == 0;
+    // three recursion warps have no instantiation with compile-time strides; the four-warp one (C3's) is faster although
+    // its lattice rows are a third wider (V = 48, S ~ 500 ... 760: 356 ns per frame and utterance with three warps and
+    // run-time strides, 279 with four; tools/gpu_cliffs.py)
+    if (R == 3 && al && V <= 60) R = 4;
     // one helper warp (softmax, then gradient rows) when one recursion warp suffices: 4 warps per CTA
     // leave 128 registers per thread, which the two-rows-in-flight combine pass needs
     // helper warps: one (softmax, then gradient rows) for the narrow vocabularies; two softmax + two gradient warps
     // for rows of more than 64 classes (one helper keeps at most 4 x 64 bit of a frame per lane in registers) and
     // for wide rows that are not 16-byte aligned (the reference's own V = 177, params.py:27: 0.82 ms with one
     // helper and the looped passes, 0.26 ms with four and the MID instantiation on B = 64, T = 750)
-    int H = R == 1 ? ((V > 64 || (!al && V > 60)) ? 4 : 1) : (V > 256 ? 4 : 2);
+    // (rows that are not 16-byte aligned take the four-helper MID passes whatever their width: the one-helper general code
+    // copies and normalises them element by element -- V = 29, characters + blank: 0.22 ms against 0.05 ms for V = 48)
+    int H = R == 1 ? ((V > 64 || !al) ? 4 : 1) : (V > 256 ? 4 : 2);
     // the MID vocabularies (60 < V <= 256) in a launch that leaves every CTA an SM of its own -- at most 74 utterances: the
     // reference trains with batches of 32 / 64 (deepspeech_ctc/train.py:75-100) at V = 177 -- get EIGHT helper warps,
     // a warp per frame of a chunk: with 7 warps on an SM the helpers' dependent chains bound every iteration
     // (B = 64, T = 750, V = 177: SOFT 2177 / GRAD 2827 busy cycles per chunk against REC 1181 / COMB 1665)
-    if (R == 1 && H == 4 && V <= 256 && 2 * std::max(n_utt, 1) <= kNumSmsHint) H = 8;
+    // ... and so does every other vocabulary of up to 256 classes but the headline one (V = 48 has steady-state loops of
+    // its own for all four roles): aligned V <= 64 runs 0.11 ... 0.13 ms there against 0.07 ms (T = 300, B <= 74)
+    const bool headline = al && V == 48 && !env().nofix;
+    if (R == 1 && V <= 256 && 2 * std::max(n_utt, 1) <= kNumSmsHint && (H == 4 || !headline)) H = 8;
     if (env().helpers == 1 || env().helpers == 2 || env().helpers == 4 || env().helpers == 8) H = env().helpers;   // developer knob
     const int NC = R <= 4 ? 2 : 1;   // two combine groups while the CTA stays within 512 threads
     const int NT = 32 * ((1 + NC) * R + H + (H == 8 ? 4 : 0));   // (eight helpers come with four copy warps: ctc_lin.cuh, MIDC)
@@ -183,7 +192,7 @@ bool pick_lin(int T, int V, int S_max, int n_utt, Geometry* g) {
     const int NP = 32 * P * R;
     const int RS = lin_row_stride_host(NP, P);
     // fixed emission-ring row stride (an immediate in the kernel): instantiated for 1, 2 and 4 recursion warps
-    const int YS = (al && V <= 60 && (R == 1 || R == 2 || R == 4)) ? 80 : 0;
+    const int YS = (al && V <= 60 && (R == 1 || R == 2 || R == 4) && !(R == 1 && H >= 4)) ? 80 : 0;
     const int tc_env = env().chunk;
     const int cand[3] = {4, 2, 1};
     for (int pass = 0; pass < 2; ++pass) {
@@ -193,7 +202,9 @@ bool pick_lin(int T, int V, int S_max, int n_utt, Geometry* g) {
             if (YS == 80 && TC != 4) continue;   // the fixed-stride variants are built for chunks of 4 frames
             // wide aligned rows: a whole warp per frame (chunks of 2 frames with two softmax warps) keeps a row in
             // registers; chunks of 4 would halve the lanes per frame and fall back to the looped passes
-            if (V > 256 && al && H == 4 && TC == 4 && tc_env == 0) continue;
+            // (nor chunks of 1: the general code is three times slower than a second wave of the WIDE instantiation --
+            // V = 2048, T = 300: 0.30 ms at B = 74, 0.97 ms at B = 75)
+            if (V > 256 && al && R == 1 && H == 4 && TC != 2 && tc_env == 0) continue;
             const int total = lin_smem_size(NP, R, V, TC, RS, YS);
             // co-resident CTAs per SM a one-wave launch would need -- but never more than the register file holds (every
             // instantiation is built for 128 registers per thread): a 224-thread CTA sits two to an SM whatever its shared

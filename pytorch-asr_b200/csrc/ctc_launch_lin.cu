@@ -71,7 +71,7 @@ int lin_variant(const Geometry& g, int V) {
         if (g.lYS != 0) return -1;
         if (g.lNT <= 128) return kLinR1;
         // eight helpers + four copy warps, 480 threads: the MID vocabularies when every CTA has an SM of its own (pick_lin)
-        if (g.lNT == 480) return (g.lH == 8 && g.lD == 2 && V > 60 && V <= 256 && g.lchunk == 4) ? kLinR1Mid8 : -1;
+        if (g.lNT == 480) return (g.lH == 8 && g.lD == 2 && V <= 256 && g.lchunk == 4) ? kLinR1Mid8 : -1;
         if (g.lNT > 256) return -1;
         // (the WIDE / MID instantiations have their CTA shape -- four helpers, 224 threads, WIDE: chunks of 2 frames --
         // as compile-time constants; any other choice of the geometry heuristics runs the general instantiation)

@@ -114,6 +114,9 @@ constexpr float kQ31 = 2147483648.0f;   // label occupancies are accumulated as 
 #ifndef CTC_LIN_WIDE_FAST
 #define CTC_LIN_WIDE_FAST 1   // WIDE: branch-free softmax / gradient passes by explicit shared addresses (see softmax_chunk)
 #endif
+#ifndef CTC_LIN_RCL_Y80
+#define CTC_LIN_RCL_Y80 1   // <8,1,80,128,4> (aligned V <= 60 other than 48): recursion / combine warps on the steady-state loops
+#endif
 #ifndef CTC_LIN_REDUX
 #define CTC_LIN_REDUX 1    // MID with a warp per frame: row maximum by redux.sync.max.f32
 #endif
@@ -380,7 +383,7 @@ ctc_lin_kernel(const PipeParams pp, int* __restrict__ flags) {
     // the steady-state loops of the recursion and combine warps (written for FIX) also serve MID8: the same CTA shape on
     // their side (one recursion warp, two combine groups, chunks of 4 frames); only the row strides of the emission ring
     // and of the occupancy rows are run-time values there (FIX: 80 and 112 floats, immediates)
-    constexpr bool RCL = FIX || MID8;
+    constexpr bool RCL = FIX || MID8 || (CTC_LIN_RCL_Y80 && RC == 1 && YS == 80 && MAXT == 128 && MINB == 4);
     const int NT = (FIX || (RC == 1 && MAXT == 128)) ? 128 : (MIDC ? 480 : (MID8 ? 352 : ((WIDE || MID) ? 224 : blockDim.x))), NW = NT >> 5;
     const int R = RC > 0 ? RC : pp.R, H = FIX ? 1 : (MID8 ? 8 : ((WIDE || MID) ? 4 : pp.H)), NP = RC > 0 ? 32 * P * RC : pp.NP;
     // loop invariants the compiler would otherwise re-derive inside the role loops at the register cap
@@ -1586,6 +1589,7 @@ ctc_lin_kernel(const PipeParams pp, int* __restrict__ flags) {
                     }
                     sts32_if(ra + (unsigned)V * 4u, 0.f, act && gl < Vs - V);   // slot V (and the padding behind it): what padding pairs gather
                 };
+                // (two buckets only: a third one for V <= 64 cost the four-helper launches 5 ... 9 % -- instruction fetch)
                 if (V <= 192) body(std::integral_constant<int, 192 / MG>{});
                 else body(std::integral_constant<int, 256 / MG>{});
                 return;
@@ -2074,6 +2078,7 @@ ctc_lin_kernel(const PipeParams pp, int* __restrict__ flags) {
 #endif
                     }
                 };
+                // (two buckets only: a third one for V <= 64 cost the four-helper launches 5 ... 9 % -- instruction fetch)
                 if (V <= 192) body(std::integral_constant<int, 192 / MG>{});
                 else body(std::integral_constant<int, 256 / MG>{});
                 return;

@@ -103,12 +103,18 @@ def test_module_backward_hook_and_input_variants():
     for b in range(4):
         pad[b, :tl[b]] = tg[o:o + tl[b]]
         o += int(tl[b])
+    # (a call without a gradient runs the log-domain kernel, `base` the probability-domain one: the same loss to fp32
+    # rounding, not bit for bit; every form of the SAME call is bit-identical)
+    fwd = CTCLoss()(acts.cuda(), tg, il, tl)
+    assert torch.allclose(fwd, base.detach(), rtol=1e-6, atol=0)
     for targets, ilv, tlv in [(tg.long(), il.long(), tl.long()),
                               (pad, il.tolist(), tl.tolist()),
                               (tg.cuda(), il.cuda(), tl.cuda()),
                               (pad.cuda(), il, tl)]:
         v = CTCLoss()(acts.cuda(), targets, ilv, tlv)
-        assert torch.equal(v, base.detach())
+        assert torch.equal(v, fwd)
+        xg = acts.cuda().requires_grad_(True)
+        assert torch.equal(CTCLoss()(xg, targets, ilv, tlv).detach(), base.detach())
 
 
 def test_argument_errors_match_torch():

@@ -45,9 +45,18 @@ def _check(prob, acts, tg, il, tl, what, grad_scale=None):
 LIN_CASES = [
     (6, 200, 48, 40, False, "ctc_lin_kernel<8,1,80,128,4,FIX>"),       # C1 / C2 / C5 shape class
     (4, 1000, 48, 200, False, "ctc_lin_kernel<8,1,80,128,4,FIX>"),     # C2 slice at full length
-    (5, 150, 32, 30, False, "ctc_lin_kernel<8,1,80,128,4>"),           # V <= 60, not 48
-    (5, 150, 60, 30, False, "ctc_lin_kernel<8,1,80,128,4>"),
-    (4, 160, 64, 30, False, "ctc_lin_kernel<8,1,0,128,4>"),            # 60 < V <= 64: one helper, a frame's row in registers
+    (76, 150, 32, 30, False, "ctc_lin_kernel<8,1,80,128,4>"),          # V <= 60, not 48, more utterances than SM pairs
+    (76, 150, 60, 30, False, "ctc_lin_kernel<8,1,80,128,4>"),
+    (75, 700, 28, 200, False, "ctc_lin_kernel<8,1,80,128,4>"),         # ... long enough for its steady-state loops
+    (76, 160, 64, 30, False, "ctc_lin_kernel<8,1,0,128,4>"),           # 60 < V <= 64: one helper, a frame's row in registers
+    # every vocabulary of up to 256 classes but the headline one, at most 74 utterances: the 15-warp MID instantiation
+    (5, 150, 32, 30, False, "ctc_lin_kernel<8,1,0,512,1,MID>"),
+    (5, 150, 60, 30, False, "ctc_lin_kernel<8,1,0,512,1,MID>"),
+    (4, 160, 64, 30, False, "ctc_lin_kernel<8,1,0,512,1,MID>"),
+    (4, 120, 29, 20, False, "ctc_lin_kernel<8,1,0,512,1,MID>"),        # characters + blank: V % 4 != 0
+    (6, 100, 5, 12, False, "ctc_lin_kernel<8,1,0,512,1,MID>"),         # a handful of classes
+    (6, 100, 3, 12, False, "ctc_lin_kernel<8,1,0,512,1,MID>"),
+    (76, 120, 29, 20, False, "ctc_lin_kernel<8,1,0,256,2,MID>"),       # rows that are not 16-byte aligned: MID whatever their width
     # 64 < V <= 256 (and 60 < V with rows that are not 16-byte aligned).  At most 74 utterances -- every CTA has an SM of
     # its own; the reference's batches of 32 / 64 (deepspeech_ctc/train.py:75-100) -- run EIGHT helper warps, a warp per frame:
     (4, 160, 128, 30, False, "ctc_lin_kernel<8,1,0,512,1,MID>"),
@@ -65,14 +74,15 @@ LIN_CASES = [
     (300, 100, 177, 20, False, "ctc_lin_kernel<8,1,0,256,2,MID>"),
     (3, 200, 1001, 30, False, "ctc_lin_kernel<8,1,0,256,2>"),             # wide rows that are not 16-byte aligned
     (3, 120, 2048, 24, False, "ctc_lin_kernel<8,1,0,256,2,WIDE>"),        # more than 8 x 128 bit per lane: the looped passes
+    (76, 80, 2048, 16, False, "ctc_lin_kernel<8,1,0,256,2,WIDE>"),        # ... one CTA per SM by its shared memory: a second wave, not chunks of 1
     (3, 120, 260, 24, False, "ctc_lin_kernel<8,1,0,256,2,WIDE>"),         # just above the MID range
-    (4, 120, 29, 20, False, "ctc_lin_kernel<8,1,0,128,4>"),            # characters + blank: V % 4 != 0, V < 60
     (8, 1000, 1024, 200, False, "ctc_lin_kernel<8,1,0,256,2,WIDE>"),        # C4 slice at full size
     (80, 120, 1024, 20, False, "ctc_lin_kernel<8,1,0,256,2,WIDE>"),         # C4's geometry: >= 75 utterances -> chunks of 2 frames
     (4, 700, 48, 300, False, "ctc_lin_kernel<8,2,80,512,1>"),          # two recursion warps
     (4, 4000, 48, 800, True, "ctc_lin_kernel<8,4,80,512,1>"),          # C3 slice: B=4 of T=4000, S=800
     (3, 700, 128, 300, False, "ctc_lin_kernel<8,0,0,256,2>"),          # run-time strides, R = 2
-    (2, 1500, 48, 600, False, "ctc_lin_kernel<8,0,0,512,1>"),          # R = 3 (no fixed-stride instantiation)
+    (2, 1500, 48, 600, False, "ctc_lin_kernel<8,4,80,512,1>"),         # three recursion warps would do: run as four (compile-time strides)
+    (2, 1500, 128, 600, False, "ctc_lin_kernel<8,0,0,512,1>"),         # R = 3, wide rows: run-time strides
     (2, 2600, 12, 1200, True, "ctc_lin_kernel<8,0,0,512,1>"),          # R = 5, one combine group
     (2, 4400, 20, 2000, True, "ctc_lin_kernel<8,0,0,1024,1>"),         # R = 8
 ]
