@@ -34,6 +34,9 @@
 //    never computed (warp granularity), stored or loaded; frames t >= T_b cost
 //    only the mandatory zero fill of their gradient rows.
 #pragma once
+#ifndef CTC_LIN_PDL_EARLY
+#define CTC_LIN_PDL_EARLY 1
+#endif
 #include <cuda_runtime.h>
 #include <math_constants.h>
 #include <stdint.h>
@@ -216,6 +219,9 @@ ctc_fused_kernel(const FusedParams p) {
     // fallback mode (vocabularies the log-domain pipe kernel cannot take, V % 4 != 0): both CTAs of the
     // cluster leave unless the linear kernel flagged the utterance
     if (p.redo != nullptr) {
+#if CTC_LIN_PDL_EARLY
+        asm volatile("griddepcontrol.launch_dependents;");
+#endif
         asm volatile("griddepcontrol.wait;" ::: "memory");
         if ((p.redo[2 * b] | p.redo[2 * b + 1]) == 0) return;
     }

@@ -117,6 +117,9 @@ constexpr float kQ31 = 2147483648.0f;   // label occupancies are accumulated as 
 #ifndef CTC_LIN_RCL_Y80
 #define CTC_LIN_RCL_Y80 1   // <8,1,80,128,4> (aligned V <= 60 other than 48): recursion / combine warps on the steady-state loops
 #endif
+#ifndef CTC_LIN_PDL_EARLY
+#define CTC_LIN_PDL_EARLY 1
+#endif
 #ifndef CTC_LIN_REDUX
 #define CTC_LIN_REDUX 1    // MID with a warp per frame: row maximum by redux.sync.max.f32
 #endif
@@ -368,6 +371,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(MAXT, MINB)
 ctc_lin_kernel(const PipeParams pp, int* __restrict__ flags) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const FusedParams& p = pp.f;
+#if CTC_LIN_PDL_EARLY
+    // The fallback pass and the loss reduction behind this kernel are launched with programmatic stream serialization:
+    // once every CTA of this grid has started, their CTAs may take whatever SM resources fall free and wait there
+    // (griddepcontrol.wait) -- the ramp of their launch disappears behind the tail of this one.
+    asm volatile("griddepcontrol.launch_dependents;");
+#endif
     // threads per CTA: a compile-time constant wherever the instantiation fixes the warp roles (what only other
     // CTA shapes need -- e.g. the two-rows-in-flight combine pass of the 4-warp CTAs -- is then compiled out)
     // (measured and rejected: the same for the several-recursion-warp instantiations -- C3 1.186 -> 1.220 ms)

@@ -23,6 +23,9 @@
 // sub-partition), so the code keeps every per-step quantity in a loop-carried register
 // (pointers advance by a stride; nothing is re-derived from kernel parameters).
 #pragma once
+#ifndef CTC_LIN_PDL_EARLY
+#define CTC_LIN_PDL_EARLY 1
+#endif
 #include "ctc_kernels.cuh"
 
 namespace ctcb200 {
@@ -149,6 +152,9 @@ ctc_pipe_kernel(const PipeParams pp) {
     const bool rev = (blockIdx.x & 1) != 0;
     // fallback mode: both CTAs of the cluster leave unless the linear kernel flagged the utterance
     // (launched with programmatic stream serialization: wait for the linear kernel's flags)
+#if CTC_LIN_PDL_EARLY
+    if (pp.redo != nullptr) asm volatile("griddepcontrol.launch_dependents;");   // (the loss reduction may queue up behind)
+#endif
     if (pp.redo != nullptr) asm volatile("griddepcontrol.wait;" ::: "memory");
     if (pp.redo != nullptr && (pp.redo[2 * b] | pp.redo[2 * b + 1]) == 0) return;
     const int T = p.T, V = p.V, blank = p.blank;
