@@ -183,7 +183,7 @@ bool pick_lin(int T, int V, int S_max, int n_utt, Geometry* g) {
     // (B = 64, T = 750, V = 177: SOFT 2177 / GRAD 2827 busy cycles per chunk against REC 1181 / COMB 1665)
     // ... and so does every other vocabulary of up to 256 classes but the headline one (V = 48 has steady-state loops of
     // its own for all four roles): aligned V <= 64 runs 0.11 ... 0.13 ms there against 0.07 ms (T = 300, B <= 74)
-    const bool headline = al && V == 48 && !env().nofix;
+    const bool headline = al && V <= 48 && !env().nofix;   // (V < 48: the same code with a run-time vocabulary, VRUN)
     if (R == 1 && V <= 256 && 2 * std::max(n_utt, 1) <= kNumSmsHint && (H == 4 || !headline)) H = 8;
     if (env().helpers == 1 || env().helpers == 2 || env().helpers == 4 || env().helpers == 8) H = env().helpers;   // developer knob
     const int NC = R <= 4 ? 2 : 1;   // two combine groups while the CTA stays within 512 threads

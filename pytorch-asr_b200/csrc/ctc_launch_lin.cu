@@ -12,7 +12,7 @@ namespace {
 
 enum LinVariant {
     kLinFix = 0,        // <8,1,80,128,4,FIX>  V = 48, S <= 248: the headline shape class (C1, C2, C5)
-    kLinR1Y80,          // <8,1,80,128,4>      V <= 60 (V % 4 == 0), S <= 248
+    kLinR1Y80,          // <8,1,80,128,4>      48 < V <= 60 (V % 4 == 0), S <= 248, more than 74 utterances
     kLinR1,             // <8,1,0,128,4>       60 < V <= 256 or V % 4 != 0 (the reference's V = 177), S <= 248
     kLinR1Wide,         // <8,1,0,256,2>       V > 256 (C4), S <= 248
     kLinR2Y80,          // <8,2,80,512,1>      V <= 60, 249 <= S <= 504
@@ -27,6 +27,7 @@ enum LinVariant {
                         // variant of its own: same code, wrapped in the loop over the utterance queue)
     kLinR1Mid8,         // <8,1,0,512,1,MID>   the MID vocabularies in launches of at most one CTA per SM (the reference's
                         // batches of 32 / 64 at V = 177): eight helper warps, a warp per frame, and four copy warps
+    kLinFixV,           // <8,1,80,128,4,FIX,VRUN>  the headline code for the narrower aligned vocabularies (V = 4 ... 44, V % 4 = 0)
     kLinCount
 };
 
@@ -35,7 +36,7 @@ const char* const kLinNames[kLinCount] = {
     "ctc_lin_kernel<8,1,0,256,2>",      "ctc_lin_kernel<8,2,80,512,1>", "ctc_lin_kernel<8,4,80,512,1>",
     "ctc_lin_kernel<8,0,0,256,2>",      "ctc_lin_kernel<8,0,0,512,1>",  "ctc_lin_kernel<8,0,0,1024,1>",
     "ctc_lin_kernel<8,1,0,256,2,MID>", "ctc_lin_kernel<8,1,0,256,2,WIDE>", "ctc_lin_kernel<8,1,80,128,4,FIX,QUEUE>",
-    "ctc_lin_kernel<8,1,0,512,1,MID>",
+    "ctc_lin_kernel<8,1,0,512,1,MID>", "ctc_lin_kernel<8,1,80,128,4,FIX,VRUN>",
 };
 
 using LinKernel = void (*)(const PipeParams, int*);
@@ -55,6 +56,7 @@ LinKernel lin_kernel(int id) {
         case kLinR1WideAl: return ctc_lin_kernel<8, 1, 0, 256, 2, false, false, false, true>;
         case kLinFixQueue: return ctc_lin_kernel<8, 1, 80, 128, 4, true, true>;
         case kLinR1Mid8: return ctc_lin_kernel<8, 1, 0, 512, 1, false, false, true>;
+        case kLinFixV: return ctc_lin_kernel<8, 1, 80, 128, 4, true, false, false, false, true>;
     }
     return nullptr;
 }
@@ -66,8 +68,10 @@ SmemMark g_marks[kLinCount];
 int lin_variant(const Geometry& g, int V) {
     if (g.lP != 8) return -1;
     if (g.lR == 1) {
-        if (g.lYS == 80 && g.lNT == 128)
-            return (g.lH == 1 && g.lD == 2 && V == 48 && !env().nofix) ? kLinFix : kLinR1Y80;
+        if (g.lYS == 80 && g.lNT == 128) {
+            if (g.lH == 1 && g.lD == 2 && !env().nofix && V % 4 == 0 && V >= 4 && V <= 48) return V == 48 ? kLinFix : kLinFixV;
+            return kLinR1Y80;
+        }
         if (g.lYS != 0) return -1;
         if (g.lNT <= 128) return kLinR1;
         // eight helpers + four copy warps, 480 threads: the MID vocabularies when every CTA has an SM of its own (pick_lin)

@@ -365,8 +365,11 @@ __device__ __forceinline__ int lin_map_utt(int c, int n, int pairs, int mode) {
 // WIDE: more than 256 classes in 16-byte aligned rows (C4): four helper warps, a warp per frame, TMA row copies;
 // everything the narrower vocabularies need is compiled out (ncu on C4: 2.3 instruction-fetch stalls per issued
 // instruction in the 175 KB kernel that carries every path).
+// VRUN (FIX only): the headline instantiation for the narrower 16-byte aligned vocabularies (V = 4 ... 44, V % 4 = 0:
+// 26 letters + space + blank, 39 phones + blank, ...): the vocabulary is a run-time value, the helper masks the classes
+// from V on (they softmax to 0) and guards its gradient stores; everything else is the headline code.
 template <int P, int RC, int YS, int MAXT, int MINB, bool FIX = false, bool QUEUE = false, bool MID = false,
-          bool WIDE = false>
+          bool WIDE = false, bool VRUN = false>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(MAXT, MINB)
 ctc_lin_kernel(const PipeParams pp, int* __restrict__ flags) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -408,7 +411,7 @@ ctc_lin_kernel(const PipeParams pp, int* __restrict__ flags) {
     int rev_pin = (int)(blockIdx.x & 1);
     asm volatile("" : "+r"(rev_pin));
     const bool rev = rev_pin != 0;
-    const int T = p.T, V = FIX ? 48 : p.V, blank = p.blank;
+    const int T = p.T, V = (FIX && !VRUN) ? 48 : p.V, blank = p.blank;
     // rows of acts / grad start on 16-byte boundaries (always, in the V <= 60 emission-ring variants);
     // otherwise (the reference's own V = 177, params.py:27) the helpers use 4-byte copies and scalar stores
     const bool al = (YS == 80 || WIDE) ? true : ((V & 3) == 0 && ((p.frame_stride | p.utt_stride) & 3) == 0);
@@ -2277,6 +2280,11 @@ ctc_lin_kernel(const PipeParams pp, int* __restrict__ flags) {
                         x[j].y = clq.cin(x[j].y);
                     }
                 }
+                if constexpr (VRUN) {              // classes from V on (whatever the ring holds there): -inf, softmax 0
+#pragma unroll
+                    for (int j = 0; j < 3; ++j)
+                        if (2 * ((lane & 7) + 8 * j) >= V) { x[j] = make_float2(-CUDART_INF_F, -CUDART_INF_F); mk &= ~(3u << (2 * j)); }
+                }
                 float m = fmaxf(fmaxf(fmaxf(x[0].x, x[0].y), fmaxf(x[1].x, x[1].y)), fmaxf(x[2].x, x[2].y));
                 float bs = 0.f, tot = 0.f;
                 float2 o[3];
@@ -2317,6 +2325,7 @@ ctc_lin_kernel(const PipeParams pp, int* __restrict__ flags) {
                         const bool mine = cb == glq + 8 * j;
                         const float ox = o[j].x + (mine ? addx : 0.f), oy = o[j].y + (mine ? addy : 0.f);
                         // (a set sign bit of y: the fused Hardtanh blocks this entry's gradient)
+                        if (!VRUN || 2 * (glq + 8 * j) < V)
                         g2[glq + 8 * j] = make_float2((CLAMPED && __float_as_int(yo[j].x) < 0) ? 0.f : gscale * (yo[j].x - ox),
                                                       (CLAMPED && __float_as_int(yo[j].y) < 0) ? 0.f : gscale * (yo[j].y - oy));
                     }

@@ -45,12 +45,18 @@ def _check(prob, acts, tg, il, tl, what, grad_scale=None):
 LIN_CASES = [
     (6, 200, 48, 40, False, "ctc_lin_kernel<8,1,80,128,4,FIX>"),       # C1 / C2 / C5 shape class
     (4, 1000, 48, 200, False, "ctc_lin_kernel<8,1,80,128,4,FIX>"),     # C2 slice at full length
-    (76, 150, 32, 30, False, "ctc_lin_kernel<8,1,80,128,4>"),          # V <= 60, not 48, more utterances than SM pairs
-    (76, 150, 60, 30, False, "ctc_lin_kernel<8,1,80,128,4>"),
-    (75, 700, 28, 200, False, "ctc_lin_kernel<8,1,80,128,4>"),         # ... long enough for its steady-state loops
+    # narrower aligned vocabularies (V = 4 ... 44): the headline code with a run-time vocabulary
+    (76, 150, 32, 30, False, "ctc_lin_kernel<8,1,80,128,4,FIX,VRUN>"),
+    (5, 150, 32, 30, False, "ctc_lin_kernel<8,1,80,128,4,FIX,VRUN>"),
+    (75, 700, 28, 200, False, "ctc_lin_kernel<8,1,80,128,4,FIX,VRUN>"),   # 26 letters + space + blank
+    (6, 400, 40, 90, False, "ctc_lin_kernel<8,1,80,128,4,FIX,VRUN>"),     # 39 phones + blank
+    (6, 100, 4, 12, False, "ctc_lin_kernel<8,1,80,128,4,FIX,VRUN>"),
+    (6, 100, 8, 12, False, "ctc_lin_kernel<8,1,80,128,4,FIX,VRUN>"),
+    (76, 150, 60, 30, False, "ctc_lin_kernel<8,1,80,128,4>"),          # 48 < V <= 60, more utterances than SM pairs
+    (75, 700, 52, 200, False, "ctc_lin_kernel<8,1,80,128,4>"),         # ... long enough for its steady-state loops
     (76, 160, 64, 30, False, "ctc_lin_kernel<8,1,0,128,4>"),           # 60 < V <= 64: one helper, a frame's row in registers
     # every vocabulary of up to 256 classes but the headline one, at most 74 utterances: the 15-warp MID instantiation
-    (5, 150, 32, 30, False, "ctc_lin_kernel<8,1,0,512,1,MID>"),
+    (5, 150, 56, 30, False, "ctc_lin_kernel<8,1,0,512,1,MID>"),
     (5, 150, 60, 30, False, "ctc_lin_kernel<8,1,0,512,1,MID>"),
     (4, 160, 64, 30, False, "ctc_lin_kernel<8,1,0,512,1,MID>"),
     (4, 120, 29, 20, False, "ctc_lin_kernel<8,1,0,512,1,MID>"),        # characters + blank: V % 4 != 0
@@ -300,6 +306,13 @@ def test_headline_instantiation_every_length(t_lo, t_hi, mode):
     and without a short last chunk, occurs), targets from empty to the longest feasible, against the fp64 oracle
     at the flat bounds; rows t >= T_b exact zeros; no utterance may need the fallback."""
     _every_length_case(48, "ctc_lin_kernel<8,1,80,128,4,FIX>", t_lo, t_hi, mode)
+
+
+@pytest.mark.parametrize("V,t_lo,t_hi,mode", [(28, 1, 64, "plain"), (40, 1, 64, "ntv+clamp"), (28, 60, 200, "ntv+clamp"),
+                                              (44, 60, 200, "plain"), (32, 3, 40, "peaky")])
+def test_narrow_vocabulary_instantiation_every_length(V, t_lo, t_hi, mode):
+    """ctc_lin_kernel<8,1,80,128,4,FIX,VRUN>: the headline code with the classes from V on masked in the helper."""
+    _every_length_case(V, "ctc_lin_kernel<8,1,80,128,4,FIX,VRUN>", t_lo, t_hi, mode)
 
 
 def _every_length_case(V, variant, t_lo, t_hi, mode):
