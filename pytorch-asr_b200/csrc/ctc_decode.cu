@@ -37,36 +37,48 @@ __global__ void ctc_argmax_kernel(const float* __restrict__ acts, int T, int N, 
     const bool al = (V & 3) == 0 && ((frame_stride | utt_stride) & 3) == 0 &&
                     (reinterpret_cast<uintptr_t>(acts) & 15) == 0;
     const long long rows = (long long)T * N;
-    for (long long r = warp0; r < rows; r += nwarps) {
-        const int t = bmajor ? (int)(r % T) : (int)(r / N);
-        const int b = bmajor ? (int)(r / T) : (int)(r % N);
-        if (t >= in_lens[b]) continue;
-        const float* row = acts + (size_t)t * (size_t)frame_stride + (size_t)b * (size_t)utt_stride;
+    // narrow rows: a group of G = 2^k lanes per row (G x 128 bit >= the row, or G floats for rows that are not 16-byte
+    // aligned), 32 / G rows per warp -- a warp per row would leave 20 of 32 lanes idle at V = 48
+    const int per_lane_units = al ? (V >> 2) : V;
+    int G = 32;
+    while (G > 1 && (G >> 1) >= per_lane_units) G >>= 1;
+    const int rpw = 32 / G, gl = lane & (G - 1), sub = lane / G;
+    for (long long r0 = warp0 * rpw; r0 < rows; r0 += nwarps * rpw) {
+        const long long r = r0 + sub;
+        bool live = r < rows;
+        int t = 0, b = 0;
+        if (live) {
+            t = bmajor ? (int)(r % T) : (int)(r / N);
+            b = bmajor ? (int)(r / T) : (int)(r % N);
+            live = t < in_lens[b];
+        }
         float v = -CUDART_INF_F;
         int idx = INT_MAX;
-        if (al) {
-            const float4* row4 = reinterpret_cast<const float4*>(row);
-            for (int c = lane; c < (V >> 2); c += 32) {
-                const float4 x = __ldg(row4 + c);
-                // ascending index inside the lane, strict '>': the first maximum is kept
-                if (x.x > v || idx == INT_MAX) { v = x.x; idx = 4 * c; }
-                if (x.y > v) { v = x.y; idx = 4 * c + 1; }
-                if (x.z > v) { v = x.z; idx = 4 * c + 2; }
-                if (x.w > v) { v = x.w; idx = 4 * c + 3; }
-            }
-        } else {
-            for (int c = lane; c < V; c += 32) {
-                const float x = __ldg(row + c);
-                if (x > v || idx == INT_MAX) { v = x; idx = c; }
+        if (live) {
+            const float* row = acts + (size_t)t * (size_t)frame_stride + (size_t)b * (size_t)utt_stride;
+            if (al) {
+                const float4* row4 = reinterpret_cast<const float4*>(row);
+                for (int c = gl; c < (V >> 2); c += G) {
+                    const float4 x = __ldg(row4 + c);
+                    // ascending index inside the lane, strict '>': the first maximum is kept
+                    if (x.x > v || idx == INT_MAX) { v = x.x; idx = 4 * c; }
+                    if (x.y > v) { v = x.y; idx = 4 * c + 1; }
+                    if (x.z > v) { v = x.z; idx = 4 * c + 2; }
+                    if (x.w > v) { v = x.w; idx = 4 * c + 3; }
+                }
+            } else {
+                for (int c = gl; c < V; c += G) {
+                    const float x = __ldg(row + c);
+                    if (x > v || idx == INT_MAX) { v = x; idx = c; }
+                }
             }
         }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
+        for (int o = G >> 1; o > 0; o >>= 1) {      // (xor partners stay inside the group: G is a power of two)
             const float vo = __shfl_xor_sync(0xffffffffu, v, o);
             const int io = __shfl_xor_sync(0xffffffffu, idx, o);
             if (io != INT_MAX && (idx == INT_MAX || vo > v || (vo == v && io < idx))) { v = vo; idx = io; }
         }
-        if (lane == 0) best[(size_t)b * T + t] = idx == INT_MAX ? 0 : idx;
+        if (live && gl == 0) best[(size_t)b * T + t] = idx == INT_MAX ? 0 : idx;
     }
 }
 
@@ -74,8 +86,8 @@ __global__ void __launch_bounds__(kDecodeThreads)
 ctc_collapse_ler_kernel(int T, const int32_t* __restrict__ in_lens, const int32_t* __restrict__ targets,
                         const int32_t* __restrict__ tgt_off, const int32_t* __restrict__ tgt_lens,
                         int blank, int32_t* __restrict__ hyp, int32_t* __restrict__ hyp_len,
-                        int32_t* __restrict__ dist, long long* __restrict__ totals) {
-    extern __shared__ int s_diag[];          // 3 x (S + 1) ints
+                        int32_t* __restrict__ dist, long long* __restrict__ totals, int stage_ints) {
+    extern __shared__ int s_diag[];          // 3 x (S + 1) ints [+ hypothesis + reference]: stage_ints in all
     __shared__ int s_warp[kDecodeThreads / 32];
     __shared__ int s_last, s_out;
     const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
@@ -122,6 +134,19 @@ ctc_collapse_ler_kernel(int T, const int32_t* __restrict__ in_lens, const int32_
     int* p2 = s_diag;                 // diagonal d - 2
     int* p1 = s_diag + (S + 1);       // diagonal d - 1
     int* cu = s_diag + 2 * (S + 1);   // diagonal d
+    // hypothesis and reference are read once per cell: staged in shared memory when they fit behind the diagonals
+    // (a global load per cell and diagonal was most of the 0.27 us a diagonal took)
+    const int32_t* hp = row;
+    const int32_t* rp = ref;
+    if (3 * (S + 1) + H + S <= stage_ints) {
+        int* s_h = s_diag + 3 * (S + 1);
+        int* s_r = s_h + H;
+        for (int i = tid; i < H; i += kDecodeThreads) s_h[i] = row[i];
+        for (int j = tid; j < S; j += kDecodeThreads) s_r[j] = ref[j];
+        hp = s_h;
+        rp = s_r;
+        __syncthreads();
+    }
     for (int d = 0; d <= H + S; ++d) {
         for (int j = tid; j <= S; j += kDecodeThreads) {
             const int i = d - j;
@@ -130,7 +155,7 @@ ctc_collapse_ler_kernel(int T, const int32_t* __restrict__ in_lens, const int32_
             if (i == 0) v = j;
             else if (j == 0) v = i;
             else {
-                const int sub = p2[j - 1] + (row[i - 1] != ref[j - 1] ? 1 : 0);
+                const int sub = p2[j - 1] + (hp[i - 1] != rp[j - 1] ? 1 : 0);
                 v = min(min(p1[j] + 1, p1[j - 1] + 1), sub);
             }
             cu[j] = v;
@@ -168,13 +193,16 @@ cudaError_t launch_decode_ler(const float* acts, int T, int N, int V, long long 
                                                                   bmajor, in_lens, hyp, totals);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return last_cuda_error_set(e);
-    // three diagonals of up to kMaxRef + 1 ints (48 KB of dynamic shared memory on top of the static part)
-    const size_t smem = 3 * (size_t)(kMaxRef + 1) * sizeof(int);
+    // three diagonals of up to kMaxRef + 1 ints (48 KB of dynamic shared memory on top of the static part), and room for
+    // the hypothesis (at most T labels) and the reference behind them where that stays within 160 KB
+    const size_t diag = 3 * (size_t)(kMaxRef + 1) * sizeof(int);
+    const size_t smem = std::min<size_t>(160 * 1024, diag + ((size_t)T + kMaxRef) * sizeof(int));
     static SmemMark mark;
     e = ensure_smem(reinterpret_cast<const void*>(ctc_collapse_ler_kernel), mark, (int)smem);
     if (e != cudaSuccess) return e;
     ctc_collapse_ler_kernel<<<dim3(N), dim3(kDecodeThreads), smem, st>>>(T, in_lens, targets, tgt_off, tgt_lens,
-                                                                        blank, hyp, hyp_len, dist, totals);
+                                                                        blank, hyp, hyp_len, dist, totals,
+                                                                        (int)(smem / sizeof(int)));
     return last_cuda_error_set(cudaGetLastError());
 }
 
