@@ -216,6 +216,8 @@ bool pick_lin(int T, int V, int S_max, int n_utt, Geometry* g) {
             if (total > limit) continue;
             g->lP = P; g->lNT = NT; g->lNP = NP; g->lchunk = TC; g->lRS = RS; g->lsmem = total;
             g->lR = R; g->lH = H; g->lD = NC; g->lYS = YS;
+            // (at most two co-resident CTAs per SM: 148 utterances on 148 SMs)
+            g->lriss = env().rec_iss >= 0 ? env().rec_iss : (std::max(n_utt, 1) <= kNumSmsHint ? 1 : 0);
             g->l_lat_utt_stride = (size_t)std::max(T, 1) * (size_t)RS;
             return lin_variant(*g, V) >= 0;
         }

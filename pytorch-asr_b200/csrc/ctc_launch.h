@@ -23,6 +23,7 @@ struct Geometry {
     size_t lat_utt_stride;  // floats
     // pipe == 2: geometry of the linear kernel (the fields above describe the fallback)
     int lP, lNT, lNP, lchunk, lRS, lsmem, lR, lH, lD, lYS;
+    int lriss;      // headline class, at most two CTAs per SM: the instantiation whose recursion warp requests the partner's rows
     size_t l_lat_utt_stride;
     size_t lattice_floats_per_utt() const {
         return pipe == 2 ? (lat_utt_stride > l_lat_utt_stride ? lat_utt_stride : l_lat_utt_stride) : lat_utt_stride;
@@ -31,7 +32,7 @@ struct Geometry {
 
 // Knobs read ONCE from the environment (developer tuning; the defaults are the product).
 struct Env {
-    int chunk, dist, rotate, utt_rot, nofix, pdl, slice_streams, persist, map_mode, helpers;
+    int chunk, dist, rotate, utt_rot, nofix, pdl, slice_streams, persist, map_mode, helpers, rec_iss;
     char kernel;   // 'g': generic, 'p': log-domain pipe, 0: default (linear)
     static int geti(const char* name, int dflt) {
         const char* e = std::getenv(name);
@@ -43,6 +44,7 @@ struct Env {
         rotate = geti("CTC_B200_ROTATE", 1);
         utt_rot = geti("CTC_B200_UTT_ROT", -1);
         map_mode = geti("CTC_B200_MAP", 0);
+        rec_iss = geti("CTC_B200_REC_ISS", -1);   // developer knob: -1 automatic, 0 / 1 force
         helpers = geti("CTC_B200_HELPERS", 0);
         nofix = geti("CTC_B200_NOFIX", 0);
         pdl = geti("CTC_B200_PDL", 1);

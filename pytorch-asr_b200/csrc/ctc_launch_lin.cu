@@ -28,6 +28,8 @@ enum LinVariant {
     kLinR1Mid8,         // <8,1,0,512,1,MID>   the MID vocabularies in launches of at most one CTA per SM (the reference's
                         // batches of 32 / 64 at V = 177): eight helper warps, a warp per frame, and four copy warps
     kLinFixV,           // <8,1,80,128,4,FIX,VRUN>  the headline code for the narrower aligned vocabularies (V = 4 ... 44, V % 4 = 0)
+    kLinFixRiss,        // <8,1,80,128,4,FIX,RISS>  the headline class in launches of at most two CTAs per SM (C1): the recursion
+                        // warp requests the partner's rows
     kLinCount
 };
 
@@ -37,6 +39,7 @@ const char* const kLinNames[kLinCount] = {
     "ctc_lin_kernel<8,0,0,256,2>",      "ctc_lin_kernel<8,0,0,512,1>",  "ctc_lin_kernel<8,0,0,1024,1>",
     "ctc_lin_kernel<8,1,0,256,2,MID>", "ctc_lin_kernel<8,1,0,256,2,WIDE>", "ctc_lin_kernel<8,1,80,128,4,FIX,QUEUE>",
     "ctc_lin_kernel<8,1,0,512,1,MID>", "ctc_lin_kernel<8,1,80,128,4,FIX,VRUN>",
+    "ctc_lin_kernel<8,1,80,128,4,FIX,RISS>",
 };
 
 using LinKernel = void (*)(const PipeParams, int*);
@@ -57,6 +60,7 @@ LinKernel lin_kernel(int id) {
         case kLinFixQueue: return ctc_lin_kernel<8, 1, 80, 128, 4, true, true>;
         case kLinR1Mid8: return ctc_lin_kernel<8, 1, 0, 512, 1, false, false, true>;
         case kLinFixV: return ctc_lin_kernel<8, 1, 80, 128, 4, true, false, false, false, true>;
+        case kLinFixRiss: return ctc_lin_kernel<8, 1, 80, 128, 4, true, false, false, false, false, true>;
     }
     return nullptr;
 }
@@ -69,7 +73,8 @@ int lin_variant(const Geometry& g, int V) {
     if (g.lP != 8) return -1;
     if (g.lR == 1) {
         if (g.lYS == 80 && g.lNT == 128) {
-            if (g.lH == 1 && g.lD == 2 && !env().nofix && V % 4 == 0 && V >= 4 && V <= 48) return V == 48 ? kLinFix : kLinFixV;
+            if (g.lH == 1 && g.lD == 2 && !env().nofix && V % 4 == 0 && V >= 4 && V <= 48)
+                return V == 48 ? (g.lriss ? kLinFixRiss : kLinFix) : kLinFixV;
             return kLinR1Y80;
         }
         if (g.lYS != 0) return -1;

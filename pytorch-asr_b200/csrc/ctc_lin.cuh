@@ -365,11 +365,16 @@ __device__ __forceinline__ int lin_map_utt(int c, int n, int pairs, int mode) {
 // WIDE: more than 256 classes in 16-byte aligned rows (C4): four helper warps, a warp per frame, TMA row copies;
 // everything the narrower vocabularies need is compiled out (ncu on C4: 2.3 instruction-fetch stalls per issued
 // instruction in the 175 KB kernel that carries every path).
+// RISS (FIX only, launches with at most two co-resident CTAs per SM): in the steady state of the second half the RECURSION
+// warp requests the partner's rows (TMA).  One lane's ~25 instructions around the request sit on the combine warps' chain
+// otherwise, and a launch that does not fill the SMs is bound by exactly that chain (B = 74: 0.124 -> 0.118 ms); with three
+// or four CTAs per SM the same move costs 4 % (C5 on one GPU 2.76 -> 2.87 ms), and as a launch PARAMETER its mere presence in
+// the two loops cost C2 2 %: hence an instantiation of its own.
 // VRUN (FIX only): the headline instantiation for the narrower 16-byte aligned vocabularies (V = 4 ... 44, V % 4 = 0:
 // 26 letters + space + blank, 39 phones + blank, ...): the vocabulary is a run-time value, the helper masks the classes
 // from V on (they softmax to 0) and guards its gradient stores; everything else is the headline code.
 template <int P, int RC, int YS, int MAXT, int MINB, bool FIX = false, bool QUEUE = false, bool MID = false,
-          bool WIDE = false, bool VRUN = false>
+          bool WIDE = false, bool VRUN = false, bool RISS = false>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(MAXT, MINB)
 ctc_lin_kernel(const PipeParams pp, int* __restrict__ flags) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -886,8 +891,23 @@ ctc_lin_kernel(const PipeParams pp, int* __restrict__ flags) {
                     __syncthreads();
                 }
                 for (; it < n_it && it <= n1; ++it) rec_iter(it);     // last chunk of the first half, phase break
+                unsigned ps = 0u;                // RISS: ring slot of chunk `it`, (it - n1) mod NS
+                if constexpr (RISS) {
+                    ps = (unsigned)(it - n1) % 3u;
+                    if (lane0) fence_proxy_async();
+                }
                 for (; it < nch; ++it) {         // chunk it - 1 in [n1, nch - 1): second half, full chunk
                     LPROF_BEGIN();
+                    if constexpr (RISS) {        // partner rows of chunk `it` (the combine warps consume them in iteration it + 2)
+                        if (it >= n1 + 3 && lane0) {
+                            const int tt0i = n_store + (it - n1) * 4, rowsi = min(4, Tb - tt0i);
+                            const int t_lo = rev ? tbase - (tt0i + rowsi - 1) : tt0i;
+                            const unsigned bytes = (unsigned)rowsi * RSB, bar = sbase + lay.bars + 8u * (unsigned)lay.NL + 8u * ps;
+                            mbar_expect_tx_a(bar, bytes);
+                            bulk_g2s_a(sbase + lay.stage + ps * (4u * RSB), lat_b + (ptrdiff_t)t_lo * 544, bytes, bar);
+                        }
+                        ps = ps == 2u ? 0u : ps + 1u;
+                    }
                     const unsigned yb0 = sbase + lay.y + (unsigned)ring_y.slot * YCH;
                     const unsigned ar = ar0 + (unsigned)a_buf * (4u * RSB);
                     float ya[P + 1], yn[P + 1];
@@ -1254,6 +1274,7 @@ ctc_lin_kernel(const PipeParams pp, int* __restrict__ flags) {
             // combine groups (this warp takes rows cg and cg + 2).  Every shared-memory address is an immediate
             // offset from a running 32-bit base; what only the general path needs is not live in here.
             static_assert(!RCL || kLinPDist >= 2, "the steady-state loop requests the partner rows kLinPDist chunks ahead");
+            static_assert(!RISS || (FIX && kLinPDist == 2), "the recursion warp's requests assume a lead of two chunks");
             const int it_fast_end = wgc ? nch_i + 1 : 0;
             if (wgc) {
                 // First half: the recursion warp publishes the pre-emission rows of chunk it - 1 in the
@@ -1296,7 +1317,7 @@ ctc_lin_kernel(const PipeParams pp, int* __restrict__ flags) {
                 for (; it < it_fast_end; ++it) {
                     LPROF_BEGIN();
                     if (it + kLinPDist - 2 < nch_i) {     // partner rows of chunk it + kLinPDist - 2 (consumed in iteration it + kLinPDist)
-                        if (iss_part && lane == 0) {
+                        if (!RISS && iss_part && lane == 0) {   // (RISS: the recursion warp requests them)
                             const int tt0i = n_store + (it + kLinPDist - 2 - n1_i) * 4, rowsi = min(4, Tb - tt0i);
                             const int t_lo = rev ? tbase - (tt0i + rowsi - 1) : tt0i;
                             const unsigned bytes = (unsigned)rowsi * (544u * 4u), bar = bar0 + 8u * (unsigned)iss_p.slot;

@@ -43,8 +43,11 @@ def _check(prob, acts, tg, il, tl, what, grad_scale=None):
 
 # (B, T, V, S, fixed lengths, expected instantiation)
 LIN_CASES = [
-    (6, 200, 48, 40, False, "ctc_lin_kernel<8,1,80,128,4,FIX>"),       # C1 / C2 / C5 shape class
-    (4, 1000, 48, 200, False, "ctc_lin_kernel<8,1,80,128,4,FIX>"),     # C2 slice at full length
+    # C1 / C2 / C5 shape class; at most 148 utterances (two CTAs per SM): the recursion warp requests the partner's rows
+    (6, 200, 48, 40, False, "ctc_lin_kernel<8,1,80,128,4,FIX,RISS>"),
+    (4, 1000, 48, 200, False, "ctc_lin_kernel<8,1,80,128,4,FIX,RISS>"),     # C2 slice at full length
+    (32, 500, 48, 100, False, "ctc_lin_kernel<8,1,80,128,4,FIX,RISS>"),     # C1
+    (150, 300, 48, 60, False, "ctc_lin_kernel<8,1,80,128,4,FIX>"),
     # narrower aligned vocabularies (V = 4 ... 44): the headline code with a run-time vocabulary
     (76, 150, 32, 30, False, "ctc_lin_kernel<8,1,80,128,4,FIX,VRUN>"),
     (5, 150, 32, 30, False, "ctc_lin_kernel<8,1,80,128,4,FIX,VRUN>"),
@@ -298,14 +301,18 @@ def test_mid_and_wide_instantiations_every_length(V, variant, t_lo, t_hi, mode):
 
 
 @pytest.mark.parametrize("t_lo,t_hi,mode", [(1, 64, "plain"), (1, 64, "ntv+clamp"), (60, 200, "plain"),
-                                            (60, 200, "ntv+clamp"), (3, 40, "peaky")])
+                                            (60, 200, "ntv+clamp"), (3, 40, "peaky"), (1, 160, "plain"),
+                                            (1, 160, "ntv+clamp"), (40, 200, "plain"), (3, 170, "peaky")])
 def test_headline_instantiation_every_length(t_lo, t_hi, mode):
-    """ctc_lin_kernel<8,1,80,128,4,FIX> runs its full chunks in steady-state loops of their own and everything
+    """(Up to 148 utterances run <8,1,80,128,4,FIX,RISS> -- the same code with the partner-row requests issued by the
+    recursion warp --, more the headline instantiation itself: both are covered, each with short and long utterances.)
+    ctc_lin_kernel<8,1,80,128,4,FIX> runs its full chunks in steady-state loops of their own and everything
     else (short chunks, the phase break, the drain, T_b of a few frames) through the general iteration: one
     utterance of EVERY length T_b in [t_lo, t_hi] (so that every count of first-half and second-half chunks, with
     and without a short last chunk, occurs), targets from empty to the longest feasible, against the fp64 oracle
     at the flat bounds; rows t >= T_b exact zeros; no utterance may need the fallback."""
-    _every_length_case(48, "ctc_lin_kernel<8,1,80,128,4,FIX>", t_lo, t_hi, mode)
+    variant = "ctc_lin_kernel<8,1,80,128,4,FIX,RISS>" if t_hi - t_lo + 1 <= 148 else "ctc_lin_kernel<8,1,80,128,4,FIX>"
+    _every_length_case(48, variant, t_lo, t_hi, mode)
 
 
 @pytest.mark.parametrize("V,t_lo,t_hi,mode", [(28, 1, 64, "plain"), (40, 1, 64, "ntv+clamp"), (28, 60, 200, "ntv+clamp"),
