@@ -12,8 +12,13 @@
 //                            loads when rows are 16-byte aligned), 4 bytes out per row.  Algorithmic bytes:
 //                            4 * V * sum_b T_b read + 4 * sum_b T_b written.
 //   ctc_collapse_ler_kernel  one CTA per utterance: in-place stream compaction of the arg-max row
-//                            (ballot / popc scan), then the Levenshtein distance by anti-diagonals
-//                            (one CTA barrier per diagonal, three diagonals of S+1 ints in shared memory).
+//                            (ballot / popc scan), then the Levenshtein distance.  References of up to 1024 labels
+//                            whose match masks (V x ceil(S / 32) words) fit the shared-memory budget: Myers' bit-vector
+//                            algorithm (J. ACM 46(3), 1999; the block form with horizontal carries), one 32-bit block
+//                            of the reference per lane of ONE warp, the blocks of a hypothesis label processed
+//                            systolically (lane k works on label t - k in step t and takes the carry lane k - 1
+//                            produced one step earlier): H + S / 32 steps of ~25 integer instructions, no barrier.
+//                            Otherwise: anti-diagonals (one CTA barrier per diagonal, three diagonals of S+1 ints).
 #include "ctc_launch.h"
 
 #include <climits>
@@ -86,8 +91,8 @@ __global__ void __launch_bounds__(kDecodeThreads)
 ctc_collapse_ler_kernel(int T, const int32_t* __restrict__ in_lens, const int32_t* __restrict__ targets,
                         const int32_t* __restrict__ tgt_off, const int32_t* __restrict__ tgt_lens,
                         int blank, int32_t* __restrict__ hyp, int32_t* __restrict__ hyp_len,
-                        int32_t* __restrict__ dist, long long* __restrict__ totals, int stage_ints) {
-    extern __shared__ int s_diag[];          // 3 x (S + 1) ints [+ hypothesis + reference]: stage_ints in all
+                        int32_t* __restrict__ dist, long long* __restrict__ totals, int stage_ints, int V) {
+    extern __shared__ __align__(16) int s_diag[];   // 3 x (S + 1) ints [+ hypothesis + reference]: stage_ints in all
     __shared__ int s_warp[kDecodeThreads / 32];
     __shared__ int s_last, s_out;
     const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
@@ -131,6 +136,67 @@ ctc_collapse_ler_kernel(int T, const int32_t* __restrict__ in_lens, const int32_
         return;
     }
     const int32_t* ref = targets + tgt_off[b];
+    // ---- Myers' bit-vector algorithm: block k (reference labels 32 k ... 32 k + 31) lives in lane k of warp 0 ----------
+    const int W = (S + 31) >> 5;
+    if (S >= 1 && W <= 32 && (long long)V * W + H <= (long long)stage_ints) {
+        unsigned* peq = reinterpret_cast<unsigned*>(s_diag);       // [V][W]: bit j of peq[c][k] = (ref[32 k + j] == c)
+        int* s_h = s_diag + V * W;                                 // the hypothesis
+        for (int i = tid; i < V * W; i += kDecodeThreads) peq[i] = 0u;
+        for (int i = tid; i < H; i += kDecodeThreads) s_h[i] = row[i];
+        __syncthreads();
+        for (int j = tid; j < S; j += kDecodeThreads) {
+            const int c = ref[j];
+            if (c >= 0 && c < V) atomicOr(&peq[c * W + (j >> 5)], 1u << (j & 31));   // (a label outside [0, V) matches nothing)
+        }
+        __syncthreads();
+        if (w != 0) return;
+        const int k = lane;                        // my block
+        const bool mine = k < W;
+        const unsigned top = k == W - 1 ? 1u << ((S - 1) & 31) : 0x80000000u;
+        unsigned Pv = 0xffffffffu, Mv = 0u;
+        int score = S, hout = 0;
+        // branch-free steps (selects only: the lanes are at different labels, and at the ends of the sweep some have
+        // none); the match mask of the NEXT step's label is loaded one step ahead, off the carry chain
+        const int kk = mine ? k : 0;
+        auto mask_of = [&](int i) -> unsigned {
+            const int ic = min(max(i, 0), max(H - 1, 0));
+            const int c = H > 0 ? s_h[ic] : -1;
+            return (c >= 0 && c < V) ? peq[c * W + kk] : 0u;
+        };
+        unsigned Eq_next = mask_of(-k);
+        for (int t = 0; t < (H > 0 ? H + W - 1 : 0); ++t) {
+            // the horizontal carry of hypothesis label t - k: what lane k - 1 produced for it one step ago; the first
+            // block takes +1 (D[i][0] = i)
+            int hin = __shfl_up_sync(0xffffffffu, hout, 1);
+            if (k == 0) hin = 1;
+            const bool active = mine && (unsigned)(t - k) < (unsigned)H;
+            unsigned Eq = Eq_next;
+            Eq_next = mask_of(t + 1 - k);
+            const unsigned neg = hin < 0 ? 1u : 0u, pos = hin > 0 ? 1u : 0u;
+            const unsigned Xv = Eq | Mv;
+            Eq |= neg;
+            const unsigned Xh = (((Eq & Pv) + Pv) ^ Pv) | Eq;
+            unsigned Ph = Mv | ~(Xh | Pv);
+            unsigned Mh = Pv & Xh;
+            const int h = (Ph & top) ? 1 : ((Mh & top) ? -1 : 0);
+            Ph = (Ph << 1) | pos;
+            Mh = (Mh << 1) | neg;
+            const unsigned Pn = Mh | ~(Xv | Ph), Mn = Ph & Xv;
+            Pv = active ? Pn : Pv;
+            Mv = active ? Mn : Mv;
+            hout = active ? h : 0;
+            score += (k == W - 1) ? hout : 0;
+        }
+        const int dval = __shfl_sync(0xffffffffu, score, W - 1);
+        if (lane == 0) {
+            dist[b] = dval;
+            if (totals != nullptr) {
+                atomicAdd(reinterpret_cast<unsigned long long*>(totals), (unsigned long long)dval);
+                atomicAdd(reinterpret_cast<unsigned long long*>(totals) + 1, (unsigned long long)S);
+            }
+        }
+        return;
+    }
     int* p2 = s_diag;                 // diagonal d - 2
     int* p1 = s_diag + (S + 1);       // diagonal d - 1
     int* cu = s_diag + 2 * (S + 1);   // diagonal d
@@ -202,7 +268,7 @@ cudaError_t launch_decode_ler(const float* acts, int T, int N, int V, long long 
     if (e != cudaSuccess) return e;
     ctc_collapse_ler_kernel<<<dim3(N), dim3(kDecodeThreads), smem, st>>>(T, in_lens, targets, tgt_off, tgt_lens,
                                                                         blank, hyp, hyp_len, dist, totals,
-                                                                        (int)(smem / sizeof(int)));
+                                                                        (int)(smem / sizeof(int)), V);
     return last_cuda_error_set(cudaGetLastError());
 }
 

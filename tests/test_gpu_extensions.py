@@ -202,6 +202,40 @@ def test_greedy_decode_and_ler(B, T, V, S, batch_major):
     assert sum(want) > 0 and sum(want) < int(tl.sum())        # a non-trivial error rate
 
 
+@pytest.mark.parametrize("V,T", [(12, 700), (177, 300), (1024, 1000)])
+def test_edit_distance_block_boundaries(V, T):
+    """The bit-vector edit distance keeps 32 reference labels per lane of one warp: reference lengths around every
+    block boundary, a single label, more than 1024 labels and match masks beyond the shared-memory budget (both on the
+    anti-diagonal path), hypotheses shorter and much longer than the reference -- bit-exact against the Python loops."""
+    g = torch.Generator().manual_seed(700 + V)
+    lens = [1, 2, 31, 32, 33, 63, 64, 65, 100, 255, 256, 257, 600, 900, 1024, 1025, 1500]
+    B = len(lens)
+    acts = torch.randn(B, T, V, generator=g)
+    acts[:, :, 0] += 1.0                                   # some blanks
+    il = torch.randint(max(1, T // 3), T + 1, (B,), generator=g, dtype=torch.int32)
+    il[0] = T; il[1] = 1; il[2] = 0
+    tl = torch.tensor(lens, dtype=torch.int32)
+    # references: half of them a noisy copy of the hypothesis (small distances), the others random
+    hyps = _py_decode(acts, il)
+    refs = []
+    for b in range(B):
+        Sb = lens[b]
+        if b % 2 == 0 and len(hyps[b]) > 0:
+            r = [hyps[b][i % len(hyps[b])] for i in range(Sb)]
+            for i in range(0, Sb, 9):
+                r[i] = int(torch.randint(1, V, (1,), generator=g))
+        else:
+            r = torch.randint(1, V, (Sb,), generator=g).tolist()
+        refs.append(r)
+    tg = torch.tensor([c for r in refs for c in r], dtype=torch.int32)
+    out = decode.greedy_decode_ler(acts.cuda(), il, tg, tl, blank=0, batch_major=True)
+    torch.cuda.synchronize()
+    want = [_py_edit_distance(r, h) for r, h in zip(refs, hyps)]
+    assert out["hyp_len"].cpu().tolist() == [len(h) for h in hyps]
+    assert out["dist"].cpu().tolist() == want
+    assert out["totals"].cpu().tolist() == [sum(want), sum(lens)]
+
+
 def test_decode_edge_cases():
     """T_b = 0, all-blank rows, ties (lowest index wins), empty references, hypotheses longer than a tile."""
     T, V = 600, 8
