@@ -92,7 +92,8 @@ typedef struct ctc_b200_geometry {
                                   per-utterance fallback pass, 1: log-domain warp-specialised kernel
                                   (ctc_pipe_kernel), 0: generic log-domain kernel (ctc_fused_kernel) */
     int rec_warps;             /* warps per CTA running the lattice recursion */
-    int grad_warps;            /* helper warps per CTA: TMA producer, softmax, gradient rows (0: generic kernel) */
+    int grad_warps;            /* helper warps per CTA: softmax, gradient rows (0: generic kernel); the 15-warp instantiation
+                                  for launches of one CTA per SM reports 8 and runs four copy warps besides (threads = 480) */
     int pairs_per_thread;      /* lattice (blank,label) cell pairs per thread */
     int threads;               /* threads per CTA */
     int chunk;                 /* frames per softmax/gradient chunk */
