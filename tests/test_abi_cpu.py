@@ -100,3 +100,31 @@ def test_module_fails_loudly_without_cuda():
              torch.tensor([1, 1], dtype=torch.int32))
     with pytest.raises(ValueError):
         CTCLoss(reduction="bogus")
+
+
+def test_geometry_routing_over_the_shape_grid():
+    """Every shape class keeps its instantiation whatever the batch size (the cliffs found by
+    tools/gpu_cliffs.py were geometry heuristics pushing a class onto the general code)."""
+    from pytorch_asr_b200 import cabi
+    for B in (1, 32, 74, 75, 148, 149, 222, 223, 256, 512, 4096):
+        small, two = B <= 74, B <= 148
+        for V in (4, 28, 40, 44):
+            assert cabi.geometry(300, B, V, 60)["variant_name"] == "ctc_lin_kernel<8,1,80,128,4,FIX,VRUN>", (B, V)
+        want48 = "ctc_lin_kernel<8,1,80,128,4,FIX,RISS>" if two else "ctc_lin_kernel<8,1,80,128,4,FIX>"
+        assert cabi.geometry(300, B, 48, 60)["variant_name"] == want48, B
+        for V in (52, 60):
+            want = "ctc_lin_kernel<8,1,0,512,1,MID>" if small else "ctc_lin_kernel<8,1,80,128,4>"
+            assert cabi.geometry(300, B, V, 60)["variant_name"] == want, (B, V)
+        want64 = "ctc_lin_kernel<8,1,0,512,1,MID>" if small else "ctc_lin_kernel<8,1,0,128,4>"
+        assert cabi.geometry(300, B, 64, 60)["variant_name"] == want64, B
+        for V in (3, 29, 62, 100, 128, 177, 255, 256):      # rows that are not 16-byte aligned, and 64 < V <= 256
+            g = cabi.geometry(300, B, V, 60)
+            want = "ctc_lin_kernel<8,1,0,512,1,MID>" if small else "ctc_lin_kernel<8,1,0,256,2,MID>"
+            assert g["variant_name"] == want and g["chunk"] == 4, (B, V, g)
+        for V in (260, 512, 1024, 2048):
+            g = cabi.geometry(300, B, V, 60)
+            assert g["variant_name"] == "ctc_lin_kernel<8,1,0,256,2,WIDE>" and g["chunk"] == 2, (B, V, g)
+        # longer targets: two / four recursion warps with compile-time strides for V <= 60 (three run as four)
+        assert cabi.geometry(900, B, 48, 300)["variant_name"] == "ctc_lin_kernel<8,2,80,512,1>", B
+        for S in (600, 800, 1000):
+            assert cabi.geometry(2 * S + 200, B, 48, S)["variant_name"] == "ctc_lin_kernel<8,4,80,512,1>", (B, S)
